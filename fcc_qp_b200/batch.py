@@ -1,0 +1,254 @@
+"""Batched solver: B independent WBC QPs of identical dimensions per launch.
+
+``FCCQPBatch`` mirrors the reference's ``FCCQP`` object (``src/fcc_qp.hpp:54-171``,
+bound in ``src/main.cpp:42-54``) -- same constructor arguments, same
+``set_options / set_rho / set_max_iter / set_warm_start / Solve / GetSolution``
+method names and argument meaning -- but every problem argument carries a
+leading batch dimension, and the carried warm-start state ``(x, mu_x,
+mu_lambda_c)`` is a set of ``[B, .]`` arrays owned by the object.
+
+Inputs are either numpy arrays (host memory; the C ABI stages them through the
+GPU) or torch CUDA tensors / anything exposing ``__cuda_array_interface__`` via
+``torch.as_tensor`` (device memory; zero-copy, asynchronous on the current torch
+stream).  There is no CPU solve path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Any, Optional
+
+import numpy as np
+
+from . import _native as nat
+
+
+@dataclasses.dataclass
+class FCCQPOptionsB:
+    """FCCQPOptions (``src/fcc_qp.hpp:30-35``) -- same fields and defaults."""
+    max_iter: int = 1000
+    rho: float = 1e-6
+    eps_fcone: float = 1e-3
+    eps_bound: float = 1e-6
+
+
+@dataclasses.dataclass
+class BatchDetails:
+    """FCCQPDetails (``src/fcc_qp.hpp:19-28``) as struct-of-arrays, python names of ``src/main.cpp:22-29``."""
+    n_iter: Any
+    eps_bounds: Any
+    eps_friction_cone: Any
+    bounds_viol: Any
+    friction_cone_viol: Any
+    solve_status: Any
+    solve_time: float = 0.0          # host wall seconds of the whole batched call
+    device_time: float = 0.0         # CUDA-event seconds of the solve kernel (device inputs) or staged call
+
+
+@dataclasses.dataclass
+class BatchSolution:
+    """FCCQPSolution (``src/fcc_qp.hpp:37-40``): ``z`` is ``[B, n]``."""
+    details: BatchDetails
+    z: Any
+
+
+def _is_torch(a) -> bool:
+    return type(a).__module__.split(".")[0] == "torch"
+
+
+class FCCQPBatch:
+    def __init__(self, num_vars: int, num_equality_constraints: int, nc: int, lambda_c_start: int,
+                 device: int = 0):
+        if nc % 3 != 0:
+            raise ValueError("nc must be a multiple of 3 (src/fcc_qp.cpp:32)")
+        if lambda_c_start < 0 or lambda_c_start + nc > num_vars:
+            raise ValueError("lambda_c_start + nc must be <= num_vars (src/fcc_qp.cpp:33)")
+        self.n, self.m, self.nc, self.lcs = int(num_vars), int(num_equality_constraints), int(nc), int(lambda_c_start)
+        self.device = int(device)
+        self.options = FCCQPOptionsB()
+        self.warm_start = False
+        self.time_kernel = True
+        self._state = None     # (x, mu_x, mu_c) arrays / tensors
+        self._sol: Optional[BatchSolution] = None
+        nat.lib()              # fail loudly if the CUDA library is not built
+
+    # --- same setters as the reference object (src/fcc_qp.hpp:75-91)
+    def set_rho(self, rho: float):
+        if not rho > 0:
+            raise ValueError("rho must be > 0")
+        self.options.rho = float(rho)
+
+    def set_max_iter(self, n: int):
+        if not n > 0:
+            raise ValueError("max_iter must be > 0")
+        self.options.max_iter = int(n)
+
+    def set_options(self, opt):
+        self.options = FCCQPOptionsB(int(opt.max_iter), float(opt.rho), float(opt.eps_fcone), float(opt.eps_bound))
+
+    def set_warm_start(self, warm_start: bool):
+        self.warm_start = bool(warm_start)
+
+    def contact_vars_start(self) -> int:
+        return self.lcs
+
+    # --- state in / out (the reference keeps it private, src/fcc_qp.hpp:147-153)
+    def GetState(self):
+        return self._state
+
+    def SetState(self, x, mu_x, mu_lambda_c):
+        self._state = (x, mu_x, mu_lambda_c)
+
+    def ResetState(self):
+        self._state = None
+
+    # ------------------------------------------------------------------
+    def Solve(self, Q, b, A_eq, b_eq, friction_coeffs, lb, ub):
+        """Batched ``FCCQP::Solve`` (``src/fcc_qp.cpp:114-191``).
+
+        Q ``[B,n,n]``, b ``[B,n]``, A_eq ``[B,m,n]``, b_eq ``[B,m]``; friction_coeffs
+        ``[B,nc/3]`` or ``[nc/3]``; lb/ub ``[B,n]`` or ``[n]`` (shared by all QPs).
+        """
+        if _is_torch(Q):
+            self._solve_torch(Q, b, A_eq, b_eq, friction_coeffs, lb, ub)
+        else:
+            self._solve_numpy(Q, b, A_eq, b_eq, friction_coeffs, lb, ub)
+
+    def GetSolution(self) -> BatchSolution:
+        if self._sol is None:
+            raise RuntimeError("GetSolution() before Solve()")
+        return self._sol
+
+    # ------------------------------------------------------------------
+    def _desc(self, B: int, mem: int) -> nat.BatchDesc:
+        d = nat.BatchDesc()
+        d.abi_version = nat.ABI_VERSION
+        d.batch, d.n, d.m, d.nc, d.lambda_c_start = B, self.n, self.m, self.nc, self.lcs
+        d.device, d.memory_space, d.precision = self.device, mem, 0
+        o = self.options
+        d.options = nat.Options(int(o.max_iter), 0, float(o.rho), float(o.eps_fcone), float(o.eps_bound))
+        return d
+
+    def _check_shapes(self, shp, B):
+        n, m, nc = self.n, self.m, self.nc
+        Q, b, A, beq, mu, lb, ub = shp
+        if tuple(Q) != (B, n, n) or tuple(b) != (B, n) or tuple(A) != (B, m, n) or tuple(beq) != (B, m):
+            raise ValueError(f"expected Q[{B},{n},{n}], b[{B},{n}], A_eq[{B},{m},{n}], b_eq[{B},{m}]; got "
+                             f"{tuple(Q)}, {tuple(b)}, {tuple(A)}, {tuple(beq)}")
+        if tuple(mu) not in ((B, nc // 3), (nc // 3,)):
+            if len(mu) and mu[-1] < nc // 3:
+                raise IndexError(f"friction_coeffs has {mu[-1]} entries per QP, need {nc // 3} "
+                                 "(reference: std::out_of_range, src/constraint_utils.cpp:32)")
+            raise ValueError(f"friction_coeffs must be [{B},{nc // 3}] or [{nc // 3}], got {tuple(mu)}")
+        for name, s in (("lb", lb), ("ub", ub)):
+            if tuple(s) not in ((B, n), (n,)):
+                raise ValueError(f"{name} must be [{B},{n}] or [{n}], got {tuple(s)}")
+
+    def _solve_numpy(self, Q, b, A_eq, b_eq, mu, lb, ub):
+        import time
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        Q, b, A_eq, b_eq, mu, lb, ub = map(f, (Q, b, A_eq, b_eq, mu, lb, ub))
+        if Q.ndim != 3:
+            raise ValueError("Q must be [B,n,n]")
+        B = Q.shape[0]
+        A_eq = A_eq.reshape(B, self.m, self.n) if A_eq.size == B * self.m * self.n else A_eq
+        self._check_shapes([a.shape for a in (Q, b, A_eq, b_eq, mu, lb, ub)], B)
+        n, m, nc = self.n, self.m, self.nc
+        warm = self.warm_start
+        st = self._state
+        if warm and st is not None and not _is_torch(st[0]) and st[0].shape == (B, n):
+            x, mux, muc = (np.ascontiguousarray(a, dtype=np.float64).copy() for a in st)
+        else:
+            # a never-solved reference object warm-starts from the zero state (src/fcc_qp.cpp:48-52)
+            x, mux, muc = np.zeros((B, n)), np.zeros((B, n)), np.zeros((B, max(nc, 1)))[:, :nc].copy()
+        n_iter = np.zeros(B, np.int32); status = np.zeros(B, np.int32)
+        res = np.zeros((4, B))
+        d = self._desc(B, nat.MEM_HOST)
+        d.warm_start = int(warm)
+        p = lambda a: a.ctypes.data
+        d.Q, d.q_batch_stride, d.q_row_stride, d.q_col_stride = p(Q), n * n, n, 1
+        d.b, d.b_batch_stride = p(b), n
+        d.A_eq, d.a_batch_stride, d.a_row_stride, d.a_col_stride = p(A_eq), m * n, n, 1
+        d.b_eq, d.beq_batch_stride = p(b_eq), m
+        d.friction_coeffs, d.mu_batch_stride = p(mu), (nc // 3 if mu.ndim == 2 else 0)
+        d.lb, d.lb_batch_stride = p(lb), (n if lb.ndim == 2 else 0)
+        d.ub, d.ub_batch_stride = p(ub), (n if ub.ndim == 2 else 0)
+        d.x, d.mu_x, d.mu_lambda_c = p(x), p(mux), p(muc)
+        d.n_iter, d.status = p(n_iter), p(status)
+        d.res_bounds, d.res_fcone, d.bounds_viol, d.fcone_viol = (p(res[i]) for i in range(4))
+        secs = C.c_double(0.0)
+        d.device_seconds = C.pointer(secs)
+        t0 = time.perf_counter()
+        nat.check(nat.lib().fccqp_batch_solve(C.byref(d)))
+        wall = time.perf_counter() - t0
+        self._state = (x, mux, muc)
+        self._sol = BatchSolution(BatchDetails(n_iter, res[0], res[1], res[2], res[3], status, wall, secs.value),
+                                  x.copy())
+
+    def _solve_torch(self, Q, b, A_eq, b_eq, mu, lb, ub):
+        import time
+        import torch
+        dev = Q.device
+        if dev.type != "cuda":
+            raise ValueError("torch inputs must be CUDA tensors (no CPU solve path); pass numpy arrays for host data")
+        self.device = dev.index if dev.index is not None else torch.cuda.current_device()
+        t = lambda a: a if (_is_torch(a) and a.dtype == torch.float64 and a.device == dev) else \
+            torch.as_tensor(a, dtype=torch.float64, device=dev)
+        Q, b, A_eq, b_eq, mu, lb, ub = map(t, (Q, b, A_eq, b_eq, mu, lb, ub))
+        B = Q.shape[0]
+        self._check_shapes([a.shape for a in (Q, b, A_eq, b_eq, mu, lb, ub)], B)
+        n, m, nc = self.n, self.m, self.nc
+        # vectors must be unit-stride in their last dimension
+        cont = lambda a: a if a.stride(-1) == 1 or a.shape[-1] <= 1 else a.contiguous()
+        b, b_eq, mu, lb, ub = map(cont, (b, b_eq, mu, lb, ub))
+        warm = self.warm_start
+        st = self._state
+        if warm and st is not None and _is_torch(st[0]) and tuple(st[0].shape) == (B, n) and st[0].device == dev:
+            x, mux, muc = (a.contiguous() for a in st)
+        else:
+            x = torch.zeros((B, n), dtype=torch.float64, device=dev)
+            mux = torch.zeros((B, n), dtype=torch.float64, device=dev)
+            muc = torch.zeros((B, nc), dtype=torch.float64, device=dev)
+        n_iter = torch.empty(B, dtype=torch.int32, device=dev)
+        status = torch.empty(B, dtype=torch.int32, device=dev)
+        res = torch.empty((4, B), dtype=torch.float64, device=dev)
+        d = self._desc(B, nat.MEM_DEVICE)
+        d.warm_start = int(warm)
+        bs = lambda a, full_ndim: int(a.stride(0)) if a.dim() == full_ndim and B > 1 else (
+            int(a.stride(0)) if a.dim() == full_ndim else 0)
+        d.Q, d.q_batch_stride, d.q_row_stride, d.q_col_stride = Q.data_ptr(), bs(Q, 3), int(Q.stride(1)), int(Q.stride(2))
+        d.b, d.b_batch_stride = b.data_ptr(), bs(b, 2)
+        d.A_eq, d.a_batch_stride = A_eq.data_ptr(), bs(A_eq, 3)
+        d.a_row_stride, d.a_col_stride = (int(A_eq.stride(1)), int(A_eq.stride(2))) if m > 0 else (n, 1)
+        d.b_eq, d.beq_batch_stride = b_eq.data_ptr(), bs(b_eq, 2)
+        d.friction_coeffs, d.mu_batch_stride = mu.data_ptr(), bs(mu, 2)
+        d.lb, d.lb_batch_stride = lb.data_ptr(), bs(lb, 2)
+        d.ub, d.ub_batch_stride = ub.data_ptr(), bs(ub, 2)
+        d.x, d.mu_x, d.mu_lambda_c = x.data_ptr(), mux.data_ptr(), muc.data_ptr()
+        d.n_iter, d.status = n_iter.data_ptr(), status.data_ptr()
+        d.res_bounds, d.res_fcone, d.bounds_viol, d.fcone_viol = (res[i].data_ptr() for i in range(4))
+        d.stream = torch.cuda.current_stream(dev).cuda_stream
+        secs = C.c_double(0.0)
+        if self.time_kernel:
+            d.device_seconds = C.pointer(secs)
+        t0 = time.perf_counter()
+        with torch.cuda.device(dev):
+            nat.check(nat.lib().fccqp_batch_solve(C.byref(d)))
+        wall = time.perf_counter() - t0
+        # keep the inputs alive until the (possibly asynchronous) launch has consumed them
+        self._keepalive = (Q, b, A_eq, b_eq, mu, lb, ub)
+        self._state = (x, mux, muc)
+        self._sol = BatchSolution(BatchDetails(n_iter, res[0], res[1], res[2], res[3], status, wall, secs.value),
+                                  x.clone())
+
+
+def solve_batch(Q, b, A_eq, b_eq, friction_coeffs, lb, ub, nc: int, lambda_c_start: int,
+                options=None, device: int = 0) -> BatchSolution:
+    """One-shot cold batched solve; dimensions are taken from the array shapes."""
+    B, n, _ = Q.shape
+    m = A_eq.shape[1]
+    s = FCCQPBatch(n, m, nc, lambda_c_start, device=device)
+    if options is not None:
+        s.set_options(options)
+    s.Solve(Q, b, A_eq, b_eq, friction_coeffs, lb, ub)
+    return s.GetSolution()

@@ -1,0 +1,649 @@
+// fccqp_capi.cu -- host side of libfccqp_b200.so: the C ABI declared in
+// include/fccqp.h over the sm_100a kernels in fccqp_kernel.cuh.
+//
+// No CPU fallback: every entry point that computes needs a CUDA device and
+// returns FCCQP_E_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/fccqp.h"
+#include "fccqp_kernel.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+struct LaunchInfo { int grid = 0, block = 0, smem = 0, ctas_per_sm = 0; };
+LaunchInfo g_last_launch;
+std::mutex g_info_mu;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess)                                                                  \
+      return fail(FCCQP_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),     \
+                  __FILE__, __LINE__);                                                       \
+  } while (0)
+
+constexpr int kCounterRing = 256;
+
+// Per-device context: properties, work counters, global scratch, host-path staging.
+struct DeviceCtx {
+  int device = -1;
+  int num_sms = 0;
+  int max_smem_optin = 0;
+  int clock_khz = 0;
+  unsigned int* counters = nullptr;
+  int next_counter = 0;
+  double* gscratch = nullptr;
+  size_t gscratch_bytes = 0;
+  // host-path staging (grow only)
+  char* stage = nullptr;
+  size_t stage_bytes = 0;
+  cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::mutex mu;       // guards counters / gscratch / occupancy cache
+  std::mutex host_mu;  // serialises FCCQP_MEM_HOST calls (they share the staging buffer)
+  std::map<std::pair<const void*, size_t>, int> occupancy;  // (kernel, smem) -> CTAs/SM
+};
+
+std::mutex g_ctx_mu;
+std::map<int, std::unique_ptr<DeviceCtx>> g_ctx;
+
+int get_ctx(int device, DeviceCtx** out) {
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  auto it = g_ctx.find(device);
+  if (it != g_ctx.end()) { *out = it->second.get(); return FCCQP_OK; }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(FCCQP_E_CUDA, "no usable CUDA device (%s); this library has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(FCCQP_E_INVALID, "device %d out of range [0,%d)", device, count);
+  CUDA_TRY(cudaSetDevice(device));
+  auto ctx = std::make_unique<DeviceCtx>();
+  ctx->device = device;
+  CUDA_TRY(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device));
+  CUDA_TRY(cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  CUDA_TRY(cudaDeviceGetAttribute(&ctx->clock_khz, cudaDevAttrClockRate, device));
+  CUDA_TRY(cudaMalloc(&ctx->counters, kCounterRing * sizeof(unsigned int)));
+  for (auto& s : ctx->streams) CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreate(&ctx->ev0));
+  CUDA_TRY(cudaEventCreate(&ctx->ev1));
+  *out = ctx.get();
+  g_ctx[device] = std::move(ctx);
+  return FCCQP_OK;
+}
+
+using KernelFn = void (*)(const fccqp::SolveParams);
+
+template <int kThreads>
+KernelFn pick_variant(bool global_m) {
+  return global_m ? (KernelFn)fccqp::fccqp_solve_kernel<kThreads, true>
+                  : (KernelFn)fccqp::fccqp_solve_kernel<kThreads, false>;
+}
+
+// Chooses the template instance (threads >= N) and the M placement.
+int pick_kernel(const DeviceCtx& ctx, int n, int m, int nc, KernelFn* fn, int* threads,
+                bool* global_m, size_t* smem) {
+  const int N = n + m;
+  if (N < 1) return fail(FCCQP_E_INVALID, "n + m must be >= 1");
+  if (N > 1024) return fail(FCCQP_E_UNSUPPORTED, "n + m = %d exceeds the 1024-row limit of the kernels", N);
+  fccqp::Layout ls(n, m, nc, true);
+  *global_m = ls.bytes() > (size_t)ctx.max_smem_optin;
+  fccqp::Layout l(n, m, nc, !*global_m);
+  *smem = l.bytes();
+  if (*smem > (size_t)ctx.max_smem_optin)
+    return fail(FCCQP_E_UNSUPPORTED, "problem needs %zu B of shared memory (> %d)", *smem, ctx.max_smem_optin);
+  if (N <= 128) { *threads = 128; *fn = pick_variant<128>(*global_m); }
+  else if (N <= 192) { *threads = 192; *fn = pick_variant<192>(*global_m); }
+  else if (N <= 256) { *threads = 256; *fn = pick_variant<256>(*global_m); }
+  else if (N <= 512) { *threads = 512; *fn = pick_variant<512>(*global_m); }
+  else { *threads = 1024; *fn = pick_variant<1024>(*global_m); }
+  return FCCQP_OK;
+}
+
+// Launches the fused solve on `stream` for device-resident data described by p
+// (work_counter / gscratch are filled in here).
+int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream) {
+  if (p.B == 0) return FCCQP_OK;
+  KernelFn fn; int threads; bool global_m; size_t smem;
+  int rc = pick_kernel(ctx, p.n, p.m, p.nc, &fn, &threads, &global_m, &smem);
+  if (rc) return rc;
+  int ctas_per_sm = 0;
+  {
+    std::lock_guard<std::mutex> lk(ctx.mu);
+    const auto key = std::make_pair((const void*)fn, smem);
+    auto it = ctx.occupancy.find(key);
+    if (it == ctx.occupancy.end()) {
+      // the attribute is per kernel, the smem size per (n, m, nc): raise it to the device maximum once
+      CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx.max_smem_optin));
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, fn, threads, smem));
+      if (ctas_per_sm < 1) return fail(FCCQP_E_UNSUPPORTED, "kernel does not fit on an SM (smem %zu B)", smem);
+      ctx.occupancy[key] = ctas_per_sm;
+    } else {
+      ctas_per_sm = it->second;
+    }
+    p.work_counter = ctx.counters + ctx.next_counter;
+    ctx.next_counter = (ctx.next_counter + 1) % kCounterRing;
+  }
+  int grid = ctas_per_sm * ctx.num_sms;
+  if (grid > p.B) grid = p.B;
+  if (global_m) {
+    fccqp::Layout l(p.n, p.m, p.nc, false);
+    const size_t slab = (l.m_doubles + 1) & ~size_t(1);
+    const size_t need = slab * sizeof(double) * (size_t)grid;
+    std::lock_guard<std::mutex> lk(ctx.mu);
+    if (need > ctx.gscratch_bytes) {
+      if (ctx.gscratch) CUDA_TRY(cudaFree(ctx.gscratch));
+      ctx.gscratch = nullptr; ctx.gscratch_bytes = 0;
+      CUDA_TRY(cudaMalloc(&ctx.gscratch, need));
+      ctx.gscratch_bytes = need;
+    }
+    p.gscratch = ctx.gscratch;
+    p.gscratch_stride = (long long)slab;
+  }
+  CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned int), stream));
+  static const bool profile = getenv("FCCQP_PROFILE") != nullptr;  // developer aid: phase cycle counters
+  unsigned long long* d_prof = nullptr;
+  if (profile) {
+    CUDA_TRY(cudaMalloc(&d_prof, 16 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), stream));
+    p.prof = d_prof;
+  }
+  fn<<<grid, threads, smem, stream>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  if (profile) {
+    unsigned long long h[16];
+    CUDA_TRY(cudaMemcpyAsync(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    CUDA_TRY(cudaFree(d_prof));
+    static const char* names[14] = {"stage-in", "lu-assemble", "lu-panel", "lu-swap-trsm", "lu-trailing",
+                                    "lu-backsub", "ldlt-assemble", "ldlt-diag", "ldlt-trsm", "ldlt-trailing",
+                                    "xinv", "admm-solve", "admm-project", "epilogue"};
+    double tot = 0;
+    for (int i = 0; i < 14; ++i) tot += (double)h[i];
+    fprintf(stderr, "[fccqp profile] B=%d grid=%d qps=%llu iters=%llu cycles/QP=%.0f\n", p.B, grid, h[14], h[15],
+            h[14] ? tot / (double)h[14] : 0.0);
+    for (int i = 0; i < 14; ++i)
+      fprintf(stderr, "   %-14s %10.0f cyc/QP  %5.1f%%\n", names[i], h[14] ? (double)h[i] / (double)h[14] : 0.0,
+              tot > 0 ? 100.0 * (double)h[i] / tot : 0.0);
+  }
+  g_launches.fetch_add(1);
+  {
+    std::lock_guard<std::mutex> lk(g_info_mu);
+    g_last_launch = {grid, threads, (int)smem, ctas_per_sm};
+  }
+  return FCCQP_OK;
+}
+
+int check_dims(int n, int m, int nc, int lcs) {
+  if (n < 0 || m < 0 || nc < 0) return fail(FCCQP_E_INVALID, "negative dimension");
+  if (nc % 3 != 0) return fail(FCCQP_E_INVALID, "nc = %d must be a multiple of 3 (src/fcc_qp.cpp:32)", nc);
+  if (lcs < 0 || lcs + nc > n)
+    return fail(FCCQP_E_INVALID, "lambda_c_start + nc = %d exceeds num_vars = %d (src/fcc_qp.cpp:33)", lcs + nc, n);
+  if (n < 1) return fail(FCCQP_E_INVALID, "num_vars must be >= 1");
+  return FCCQP_OK;
+}
+
+int check_options(const fccqp_options& o) {
+  if (o.max_iter < 0) return fail(FCCQP_E_INVALID, "max_iter must be >= 0");
+  if (!(o.rho > 0.0)) return fail(FCCQP_E_INVALID, "rho must be > 0 (src/fcc_qp.hpp:76)");
+  return FCCQP_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// single-problem object
+// ---------------------------------------------------------------------------
+struct fccqp_solver {
+  int n, m, nc, lcs, device;
+  fccqp_options opt;
+  int warm = 0;
+  bool has_state = false;  // a Solve has happened (x_ is meaningful)
+  DeviceCtx* ctx = nullptr;
+  cudaStream_t stream = nullptr;
+  // device: inputs packed [Q n*n | A m*n | b n | beq m | mu nc/3 | lb n | ub n], state, outputs
+  double* d_in = nullptr;
+  double* d_x = nullptr; double* d_mux = nullptr; double* d_muc = nullptr;
+  double* d_out = nullptr;   // [4] res_b res_f bviol fviol ; then ints
+  int* d_iout = nullptr;     // [2] n_iter status
+  unsigned long long* d_cycles = nullptr;
+  // pinned host mirrors
+  double* h_in = nullptr;
+  double* h_out = nullptr;   // [n + 4] z + scalars
+  int* h_iout = nullptr;
+  unsigned long long* h_cycles = nullptr;
+  size_t in_doubles = 0;
+  fccqp_details details{};
+};
+
+extern "C" {
+
+void fccqp_default_options(fccqp_options* opt) {
+  if (!opt) return;
+  opt->max_iter = 1000; opt->reserved = 0; opt->rho = 1e-6; opt->eps_fcone = 1e-3; opt->eps_bound = 1e-6;
+}
+const char* fccqp_last_error(void) { return g_err.c_str(); }
+int fccqp_abi_version(void) { return FCCQP_ABI_VERSION; }
+int fccqp_device_count(void) {
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return c;
+}
+int64_t fccqp_kernel_launch_count(void) { return g_launches.load(); }
+int fccqp_last_launch_info(int* grid, int* block, int* smem_bytes, int* ctas_per_sm) {
+  std::lock_guard<std::mutex> lk(g_info_mu);
+  if (grid) *grid = g_last_launch.grid;
+  if (block) *block = g_last_launch.block;
+  if (smem_bytes) *smem_bytes = g_last_launch.smem;
+  if (ctas_per_sm) *ctas_per_sm = g_last_launch.ctas_per_sm;
+  return FCCQP_OK;
+}
+
+int fccqp_create(int n, int m, int nc, int lcs, int device, fccqp_handle* out) {
+  if (!out) return fail(FCCQP_E_INVALID, "out is null");
+  *out = nullptr;
+  int rc = check_dims(n, m, nc, lcs);
+  if (rc) return rc;
+  DeviceCtx* ctx = nullptr;
+  rc = get_ctx(device, &ctx);
+  if (rc) return rc;
+  KernelFn fn; int threads; bool gm; size_t smem;
+  rc = pick_kernel(*ctx, n, m, nc, &fn, &threads, &gm, &smem);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(device));
+  auto* h = new fccqp_solver();
+  h->n = n; h->m = m; h->nc = nc; h->lcs = lcs; h->device = device; h->ctx = ctx;
+  fccqp_default_options(&h->opt);
+  h->in_doubles = (size_t)n * n + (size_t)m * n + n + m + nc / 3 + n + n;
+  auto cleanup_fail = [&](cudaError_t e, const char* what) {
+    int r = fail(FCCQP_E_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+    fccqp_destroy(h);
+    return r;
+  };
+  cudaError_t e;
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking))) return cleanup_fail(e, "cudaStreamCreate");
+  if ((e = cudaMalloc(&h->d_in, (h->in_doubles + 2) * sizeof(double)))) return cleanup_fail(e, "cudaMalloc");
+  if ((e = cudaMalloc(&h->d_x, (size_t)(n + 1) * sizeof(double)))) return cleanup_fail(e, "cudaMalloc");
+  if ((e = cudaMalloc(&h->d_mux, (size_t)(n + 1) * sizeof(double)))) return cleanup_fail(e, "cudaMalloc");
+  if ((e = cudaMalloc(&h->d_muc, (size_t)(nc + 1) * sizeof(double)))) return cleanup_fail(e, "cudaMalloc");
+  if ((e = cudaMalloc(&h->d_out, 4 * sizeof(double)))) return cleanup_fail(e, "cudaMalloc");
+  if ((e = cudaMalloc(&h->d_iout, 2 * sizeof(int)))) return cleanup_fail(e, "cudaMalloc");
+  if ((e = cudaMalloc(&h->d_cycles, 2 * sizeof(unsigned long long)))) return cleanup_fail(e, "cudaMalloc");
+  if ((e = cudaMallocHost(&h->h_in, (h->in_doubles + 2) * sizeof(double)))) return cleanup_fail(e, "cudaMallocHost");
+  if ((e = cudaMallocHost(&h->h_out, (size_t)(n + 4) * sizeof(double)))) return cleanup_fail(e, "cudaMallocHost");
+  if ((e = cudaMallocHost(&h->h_iout, 2 * sizeof(int)))) return cleanup_fail(e, "cudaMallocHost");
+  if ((e = cudaMallocHost(&h->h_cycles, 2 * sizeof(unsigned long long)))) return cleanup_fail(e, "cudaMallocHost");
+  if ((e = cudaMemset(h->d_x, 0, (size_t)(n + 1) * sizeof(double)))) return cleanup_fail(e, "cudaMemset");
+  if ((e = cudaMemset(h->d_mux, 0, (size_t)(n + 1) * sizeof(double)))) return cleanup_fail(e, "cudaMemset");
+  if ((e = cudaMemset(h->d_muc, 0, (size_t)(nc + 1) * sizeof(double)))) return cleanup_fail(e, "cudaMemset");
+  memset(h->h_out, 0, (size_t)(n + 4) * sizeof(double));
+  h->h_iout[0] = h->h_iout[1] = 0;
+  *out = h;
+  return FCCQP_OK;
+}
+
+int fccqp_destroy(fccqp_handle h) {
+  if (!h) return FCCQP_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  cudaFree(h->d_in); cudaFree(h->d_x); cudaFree(h->d_mux); cudaFree(h->d_muc);
+  cudaFree(h->d_out); cudaFree(h->d_iout); cudaFree(h->d_cycles);
+  cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_iout); cudaFreeHost(h->h_cycles);
+  delete h;
+  return FCCQP_OK;
+}
+
+int fccqp_set_options(fccqp_handle h, const fccqp_options* opt) {
+  if (!h || !opt) return fail(FCCQP_E_INVALID, "null argument");
+  int rc = check_options(*opt);
+  if (rc) return rc;
+  h->opt = *opt;
+  return FCCQP_OK;
+}
+int fccqp_get_options(fccqp_handle h, fccqp_options* opt) {
+  if (!h || !opt) return fail(FCCQP_E_INVALID, "null argument");
+  *opt = h->opt;
+  return FCCQP_OK;
+}
+int fccqp_set_rho(fccqp_handle h, double rho) {
+  if (!h) return fail(FCCQP_E_INVALID, "null handle");
+  if (!(rho > 0.0)) return fail(FCCQP_E_INVALID, "rho must be > 0 (src/fcc_qp.hpp:76)");
+  h->opt.rho = rho;
+  return FCCQP_OK;
+}
+int fccqp_set_max_iter(fccqp_handle h, int max_iter) {
+  if (!h) return fail(FCCQP_E_INVALID, "null handle");
+  if (max_iter <= 0) return fail(FCCQP_E_INVALID, "max_iter must be > 0 (src/fcc_qp.hpp:81)");
+  h->opt.max_iter = max_iter;
+  return FCCQP_OK;
+}
+int fccqp_set_warm_start(fccqp_handle h, int warm) {
+  if (!h) return fail(FCCQP_E_INVALID, "null handle");
+  h->warm = warm != 0;
+  return FCCQP_OK;
+}
+int fccqp_contact_vars_start(fccqp_handle h) { return h ? h->lcs : -1; }
+
+int fccqp_solve(fccqp_handle h, const double* Q, ptrdiff_t q_rs, ptrdiff_t q_cs, const double* b,
+                const double* A, ptrdiff_t a_rs, ptrdiff_t a_cs, const double* b_eq,
+                const double* mu, int n_mu, const double* lb, const double* ub) {
+  if (!h) return fail(FCCQP_E_INVALID, "null handle");
+  const int n = h->n, m = h->m, nc = h->nc;
+  if (!Q || !b || (m > 0 && (!A || !b_eq)) || !lb || !ub || (nc > 0 && !mu))
+    return fail(FCCQP_E_INVALID, "null input pointer");
+  if (n_mu < nc / 3)
+    return fail(FCCQP_E_INVALID, "friction_coeffs has %d entries, need %d (src/constraint_utils.cpp:32)", n_mu, nc / 3);
+  const auto t0 = std::chrono::steady_clock::now();
+  CUDA_TRY(cudaSetDevice(h->device));
+  // pack into pinned staging: Q row-major n x n (symmetric), A in its cheaper traversal order
+  double* s = h->h_in;
+  double* sQ = s; s += (size_t)n * n;
+  double* sA = s; s += (size_t)m * n;
+  double* sb = s; s += n;
+  double* sbeq = s; s += m;
+  double* smu = s; s += nc / 3;
+  double* slb = s; s += n;
+  double* sub = s;
+  // Q: copy along the contiguous direction when there is one
+  if (q_cs == 1) for (int i = 0; i < n; ++i) memcpy(sQ + (size_t)i * n, Q + i * q_rs, sizeof(double) * n);
+  else if (q_rs == 1) for (int j = 0; j < n; ++j) memcpy(sQ + (size_t)j * n, Q + j * q_cs, sizeof(double) * n);  // symmetric
+  else for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) sQ[(size_t)i * n + j] = Q[i * q_rs + j * q_cs];
+  long long k_a_rs, k_a_cs;
+  if (a_rs == 1 && a_cs != 1) {  // column-major (Eigen): keep columns contiguous
+    for (int j = 0; j < n; ++j) memcpy(sA + (size_t)j * m, A + j * a_cs, sizeof(double) * m);
+    k_a_rs = 1; k_a_cs = m;
+  } else {
+    for (int i = 0; i < m; ++i)
+      for (int j = 0; j < n; ++j) sA[(size_t)i * n + j] = A[i * a_rs + j * a_cs];
+    k_a_rs = n; k_a_cs = 1;
+  }
+  memcpy(sb, b, sizeof(double) * n);
+  if (m) memcpy(sbeq, b_eq, sizeof(double) * m);
+  if (nc) memcpy(smu, mu, sizeof(double) * (nc / 3));
+  memcpy(slb, lb, sizeof(double) * n);
+  memcpy(sub, ub, sizeof(double) * n);
+  CUDA_TRY(cudaMemcpyAsync(h->d_in, h->h_in, h->in_doubles * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->d_cycles, 0, 2 * sizeof(unsigned long long), h->stream));
+
+  fccqp::SolveParams p{};
+  p.B = 1; p.n = n; p.m = m; p.nc = nc; p.lcs = h->lcs;
+  p.max_iter = h->opt.max_iter; p.rho = h->opt.rho; p.eps_fcone = h->opt.eps_fcone; p.eps_bound = h->opt.eps_bound;
+  p.warm = h->warm;  // warm with no earlier Solve starts from the zero state, like the reference object
+  double* d = h->d_in;
+  p.Q = d; p.q_bs = 0; p.q_rs = n; p.q_cs = 1; d += (size_t)n * n;
+  p.A = d; p.a_bs = 0; p.a_rs = k_a_rs; p.a_cs = k_a_cs; d += (size_t)m * n;
+  p.b = d; p.b_bs = 0; d += n;
+  p.beq = d; p.beq_bs = 0; d += m;
+  p.mu = d; p.mu_bs = 0; d += nc / 3;
+  p.lb = d; p.lb_bs = 0; d += n;
+  p.ub = d; p.ub_bs = 0;
+  p.x = h->d_x; p.mu_x = h->d_mux; p.mu_c = h->d_muc;
+  p.n_iter = h->d_iout; p.status = h->d_iout + 1;
+  p.res_b = h->d_out; p.res_f = h->d_out + 1; p.bviol = h->d_out + 2; p.fviol = h->d_out + 3;
+  p.cycles = h->d_cycles;
+  int rc = launch_solve(*h->ctx, p, h->stream);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(h->h_out, h->d_x, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->h_out + n, h->d_out, sizeof(double) * 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->h_iout, h->d_iout, sizeof(int) * 2, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->h_cycles, h->d_cycles, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->has_state = true;
+  h->details.n_iter = h->h_iout[0];
+  h->details.solve_status = h->h_iout[1];
+  h->details.admm_residual_bounds = h->h_out[n];
+  h->details.admm_residual_friction_cone = h->h_out[n + 1];
+  h->details.bounds_viol = h->h_out[n + 2];
+  h->details.friction_cone_viol = h->h_out[n + 3];
+  h->details.factorization_time = h->ctx->clock_khz > 0 ? (double)h->h_cycles[0] / (1e3 * h->ctx->clock_khz) : 0.0;
+  h->details.solve_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return FCCQP_OK;
+}
+
+int fccqp_get_solution(fccqp_handle h, double* z, fccqp_details* details) {
+  if (!h) return fail(FCCQP_E_INVALID, "null handle");
+  if (z) memcpy(z, h->h_out, sizeof(double) * h->n);
+  if (details) *details = h->details;
+  return FCCQP_OK;
+}
+
+int fccqp_get_warm_state(fccqp_handle h, double* x, double* mu_x, double* mu_c) {
+  if (!h) return fail(FCCQP_E_INVALID, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (x) CUDA_TRY(cudaMemcpy(x, h->d_x, sizeof(double) * h->n, cudaMemcpyDeviceToHost));
+  if (mu_x) CUDA_TRY(cudaMemcpy(mu_x, h->d_mux, sizeof(double) * h->n, cudaMemcpyDeviceToHost));
+  if (mu_c && h->nc) CUDA_TRY(cudaMemcpy(mu_c, h->d_muc, sizeof(double) * h->nc, cudaMemcpyDeviceToHost));
+  return FCCQP_OK;
+}
+int fccqp_set_warm_state(fccqp_handle h, const double* x, const double* mu_x, const double* mu_c) {
+  if (!h) return fail(FCCQP_E_INVALID, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (x) CUDA_TRY(cudaMemcpy(h->d_x, x, sizeof(double) * h->n, cudaMemcpyHostToDevice));
+  if (mu_x) CUDA_TRY(cudaMemcpy(h->d_mux, mu_x, sizeof(double) * h->n, cudaMemcpyHostToDevice));
+  if (mu_c && h->nc) CUDA_TRY(cudaMemcpy(h->d_muc, mu_c, sizeof(double) * h->nc, cudaMemcpyHostToDevice));
+  h->has_state = true;
+  return FCCQP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// batched entry point
+// ---------------------------------------------------------------------------
+static int fill_params(const fccqp_batch_desc& d, fccqp::SolveParams& p) {
+  p.B = d.batch; p.n = d.n; p.m = d.m; p.nc = d.nc; p.lcs = d.lambda_c_start;
+  p.max_iter = d.options.max_iter; p.rho = d.options.rho;
+  p.eps_fcone = d.options.eps_fcone; p.eps_bound = d.options.eps_bound;
+  p.warm = d.warm_start != 0;
+  return FCCQP_OK;
+}
+
+static int validate_desc(const fccqp_batch_desc* d) {
+  if (!d) return fail(FCCQP_E_INVALID, "desc is null");
+  if (d->abi_version != FCCQP_ABI_VERSION)
+    return fail(FCCQP_E_INVALID, "abi_version %d != %d", d->abi_version, FCCQP_ABI_VERSION);
+  if (d->batch < 0) return fail(FCCQP_E_INVALID, "batch < 0");
+  int rc = check_dims(d->n, d->m, d->nc, d->lambda_c_start);
+  if (rc) return rc;
+  rc = check_options(d->options);
+  if (rc) return rc;
+  if (d->precision != FCCQP_PRECISION_FP64) return fail(FCCQP_E_UNSUPPORTED, "only FCCQP_PRECISION_FP64 is implemented");
+  if (d->memory_space != FCCQP_MEM_HOST && d->memory_space != FCCQP_MEM_DEVICE)
+    return fail(FCCQP_E_INVALID, "bad memory_space");
+  if (d->batch == 0) return FCCQP_OK;
+  if (!d->Q || !d->b || !d->lb || !d->ub || !d->x) return fail(FCCQP_E_INVALID, "null Q/b/lb/ub/x");
+  if (d->m > 0 && (!d->A_eq || !d->b_eq)) return fail(FCCQP_E_INVALID, "null A_eq/b_eq with m > 0");
+  if (d->nc > 0 && !d->friction_coeffs) return fail(FCCQP_E_INVALID, "null friction_coeffs with nc > 0");
+  if (d->warm_start && (!d->mu_x || (d->nc > 0 && !d->mu_lambda_c)))
+    return fail(FCCQP_E_INVALID, "warm_start needs mu_x and mu_lambda_c");
+  return FCCQP_OK;
+}
+
+int fccqp_batch_solve(const fccqp_batch_desc* desc) {
+  int rc = validate_desc(desc);
+  if (rc) return rc;
+  const fccqp_batch_desc& d = *desc;
+  DeviceCtx* ctx = nullptr;
+  rc = get_ctx(d.device, &ctx);
+  if (rc) return rc;
+  if (d.batch == 0) { if (d.device_seconds) *d.device_seconds = 0.0; return FCCQP_OK; }
+  CUDA_TRY(cudaSetDevice(d.device));
+  const int n = d.n, m = d.m, nc = d.nc, B = d.batch;
+
+  if (d.memory_space == FCCQP_MEM_DEVICE) {
+    fccqp::SolveParams p{};
+    fill_params(d, p);
+    p.Q = d.Q; p.q_bs = d.q_batch_stride; p.q_rs = d.q_row_stride; p.q_cs = d.q_col_stride;
+    p.b = d.b; p.b_bs = d.b_batch_stride;
+    p.A = d.A_eq; p.a_bs = d.a_batch_stride; p.a_rs = d.a_row_stride; p.a_cs = d.a_col_stride;
+    p.beq = d.b_eq; p.beq_bs = d.beq_batch_stride;
+    p.mu = d.friction_coeffs; p.mu_bs = d.mu_batch_stride;
+    p.lb = d.lb; p.lb_bs = d.lb_batch_stride;
+    p.ub = d.ub; p.ub_bs = d.ub_batch_stride;
+    p.x = d.x; p.mu_x = d.mu_x; p.mu_c = d.mu_lambda_c;
+    p.n_iter = d.n_iter; p.status = d.status;
+    p.res_b = d.res_bounds; p.res_f = d.res_fcone; p.bviol = d.bounds_viol; p.fviol = d.fcone_viol;
+    cudaStream_t st = (cudaStream_t)d.stream;
+    if (d.device_seconds) CUDA_TRY(cudaEventRecord(ctx->ev0, st));
+    rc = launch_solve(*ctx, p, st);
+    if (rc) return rc;
+    if (d.device_seconds) {
+      CUDA_TRY(cudaEventRecord(ctx->ev1, st));
+      CUDA_TRY(cudaEventSynchronize(ctx->ev1));
+      float ms = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+      *d.device_seconds = 1e-3 * ms;
+    }
+    return FCCQP_OK;
+  }
+
+  // ---- host memory: stage through device buffers, chunked over 3 streams so that the
+  // H2D copy of chunk c+1 overlaps the solve of chunk c and the D2H of chunk c-1.
+  std::lock_guard<std::mutex> lk(ctx->host_mu);  // one host-path call per device at a time
+  struct Seg { size_t off; size_t per_qp; bool shared; };
+  auto seg = [&](size_t& cur, size_t per_qp, bool shared) {
+    Seg s{cur, per_qp, shared};
+    cur += align_up((shared ? per_qp : per_qp * (size_t)B) * sizeof(double), 256);
+    return s;
+  };
+  // dense (packed) per-QP sizes on the device
+  size_t cur = 0;
+  const bool q_shared = d.q_batch_stride == 0, a_shared = d.a_batch_stride == 0;
+  const bool b_shared = d.b_batch_stride == 0, beq_shared = d.beq_batch_stride == 0;
+  const bool mu_shared = d.mu_batch_stride == 0, lb_shared = d.lb_batch_stride == 0, ub_shared = d.ub_batch_stride == 0;
+  // The host path requires each QP's Q / A block to be a dense n*n / m*n slab (either order).
+  const bool q_dense = (d.q_row_stride == n && d.q_col_stride == 1) || (d.q_row_stride == 1 && d.q_col_stride == n);
+  const bool a_dense = m == 0 || (d.a_row_stride == n && d.a_col_stride == 1) || (d.a_row_stride == 1 && d.a_col_stride == m);
+  if (!q_dense || !a_dense) return fail(FCCQP_E_UNSUPPORTED, "host path needs dense per-QP Q and A_eq blocks");
+  if ((!q_shared && d.q_batch_stride != (int64_t)n * n) || (!a_shared && m > 0 && d.a_batch_stride != (int64_t)m * n) ||
+      (!b_shared && d.b_batch_stride != n) || (!beq_shared && m > 0 && d.beq_batch_stride != m) ||
+      (!mu_shared && nc > 0 && d.mu_batch_stride != nc / 3) || (!lb_shared && d.lb_batch_stride != n) ||
+      (!ub_shared && d.ub_batch_stride != n))
+    return fail(FCCQP_E_UNSUPPORTED, "host path needs densely stacked inputs (batch stride 0 or the per-QP size)");
+  Seg sQ = seg(cur, (size_t)n * n, q_shared), sA = seg(cur, (size_t)m * n, a_shared);
+  Seg sb = seg(cur, n, b_shared), sbeq = seg(cur, m, beq_shared), smu = seg(cur, nc / 3, mu_shared);
+  Seg slb = seg(cur, n, lb_shared), sub = seg(cur, n, ub_shared);
+  Seg sx = seg(cur, n, false), smx = seg(cur, n, false), smc = seg(cur, nc, false);
+  Seg sres = seg(cur, 4, false);
+  Seg sint = seg(cur, 1, false);  // 2 ints per QP packed in one double slot
+  if (cur > ctx->stage_bytes) {
+    if (ctx->stage) CUDA_TRY(cudaFree(ctx->stage));
+    ctx->stage = nullptr; ctx->stage_bytes = 0;
+    CUDA_TRY(cudaMalloc(&ctx->stage, cur));
+    ctx->stage_bytes = cur;
+  }
+  char* base = ctx->stage;
+  auto dp = [&](const Seg& s) { return reinterpret_cast<double*>(base + s.off); };
+  int* d_niter = reinterpret_cast<int*>(base + sint.off);
+  int* d_status = d_niter + B;
+
+  const auto t0 = std::chrono::steady_clock::now();
+  // shared inputs once
+  cudaStream_t s0 = ctx->streams[0];
+  auto h2d_shared = [&](const Seg& s, const double* src) -> int {
+    if (s.shared && s.per_qp && src)
+      CUDA_TRY(cudaMemcpyAsync(dp(s), src, s.per_qp * sizeof(double), cudaMemcpyHostToDevice, s0));
+    return FCCQP_OK;
+  };
+  if ((rc = h2d_shared(sQ, d.Q)) || (rc = h2d_shared(sA, d.A_eq)) || (rc = h2d_shared(sb, d.b)) ||
+      (rc = h2d_shared(sbeq, d.b_eq)) || (rc = h2d_shared(smu, d.friction_coeffs)) ||
+      (rc = h2d_shared(slb, d.lb)) || (rc = h2d_shared(sub, d.ub)))
+    return rc;
+  CUDA_TRY(cudaStreamSynchronize(s0));
+
+  int nchunks = (B + 4095) / 4096;
+  if (nchunks > 16) nchunks = 16;
+  if (nchunks < 1) nchunks = 1;
+  for (int c = 0; c < nchunks; ++c) {
+    const long long lo = (long long)B * c / nchunks, hi = (long long)B * (c + 1) / nchunks;
+    const size_t cnt = (size_t)(hi - lo);
+    if (!cnt) continue;
+    cudaStream_t st = ctx->streams[c % 3];
+    auto h2d = [&](const Seg& s, const double* src) -> int {
+      if (!s.shared && s.per_qp && src)
+        CUDA_TRY(cudaMemcpyAsync(dp(s) + lo * s.per_qp, src + lo * s.per_qp, cnt * s.per_qp * sizeof(double),
+                                 cudaMemcpyHostToDevice, st));
+      return FCCQP_OK;
+    };
+    if ((rc = h2d(sQ, d.Q)) || (rc = h2d(sA, d.A_eq)) || (rc = h2d(sb, d.b)) || (rc = h2d(sbeq, d.b_eq)) ||
+        (rc = h2d(smu, d.friction_coeffs)) || (rc = h2d(slb, d.lb)) || (rc = h2d(sub, d.ub)))
+      return rc;
+    if (d.warm_start) {
+      if ((rc = h2d(sx, d.x)) || (rc = h2d(smx, d.mu_x)) || (rc = h2d(smc, d.mu_lambda_c))) return rc;
+    }
+    fccqp::SolveParams p{};
+    fill_params(d, p);
+    p.B = (int)cnt;
+    auto off = [&](const Seg& s) { return s.shared ? dp(s) : dp(s) + lo * s.per_qp; };
+    p.Q = off(sQ); p.q_bs = q_shared ? 0 : (long long)n * n; p.q_rs = d.q_row_stride; p.q_cs = d.q_col_stride;
+    p.A = off(sA); p.a_bs = a_shared ? 0 : (long long)m * n; p.a_rs = d.a_row_stride; p.a_cs = d.a_col_stride;
+    p.b = off(sb); p.b_bs = b_shared ? 0 : n;
+    p.beq = off(sbeq); p.beq_bs = beq_shared ? 0 : m;
+    p.mu = off(smu); p.mu_bs = mu_shared ? 0 : nc / 3;
+    p.lb = off(slb); p.lb_bs = lb_shared ? 0 : n;
+    p.ub = off(sub); p.ub_bs = ub_shared ? 0 : n;
+    p.x = off(sx); p.mu_x = off(smx); p.mu_c = off(smc);
+    p.n_iter = d_niter + lo; p.status = d_status + lo;
+    double* res = dp(sres);
+    p.res_b = res + lo; p.res_f = res + (size_t)B + lo; p.bviol = res + 2 * (size_t)B + lo; p.fviol = res + 3 * (size_t)B + lo;
+    rc = launch_solve(*ctx, p, st);
+    if (rc) return rc;
+    auto d2h = [&](void* dst, const void* src, size_t bytes) -> int {
+      if (dst && bytes) CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+      return FCCQP_OK;
+    };
+    if ((rc = d2h(d.x + lo * n, p.x, cnt * n * sizeof(double))) ||
+        (rc = d2h(d.mu_x ? d.mu_x + lo * n : nullptr, p.mu_x, cnt * n * sizeof(double))) ||
+        (rc = d2h(d.mu_lambda_c ? d.mu_lambda_c + lo * nc : nullptr, p.mu_c, cnt * nc * sizeof(double))) ||
+        (rc = d2h(d.n_iter ? d.n_iter + lo : nullptr, p.n_iter, cnt * sizeof(int))) ||
+        (rc = d2h(d.status ? d.status + lo : nullptr, p.status, cnt * sizeof(int))) ||
+        (rc = d2h(d.res_bounds ? d.res_bounds + lo : nullptr, p.res_b, cnt * sizeof(double))) ||
+        (rc = d2h(d.res_fcone ? d.res_fcone + lo : nullptr, p.res_f, cnt * sizeof(double))) ||
+        (rc = d2h(d.bounds_viol ? d.bounds_viol + lo : nullptr, p.bviol, cnt * sizeof(double))) ||
+        (rc = d2h(d.fcone_viol ? d.fcone_viol + lo : nullptr, p.fviol, cnt * sizeof(double))))
+      return rc;
+  }
+  for (auto& s : ctx->streams) CUDA_TRY(cudaStreamSynchronize(s));
+  if (d.device_seconds)
+    *d.device_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return FCCQP_OK;
+}
+
+int fccqp_release_workspaces(void) {
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  for (auto& kv : g_ctx) {
+    DeviceCtx& c = *kv.second;
+    std::lock_guard<std::mutex> lk2(c.host_mu);
+    std::lock_guard<std::mutex> lk3(c.mu);
+    cudaSetDevice(c.device);
+    if (c.stage) { cudaFree(c.stage); c.stage = nullptr; c.stage_bytes = 0; }
+    if (c.gscratch) { cudaFree(c.gscratch); c.gscratch = nullptr; c.gscratch_bytes = 0; }
+  }
+  return FCCQP_OK;
+}
+
+}  // extern "C"

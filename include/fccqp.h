@@ -1,0 +1,177 @@
+/*
+ * fccqp.h -- C ABI of the B200-native batched FCCQP solver (libfccqp_b200.so).
+ *
+ * This is the drop-in boundary for the one hot path of Brian-Acosta/fcc_qp:
+ * the ADMM whole-body-control QP solve
+ *
+ *     minimize   1/2 x'Qx + b'x
+ *     subject to A_eq x = b_eq,  lb <= x <= ub,
+ *                x[lambda_c_start : lambda_c_start+nc] in a product of nc/3 Coulomb cones
+ *
+ * (reference: src/fcc_qp.hpp:43-53).  Plain pointers and sizes only -- no C++
+ * or torch types -- so it can be bound from C++, ctypes, cgo, JNI, ...
+ * Every entry point cites the reference interface it replaces (file:line is
+ * relative to the reference repository root).
+ *
+ * There is NO CPU fallback: every solve runs on a CUDA device (sm_100a);
+ * fccqp_create / fccqp_batch_solve fail with FCCQP_E_CUDA when none is usable.
+ *
+ * Return convention: 0 (FCCQP_OK) on success, negative fccqp_error otherwise;
+ * fccqp_last_error() returns a thread-local human-readable message.
+ */
+#ifndef FCCQP_H
+#define FCCQP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FCCQP_ABI_VERSION 1
+
+typedef enum fccqp_error {
+  FCCQP_OK = 0,
+  FCCQP_E_INVALID = -1,     /* bad dimensions / null pointers / too few friction coefficients */
+  FCCQP_E_CUDA = -2,        /* CUDA runtime failure (message has the CUDA error string)      */
+  FCCQP_E_UNSUPPORTED = -3  /* problem too large for the device kernels, unknown precision   */
+} fccqp_error;
+
+/* Per-QP solve status.  0/1 are the reference's FCCQPSolveStatus
+ * (src/fcc_qp.hpp:14-17; derived at src/fcc_qp.cpp:203-204).  2 is an
+ * extension: the KKT solve broke down (singular pre-solve matrix or a
+ * non-finite iterate) -- the reference would return garbage/NaN silently. */
+typedef enum fccqp_solve_status {
+  FCCQP_STATUS_SUCCESS = 0,
+  FCCQP_STATUS_MAX_ITERATIONS = 1,
+  FCCQP_STATUS_NUMERICAL_ISSUE = 2
+} fccqp_solve_status;
+
+/* FCCQPOptions, src/fcc_qp.hpp:30-35 (same defaults via fccqp_default_options). */
+typedef struct fccqp_options {
+  int32_t max_iter;  /* 1000 */
+  int32_t reserved;
+  double rho;        /* 1e-6 */
+  double eps_fcone;  /* 1e-3 */
+  double eps_bound;  /* 1e-6 */
+} fccqp_options;
+
+/* FCCQPDetails, src/fcc_qp.hpp:19-28.  Times are seconds; for the device path
+ * solve_time is host wall time of the call and factorization_time the device
+ * time spent in the KKT factorizations (clock64-derived, 0 if not profiled). */
+typedef struct fccqp_details {
+  int32_t n_iter;
+  int32_t solve_status; /* fccqp_solve_status */
+  double admm_residual_bounds;
+  double admm_residual_friction_cone;
+  double solve_time;
+  double factorization_time;
+  double bounds_viol;
+  double friction_cone_viol;
+} fccqp_details;
+
+void fccqp_default_options(fccqp_options* opt);
+const char* fccqp_last_error(void);
+int fccqp_abi_version(void);
+/* number of usable CUDA devices (0 if none / no driver) */
+int fccqp_device_count(void);
+
+/* ------------------------------------------------------------------------- *
+ * Single-problem object: replaces class fcc_qp::FCCQP (src/fcc_qp.hpp:54-171)
+ * ------------------------------------------------------------------------- */
+typedef struct fccqp_solver* fccqp_handle;
+
+/* FCCQP::FCCQP(num_vars, num_equality_constraints, nc, lambda_c_start),
+ * src/fcc_qp.hpp:73, src/fcc_qp.cpp:24-55.  Requires nc % 3 == 0 and
+ * lambda_c_start + nc <= n (asserted there, checked here).  `device` is the
+ * CUDA ordinal that owns the workspace and the warm-start state. */
+int fccqp_create(int n, int m, int nc, int lambda_c_start, int device, fccqp_handle* out);
+int fccqp_destroy(fccqp_handle h);
+/* set_options / set_rho / set_max_iter / set_warm_start, src/fcc_qp.hpp:75-91 */
+int fccqp_set_options(fccqp_handle h, const fccqp_options* opt);
+int fccqp_get_options(fccqp_handle h, fccqp_options* opt);
+int fccqp_set_rho(fccqp_handle h, double rho);
+int fccqp_set_max_iter(fccqp_handle h, int max_iter);
+int fccqp_set_warm_start(fccqp_handle h, int warm_start);
+/* contact_vars_start(), src/fcc_qp.hpp:121 */
+int fccqp_contact_vars_start(fccqp_handle h);
+
+/* FCCQP::Solve, src/fcc_qp.hpp:114-117 / src/fcc_qp.cpp:114-191.
+ * HOST pointers.  Q is n x n and A_eq is m x n with element (i,j) at
+ * base[i*row_stride + j*col_stride] (Eigen column-major with outer stride ld:
+ * row_stride = 1, col_stride = ld; C-ordered numpy: row_stride = n, col_stride = 1).
+ * friction_coeffs must hold at least nc/3 values (the reference throws
+ * std::out_of_range, src/constraint_utils.cpp:32,55) -> FCCQP_E_INVALID. */
+int fccqp_solve(fccqp_handle h, const double* Q, ptrdiff_t q_row_stride, ptrdiff_t q_col_stride,
+                const double* b, const double* A_eq, ptrdiff_t a_row_stride,
+                ptrdiff_t a_col_stride, const double* b_eq, const double* friction_coeffs,
+                int n_friction_coeffs, const double* lb, const double* ub);
+/* FCCQP::GetSolution, src/fcc_qp.cpp:194-207: copies z (n doubles) + details. */
+int fccqp_get_solution(fccqp_handle h, double* z, fccqp_details* details);
+/* Warm-start state x_, mu_x_, mu_lambda_c_ (src/fcc_qp.hpp:147-153) -- private in
+ * the reference, exposed here so callers can checkpoint / migrate it. */
+int fccqp_get_warm_state(fccqp_handle h, double* x, double* mu_x, double* mu_lambda_c);
+int fccqp_set_warm_state(fccqp_handle h, const double* x, const double* mu_x,
+                         const double* mu_lambda_c);
+
+/* ------------------------------------------------------------------------- *
+ * Batched entry point: B independent QPs of identical dimensions per call.
+ * Semantically B calls of FCCQP::Solve + GetSolution (src/fcc_qp.cpp:114-207)
+ * on B solver objects, one launch.
+ * ------------------------------------------------------------------------- */
+typedef enum fccqp_memory_space { FCCQP_MEM_HOST = 0, FCCQP_MEM_DEVICE = 1 } fccqp_memory_space;
+typedef enum fccqp_precision { FCCQP_PRECISION_FP64 = 0 } fccqp_precision;
+
+typedef struct fccqp_batch_desc {
+  int32_t abi_version;     /* FCCQP_ABI_VERSION */
+  int32_t batch;           /* B >= 0 */
+  int32_t n, m, nc, lambda_c_start;
+  int32_t device;          /* CUDA ordinal */
+  int32_t memory_space;    /* fccqp_memory_space: where EVERY pointer below lives */
+  int32_t precision;       /* fccqp_precision */
+  int32_t warm_start;      /* 0: cold (pre-solve, duals zeroed; fcc_qp.cpp:136-139,159-178)
+                              1: warm: x/mu_x/mu_lambda_c are read as the carried state      */
+  fccqp_options options;
+
+  /* inputs; *_batch_stride in elements between consecutive QPs (0 = shared by all) */
+  const double* Q;        int64_t q_batch_stride, q_row_stride, q_col_stride;
+  const double* b;        int64_t b_batch_stride;
+  const double* A_eq;     int64_t a_batch_stride, a_row_stride, a_col_stride;
+  const double* b_eq;     int64_t beq_batch_stride;
+  const double* friction_coeffs; int64_t mu_batch_stride; /* nc/3 per QP */
+  const double* lb;       int64_t lb_batch_stride;
+  const double* ub;       int64_t ub_batch_stride;
+
+  /* in/out state, dense [B,n] / [B,n] / [B,nc].  x is also the solution z.
+   * mu_x / mu_lambda_c may be NULL for cold solves whose duals are not needed. */
+  double* x;
+  double* mu_x;
+  double* mu_lambda_c;
+
+  /* outputs, dense [B]; any may be NULL */
+  int32_t* n_iter;
+  int32_t* status;         /* fccqp_solve_status */
+  double* res_bounds;      /* admm_residual_bounds        */
+  double* res_fcone;       /* admm_residual_friction_cone */
+  double* bounds_viol;
+  double* fcone_viol;
+
+  void* stream;            /* cudaStream_t for FCCQP_MEM_DEVICE (NULL = default stream).
+                              Device calls are asynchronous on this stream. */
+  double* device_seconds;  /* optional HOST pointer: kernel time by CUDA events (forces a sync) */
+} fccqp_batch_desc;
+
+int fccqp_batch_solve(const fccqp_batch_desc* desc);
+/* Frees the cached per-device staging buffers used by FCCQP_MEM_HOST calls. */
+int fccqp_release_workspaces(void);
+
+/* Introspection used by bench.py for the roofline line: kernel launches issued
+ * by this library since load, and the launch geometry of the last batch call. */
+int64_t fccqp_kernel_launch_count(void);
+int fccqp_last_launch_info(int* grid, int* block, int* smem_bytes, int* ctas_per_sm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FCCQP_H */
