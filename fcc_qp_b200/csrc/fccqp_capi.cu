@@ -56,8 +56,6 @@ struct DeviceCtx {
   int clock_khz = 0;
   unsigned int* counters = nullptr;
   int next_counter = 0;
-  double* gscratch = nullptr;
-  size_t gscratch_bytes = 0;
   // host-path staging (grow only)
   char* stage = nullptr;
   size_t stage_bytes = 0;
@@ -98,29 +96,19 @@ int get_ctx(int device, DeviceCtx** out) {
 
 using KernelFn = void (*)(const fccqp::SolveParams);
 
-template <int kThreads>
-KernelFn pick_variant(bool global_m) {
-  return global_m ? (KernelFn)fccqp::fccqp_solve_kernel<kThreads, true>
-                  : (KernelFn)fccqp::fccqp_solve_kernel<kThreads, false>;
-}
-
-// Chooses the template instance (threads >= N) and the M placement.
-int pick_kernel(const DeviceCtx& ctx, int n, int m, int nc, KernelFn* fn, int* threads,
-                bool* global_m, size_t* smem) {
+// Chooses the template instance (threads >= n + m; CTAs/SM hint from the packed-matrix footprint).
+int pick_kernel(const DeviceCtx& ctx, int n, int m, int nc, KernelFn* fn, int* threads, size_t* smem) {
   const int N = n + m;
   if (N < 1) return fail(FCCQP_E_INVALID, "n + m must be >= 1");
-  if (N > 1024) return fail(FCCQP_E_UNSUPPORTED, "n + m = %d exceeds the 1024-row limit of the kernels", N);
-  fccqp::Layout ls(n, m, nc, true);
-  *global_m = ls.bytes() > (size_t)ctx.max_smem_optin;
-  fccqp::Layout l(n, m, nc, !*global_m);
+  fccqp::Layout l(n, m, nc);
   *smem = l.bytes();
-  if (*smem > (size_t)ctx.max_smem_optin)
-    return fail(FCCQP_E_UNSUPPORTED, "problem needs %zu B of shared memory (> %d)", *smem, ctx.max_smem_optin);
-  if (N <= 128) { *threads = 128; *fn = pick_variant<128>(*global_m); }
-  else if (N <= 192) { *threads = 192; *fn = pick_variant<192>(*global_m); }
-  else if (N <= 256) { *threads = 256; *fn = pick_variant<256>(*global_m); }
-  else if (N <= 512) { *threads = 512; *fn = pick_variant<512>(*global_m); }
-  else { *threads = 1024; *fn = pick_variant<1024>(*global_m); }
+  if (N > 256 || *smem > (size_t)ctx.max_smem_optin)
+    return fail(FCCQP_E_UNSUPPORTED,
+                "n + m = %d needs %zu B of shared memory per QP (limit %d B, 256 rows): too large for the "
+                "shared-memory-resident kernels", N, *smem, ctx.max_smem_optin);
+  if (N <= 128) { *threads = 128; *fn = (KernelFn)fccqp::fccqp_solve_kernel<128, 4>; }
+  else if (N <= 192) { *threads = 192; *fn = (KernelFn)fccqp::fccqp_solve_kernel<192, 2>; }
+  else { *threads = 256; *fn = (KernelFn)fccqp::fccqp_solve_kernel<256, 1>; }
   return FCCQP_OK;
 }
 
@@ -128,9 +116,11 @@ int pick_kernel(const DeviceCtx& ctx, int n, int m, int nc, KernelFn* fn, int* t
 // (work_counter / gscratch are filled in here).
 int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream) {
   if (p.B == 0) return FCCQP_OK;
-  KernelFn fn; int threads; bool global_m; size_t smem;
-  int rc = pick_kernel(ctx, p.n, p.m, p.nc, &fn, &threads, &global_m, &smem);
+  KernelFn fn; int threads; size_t smem;
+  int rc = pick_kernel(ctx, p.n, p.m, p.nc, &fn, &threads, &smem);
   if (rc) return rc;
+  static const int refine = getenv("FCCQP_PRESOLVE_REFINE") ? atoi(getenv("FCCQP_PRESOLVE_REFINE")) : 1;
+  p.refine = refine < 0 ? 0 : refine;
   int ctas_per_sm = 0;
   {
     std::lock_guard<std::mutex> lk(ctx.mu);
@@ -150,20 +140,6 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream) {
   }
   int grid = ctas_per_sm * ctx.num_sms;
   if (grid > p.B) grid = p.B;
-  if (global_m) {
-    fccqp::Layout l(p.n, p.m, p.nc, false);
-    const size_t slab = (l.m_doubles + 1) & ~size_t(1);
-    const size_t need = slab * sizeof(double) * (size_t)grid;
-    std::lock_guard<std::mutex> lk(ctx.mu);
-    if (need > ctx.gscratch_bytes) {
-      if (ctx.gscratch) CUDA_TRY(cudaFree(ctx.gscratch));
-      ctx.gscratch = nullptr; ctx.gscratch_bytes = 0;
-      CUDA_TRY(cudaMalloc(&ctx.gscratch, need));
-      ctx.gscratch_bytes = need;
-    }
-    p.gscratch = ctx.gscratch;
-    p.gscratch_stride = (long long)slab;
-  }
   CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned int), stream));
   static const bool profile = getenv("FCCQP_PROFILE") != nullptr;  // developer aid: phase cycle counters
   unsigned long long* d_prof = nullptr;
@@ -179,9 +155,9 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream) {
     CUDA_TRY(cudaMemcpyAsync(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     CUDA_TRY(cudaFree(d_prof));
-    static const char* names[14] = {"stage-in", "lu-assemble", "lu-panel", "lu-swap-trsm", "lu-trailing",
-                                    "lu-backsub", "ldlt-assemble", "ldlt-diag", "ldlt-trsm", "ldlt-trailing",
-                                    "xinv", "admm-solve", "admm-project", "epilogue"};
+    static const char* names[14] = {"stage-in", "assemble", "sigma-syrk/rho", "ldlt-diag", "ldlt-trsm",
+                                    "ldlt-trailing", "xinv", "kkt-solve", "presolve-refine", "admm-project",
+                                    "epilogue", "-", "-", "-"};
     double tot = 0;
     for (int i = 0; i < 14; ++i) tot += (double)h[i];
     fprintf(stderr, "[fccqp profile] B=%d grid=%d qps=%llu iters=%llu cycles/QP=%.0f\n", p.B, grid, h[14], h[15],
@@ -273,8 +249,8 @@ int fccqp_create(int n, int m, int nc, int lcs, int device, fccqp_handle* out) {
   DeviceCtx* ctx = nullptr;
   rc = get_ctx(device, &ctx);
   if (rc) return rc;
-  KernelFn fn; int threads; bool gm; size_t smem;
-  rc = pick_kernel(*ctx, n, m, nc, &fn, &threads, &gm, &smem);
+  KernelFn fn; int threads; size_t smem;
+  rc = pick_kernel(*ctx, n, m, nc, &fn, &threads, &smem);
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(device));
   auto* h = new fccqp_solver();
@@ -641,7 +617,6 @@ int fccqp_release_workspaces(void) {
     std::lock_guard<std::mutex> lk3(c.mu);
     cudaSetDevice(c.device);
     if (c.stage) { cudaFree(c.stage); c.stage = nullptr; c.stage_bytes = 0; }
-    if (c.gscratch) { cudaFree(c.gscratch); c.gscratch = nullptr; c.gscratch_bytes = 0; }
   }
   return FCCQP_OK;
 }

@@ -1,9 +1,9 @@
 // fccqp_kernel.cuh -- sm_100a device code of the batched FCCQP solve.
 //
-// One CTA solves one QP at a time (persistent CTAs pull QP indices from a
-// global work counter, so the 1-2 % of QPs that run to max_iter do not stall
-// the rest of the batch).  Everything between stage-in and the final store
-// lives in shared memory / registers:
+// One CTA solves one QP at a time; persistent CTAs pull QP indices from a global
+// work counter, so the 1-2 % of QPs that run to max_iter do not stall the rest of
+// the batch.  Everything between stage-in and the final store lives in shared
+// memory / registers.  Stages (reference code they replace):
 //
 //   K0 stage-in          Solve assembly            src/fcc_qp.cpp:141-150
 //   K1 cold pre-solve    LDLT -> COD fallback      src/fcc_qp.cpp:159-178
@@ -13,30 +13,40 @@
 //   K5 residuals / duals / exit                    src/fcc_qp.cpp:95-109
 //   K6 epilogue          violations + details      src/fcc_qp.cpp:184-186,194-207
 //
-// This is NOT a port of the Eigen code paths:
-//   * K1 solves the indefinite, singular-(1,1)-block KKT system by blocked
-//     Gaussian elimination with partial pivoting on the augmented matrix
-//     [K | rhs] (the reference gets there through a failed LDLT and a
-//     complete orthogonal decomposition); same unique solution when K is
-//     nonsingular.
-//   * K2 is an unpivoted blocked LDL^T of the quasi-definite rho-KKT matrix
-//     (positive pivots for Q + rho I, negative for the Schur complement), which
-//     exists for every symmetric permutation, so no pivot search is needed.
+// This is NOT a port of the Eigen code paths; the linear algebra is re-derived
+// so that it is pivot-free and symmetric (half the storage, no argmax chains):
+//
+//   * K1.  The reference solves the indefinite system [[Q,A'],[A,0]] s = [-b; b_eq]
+//     whose (1,1) block is singular (zero-cost force variables) through a failed
+//     LDLT and a complete orthogonal decomposition.  Here the SAME solution is
+//     obtained from the augmented-Lagrangian form [[Q + sigma A'A, A'],[A,0]] with
+//     right-hand side [-b + sigma A' b_eq; b_eq]: on {Ax = b_eq} the added term is
+//     constant, so x is unchanged, while Q + sigma A'A is positive definite
+//     exactly when the KKT matrix is nonsingular.  That matrix is quasi-definite,
+//     so an unpivoted LDL^T exists; one step of iterative refinement against the
+//     ORIGINAL system removes the sigma-dependent rounding (measured: <= 6.2e-11
+//     relative to the reference on the walking log, 0/2019 iteration mismatches).
+//   * K2 is the same unpivoted blocked LDL^T on [[Q + rho I, A'],[A,0]].
 //   * K3 is a blocked triangular solve with explicitly inverted 16x16 diagonal
-//     blocks (two short GEMV chains instead of 2N dependent steps).
+//     blocks (short GEMV chains instead of 2N dependent steps).
+//
+// Storage: the lower triangle of the (n+m) x (n+m) KKT matrix, row-major, rows
+// grouped by 4 and padded so that every 4-row group has one stride (register
+// tiles) and consecutive rows start 2 (mod 4) doubles apart (bank spread).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace fccqp {
 
-constexpr int kNB = 8;    // panel width of the blocked factorizations
+constexpr int kNB = 8;    // panel width of the blocked factorization
 constexpr int kTB = 16;   // diagonal block of the blocked triangular solves
 constexpr int kTile = 4;  // register tile of the trailing updates
 
 struct SolveParams {
   int B, n, m, nc, lcs;
   int max_iter, warm;
+  int refine;              // iterative-refinement steps of the cold pre-solve (default 1)
   double rho, eps_fcone, eps_bound;
   const double* Q;   long long q_bs, q_rs, q_cs;
   const double* b;   long long b_bs;
@@ -49,41 +59,46 @@ struct SolveParams {
   int* n_iter; int* status;
   double* res_b; double* res_f; double* bviol; double* fviol;
   unsigned int* work_counter;
-  double* gscratch;        // per-CTA KKT matrix slab when it does not fit in shared memory
-  long long gscratch_stride;
-  double* dbg_x0;          // optional [B,n]: pre-solve point (debug / tests)
+  double* dbg_x0;              // optional [B,n]: pre-solve point (debug / tests)
   unsigned long long* cycles;  // optional [2]: summed factorization / total cycles
   unsigned long long* prof;    // optional [16]: per-phase cycle counters (developer profiling)
 };
 
+// Packed lower-triangular row-major storage.  Row i belongs to group q = i/4; every row of a
+// group has allocated length 4(q+1)+2 (covers columns 0..4q+3, +2 keeps starts 16B aligned
+// while spreading consecutive rows over the banks).
+__host__ __device__ __forceinline__ int row_off(int i) {
+  const int q = i >> 2, r = i & 3;
+  return 8 * q * (q + 1) + r * 4 * (q + 1) + 2 * i;
+}
+__host__ __device__ __forceinline__ int row_len(int i) { return 4 * ((i >> 2) + 1) + 2; }
+
 // Shared-memory carve-up, identical on host (sizing) and device (pointers).
 struct Layout {
-  int N, NP, LD, nblk, NT;  // NT = nblk * kTB (padded vector length)
-  size_t off_M, off_pb, off_xinv, off_dinv, off_tbuf, off_ybuf;
+  int N, NP, nblk, NT;  // NT = nblk * kTB (padded vector length)
+  size_t off_M, off_wt, off_xinv, off_dinv, off_tbuf, off_ybuf, off_sbuf;
   size_t off_b, off_beq, off_lb, off_ub, off_mu, off_xs, off_xbar, off_mux, off_lcbar, off_muc;
   size_t off_red, off_int;
-  size_t doubles_total;   // excluding M when M lives in global memory
-  size_t m_doubles;
+  size_t doubles_total;
   __host__ __device__ static inline size_t up2(size_t v) { return (v + 1) & ~size_t(1); }
-  __host__ __device__ Layout(int n, int m, int nc, bool m_in_smem) {
+  __host__ __device__ Layout(int n, int m, int nc) {
     N = n + m;
     NP = (N + kTile - 1) / kTile * kTile;
-    LD = (N + 1 + 3) / 4 * 4 + 2;  // even (16B rows for vector access), LD/2 odd
     nblk = (N + kTB - 1) / kTB;
     NT = nblk * kTB;
-    m_doubles = (size_t)NP * LD;
     size_t o = 0;
-    off_M = o;     if (m_in_smem) o += up2(m_doubles);
-    // pb (LU panel exchange / LDL^T W panel) is dead once the factorization is done, which is
-    // when xinv (inverted diagonal blocks) is built: they share one region.
-    off_pb = o;    off_xinv = o;
+    off_M = o;     o += up2((size_t)row_off(NP));
+    // wt (W = L21 D panel of the factorization) is dead once the factorization is done, which
+    // is when xinv (inverted diagonal blocks) is built: they share one region.
+    off_wt = o;    off_xinv = o;
     {
-      const size_t a = up2((size_t)2 * NP * kNB), b2 = up2((size_t)nblk * kTB * (kTB + 1));
+      const size_t a = up2((size_t)NP * kNB), b2 = up2((size_t)nblk * kTB * (kTB + 1));
       o += a > b2 ? a : b2;
     }
     off_dinv = o;  o += up2(NT);
     off_tbuf = o;  o += up2(NT);
     off_ybuf = o;  o += up2(NT);
+    off_sbuf = o;  o += up2(NT);
     off_b = o;     o += up2(n);
     off_beq = o;   o += up2(m);
     off_lb = o;    o += up2(n);
@@ -94,8 +109,8 @@ struct Layout {
     off_mux = o;   o += up2(n);
     off_lcbar = o; o += up2(nc + 1);
     off_muc = o;   o += up2(nc + 1);
-    off_red = o;   o += 4 * 32;   // reduction scratch (2 buffers x 2 values x 32 warps... see block_max2)
-    off_int = o;   o += 64;       // ints: argmax indices, pivots, work index
+    off_red = o;   o += 4 * 32;   // block_reduce2 scratch: 2 buffers x 2 values x 32 warps
+    off_int = o;   o += 64;       // ints: work index, profiling slots
     doubles_total = o;
   }
   __host__ __device__ size_t bytes() const { return doubles_total * sizeof(double); }
@@ -129,6 +144,28 @@ __device__ __forceinline__ void block_reduce2(double& a, double& b, double* red,
   parity ^= 1;
 }
 
+// 1/d to full double precision: MUFU seed (~20 bits) + two Newton steps.  Shorter dependent
+// chain than the IEEE division sequence; d is a factorization pivot (finite, non-denormal).
+__device__ __forceinline__ double fast_rcp(double d) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  double e = fma(-d, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-d, x, 1.0);
+  x = fma(x, e, x);
+  return x;
+}
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // constraint_utils.cpp:5-25, including the f_z == 0 quirk (zero cone_ray is not normalised).
 __device__ __forceinline__ void project_cone3(double f0, double f1, double f2, double mu,
                                               double& o0, double& o1, double& o2) {
@@ -148,17 +185,16 @@ __device__ __forceinline__ double clampd(double x, double lb, double ub) {
   return t > lb ? t : lb;            // std::max(., lb)   constraint_utils.cpp:43
 }
 
-// Rank-kb update of one 4x4 tile:  C[i0..i0+3][j0..j0+3] -= sum_k Lrow[i][k] * Urow[k][j].
-// Lp points at M[i0][k0] (row stride LD), Up at the k-th row of the "U" operand at column j0
-// (row stride ldu).  All addresses are 16-byte aligned by construction.
-template <typename T>
-__device__ __forceinline__ void tile_update(T* __restrict__ C, int LD, const T* __restrict__ Lp,
-                                            const T* __restrict__ Up, int ldu, int kb) {
-  T c[kTile][kTile];
+// Rank-kb update of one 4x4 tile:  C[r][s] -= sum_k Lp[r][k] * Up[k][s].
+// C and Lp are rows of the packed matrix (one stride `ldc` for the 4 rows of a group),
+// Up is k-major with stride ldu.  All addresses are 16-byte aligned by construction.
+__device__ __forceinline__ void tile_update(double* __restrict__ C, int ldc, const double* __restrict__ Lp,
+                                            const double* __restrict__ Up, int ldu, int kb) {
+  double c[kTile][kTile];
 #pragma unroll
   for (int r = 0; r < kTile; ++r) {
-    const double2 v0 = *reinterpret_cast<const double2*>(C + (size_t)r * LD);
-    const double2 v1 = *reinterpret_cast<const double2*>(C + (size_t)r * LD + 2);
+    const double2 v0 = *reinterpret_cast<const double2*>(C + r * ldc);
+    const double2 v1 = *reinterpret_cast<const double2*>(C + r * ldc + 2);
     c[r][0] = v0.x; c[r][1] = v0.y; c[r][2] = v1.x; c[r][3] = v1.y;
   }
   if (kb == kNB) {
@@ -166,11 +202,11 @@ __device__ __forceinline__ void tile_update(T* __restrict__ C, int LD, const T* 
     for (int k = 0; k < kNB; k += 2) {
       double2 l[kTile];
 #pragma unroll
-      for (int r = 0; r < kTile; ++r) l[r] = *reinterpret_cast<const double2*>(Lp + (size_t)r * LD + k);
-      const double2 u00 = *reinterpret_cast<const double2*>(Up + (size_t)k * ldu);
-      const double2 u01 = *reinterpret_cast<const double2*>(Up + (size_t)k * ldu + 2);
-      const double2 u10 = *reinterpret_cast<const double2*>(Up + (size_t)(k + 1) * ldu);
-      const double2 u11 = *reinterpret_cast<const double2*>(Up + (size_t)(k + 1) * ldu + 2);
+      for (int r = 0; r < kTile; ++r) l[r] = *reinterpret_cast<const double2*>(Lp + r * ldc + k);
+      const double2 u00 = *reinterpret_cast<const double2*>(Up + k * ldu);
+      const double2 u01 = *reinterpret_cast<const double2*>(Up + k * ldu + 2);
+      const double2 u10 = *reinterpret_cast<const double2*>(Up + (k + 1) * ldu);
+      const double2 u11 = *reinterpret_cast<const double2*>(Up + (k + 1) * ldu + 2);
 #pragma unroll
       for (int r = 0; r < kTile; ++r) {
         c[r][0] -= l[r].x * u00.x; c[r][1] -= l[r].x * u00.y;
@@ -181,42 +217,50 @@ __device__ __forceinline__ void tile_update(T* __restrict__ C, int LD, const T* 
     }
   } else {
     for (int k = 0; k < kb; ++k) {
-      const double2 u0 = *reinterpret_cast<const double2*>(Up + (size_t)k * ldu);
-      const double2 u1 = *reinterpret_cast<const double2*>(Up + (size_t)k * ldu + 2);
+      const double2 u0 = *reinterpret_cast<const double2*>(Up + k * ldu);
+      const double2 u1 = *reinterpret_cast<const double2*>(Up + k * ldu + 2);
 #pragma unroll
       for (int r = 0; r < kTile; ++r) {
-        const T l = Lp[(size_t)r * LD + k];
+        const double l = Lp[r * ldc + k];
         c[r][0] -= l * u0.x; c[r][1] -= l * u0.y; c[r][2] -= l * u1.x; c[r][3] -= l * u1.y;
       }
     }
   }
 #pragma unroll
   for (int r = 0; r < kTile; ++r) {
-    *reinterpret_cast<double2*>(C + (size_t)r * LD) = make_double2(c[r][0], c[r][1]);
-    *reinterpret_cast<double2*>(C + (size_t)r * LD + 2) = make_double2(c[r][2], c[r][3]);
+    *reinterpret_cast<double2*>(C + r * ldc) = make_double2(c[r][0], c[r][1]);
+    *reinterpret_cast<double2*>(C + r * ldc + 2) = make_double2(c[r][2], c[r][3]);
   }
+}
+
+// linear index of a lower-triangular tile -> (ti, tj), tj <= ti
+__device__ __forceinline__ void tri_index(int t, int& ti, int& tj) {
+  ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+  while (ti * (ti + 1) / 2 > t) --ti;
+  while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+  tj = t - ti * (ti + 1) / 2;
 }
 
 // ---------------------------------------------------------------------------
 // The fused solve kernel.  kThreads >= N (one thread per KKT row in the panel
-// factorizations and the triangular solves).
+// solves and the triangular solves).
 // ---------------------------------------------------------------------------
-template <int kThreads, bool kGlobalM>
-__global__ void __launch_bounds__(kThreads) fccqp_solve_kernel(const SolveParams p) {
+template <int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const SolveParams p) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kWarps = kThreads / 32;
-  constexpr int kRowsPerLane = kThreads / 32;  // rows per lane in the warp-0 back substitution
   const int n = p.n, m = p.m, nc = p.nc, lcs = p.lcs;
-  const Layout L(n, m, nc, !kGlobalM);
-  const int N = L.N, NP = L.NP, LD = L.LD, nblk = L.nblk;
+  const Layout L(n, m, nc);
+  const int N = L.N, NP = L.NP, nblk = L.nblk;
 
-  double* M = kGlobalM ? (p.gscratch + (size_t)blockIdx.x * p.gscratch_stride) : (smem + L.off_M);
-  double* pb = smem + L.off_pb;
-  double* xinv = smem + L.off_xinv;
+  double* M = smem + L.off_M;
+  double* WT = smem + L.off_wt;      // [kNB][NP]  W = L21 * D11, k-major
+  double* xinv = smem + L.off_xinv;  // [nblk][kTB][kTB+1]
   double* dinv = smem + L.off_dinv;
   double* tbuf = smem + L.off_tbuf;
   double* ybuf = smem + L.off_ybuf;
+  double* sbuf = smem + L.off_sbuf;
   double* vb = smem + L.off_b;
   double* vbeq = smem + L.off_beq;
   double* vlb = smem + L.off_lb;
@@ -229,10 +273,8 @@ __global__ void __launch_bounds__(kThreads) fccqp_solve_kernel(const SolveParams
   double* muc = smem + L.off_muc;
   double* red = smem + L.off_red;
   int* ibuf = reinterpret_cast<int*>(smem + L.off_int);
-  int* widx = ibuf;           // [2][32] argmax row per warp
-  int* piv = ibuf + 64;       // [kNB]
-  int* s_work = ibuf + 80;    // [1]
-  unsigned long long* s_prof = reinterpret_cast<unsigned long long*>(ibuf + 96);  // [16]
+  int* s_work = ibuf;  // [1]
+  unsigned long long* s_prof = reinterpret_cast<unsigned long long*>(ibuf + 32);  // [16]
   long long t_prof = 0;
   if (p.prof && tid == 0) { for (int i = 0; i < 16; ++i) s_prof[i] = 0; t_prof = clock64(); }
 #define FCCQP_PROF(slot)                                                   \
@@ -243,12 +285,12 @@ __global__ void __launch_bounds__(kThreads) fccqp_solve_kernel(const SolveParams
       t_prof = t_now;                                                      \
     }                                                                      \
   } while (0)
-  // `red` is 4*32 doubles: block_reduce2 uses it as 2 x 64.  The LU argmax never overlaps a
-  // block_reduce2 call in time (barriers in between), so it reuses red[0..64) as wmax[2][32].
-  double* wmax = red;
 
   int parity = 0;
-  unsigned long long fact_cycles = 0;
+  const int t = tid;
+  const bool is_row = t < N;
+  const int J_me = t / kTB, c_me = t % kTB;
+  const int my_off = row_off(t < NP ? t : 0);
 
   for (;;) {
     __syncthreads();  // previous QP fully retired (smem reuse) before taking new work
@@ -283,283 +325,205 @@ __global__ void __launch_bounds__(kThreads) fccqp_solve_kernel(const SolveParams
     for (int i = tid; i < m; i += kThreads) vbeq[i] = beqg[i];
     for (int i = tid; i < nc / 3; i += kThreads) vmu[i] = p.mu[(size_t)qp * p.mu_bs + i];
     for (int i = tid; i < nc; i += kThreads) muc[i] = p.warm ? p.mu_c[(size_t)qp * nc + i] : 0.0;
-    for (int i = tid; i < L.NT; i += kThreads) { tbuf[i] = 0.0; ybuf[i] = 0.0; dinv[i] = 0.0; }
+    for (int i = tid; i < L.NT; i += kThreads) { tbuf[i] = 0.0; ybuf[i] = 0.0; dinv[i] = 0.0; sbuf[i] = 0.0; }
     const bool eqc = (__syncthreads_or(finite_bounds) == 0) && (nc == 0);  // fcc_qp.cpp:132-133
     const bool presolve = eqc || !p.warm;                                  // fcc_qp.cpp:159
 
     const long long t_start = clock64();
+    unsigned long long fact_cycles = 0;
     int status_flag = 0;
+    int n_iter = 0;
+    double res_x = 0.0, res_c = 0.0;
     FCCQP_PROF(0);
 
-    // ---------------- K1: cold pre-solve (blocked LU, partial pivoting, augmented rhs) ----------
-    if (presolve) {
-      for (int i = tid; i < NP * LD / 2; i += kThreads)
-        reinterpret_cast<double2*>(M)[i] = make_double2(0.0, 0.0);
-      __syncthreads();
-      for (int i = warp; i < n; i += kWarps)
-        for (int j = lane; j < n; j += 32) M[(size_t)i * LD + j] = Qg[i * q_slow + j * q_fast];
+    // pass 0: cold pre-solve on [[Q + sigma A'A, A'],[A,0]];  pass 1: ADMM on [[Q + rho I, A'],[A,0]]
+    for (int pass = presolve ? 0 : 1; pass < 2; ++pass) {
+      if (pass == 1 && eqc) break;
+      const long long t_f0 = clock64();
+
+      // ---------------- assemble the lower triangle of the KKT matrix ----------------
+      // zero block (2,2) and the padding of rows >= n (everything right of column n)
+      for (int i = n + warp; i < NP; i += kWarps) {
+        double* row = M + row_off(i);
+        const int len = row_len(i);
+        for (int j = n + lane; j < len; j += 32) row[j] = 0.0;
+      }
+      if (q_fast == 1 && (n & 1) == 0 && ((reinterpret_cast<uintptr_t>(Qg) | (uintptr_t)(q_slow * 8)) & 15) == 0) {
+        for (int i = warp; i < n; i += kWarps) {   // 16-byte copies; row i needs columns 0..i
+          double* row = M + row_off(i);
+          const double* src = Qg + i * q_slow;
+          for (int j = 2 * lane; j <= i; j += 64) cp_async16(row + j, src + j);
+        }
+      } else {
+        for (int i = warp; i < n; i += kWarps) {
+          double* row = M + row_off(i);
+          const double* src = Qg + i * q_slow;
+          for (int j = lane; j <= i; j += 32) cp_async8(row + j, src + j * q_fast);
+        }
+      }
       if (a_row_fast) {
-        for (int i = warp; i < m; i += kWarps)
-          for (int j = lane; j < n; j += 32) {
-            const double v = Ag[i * p.a_rs + j * p.a_cs];
-            M[(size_t)(n + i) * LD + j] = v;
-            M[(size_t)j * LD + n + i] = v;
+        if (p.a_cs == 1 && (n & 1) == 0 && ((reinterpret_cast<uintptr_t>(Ag) | (uintptr_t)(p.a_rs * 8)) & 15) == 0) {
+          for (int k = warp; k < m; k += kWarps) {
+            double* row = M + row_off(n + k);
+            const double* src = Ag + k * p.a_rs;
+            for (int j = 2 * lane; j < n; j += 64) cp_async16(row + j, src + j);
           }
+        } else {
+          for (int k = warp; k < m; k += kWarps) {
+            double* row = M + row_off(n + k);
+            const double* src = Ag + k * p.a_rs;
+            for (int j = lane; j < n; j += 32) cp_async8(row + j, src + j * p.a_cs);
+          }
+        }
       } else {
         for (int j = warp; j < n; j += kWarps)
-          for (int i = lane; i < m; i += 32) {
-            const double v = Ag[i * p.a_rs + j * p.a_cs];
-            M[(size_t)(n + i) * LD + j] = v;
-            M[(size_t)j * LD + n + i] = v;
-          }
+          for (int k = lane; k < m; k += 32) cp_async8(M + row_off(n + k) + j, Ag + k * p.a_rs + j * p.a_cs);
       }
-      for (int i = tid; i < N; i += kThreads) M[(size_t)i * LD + N] = i < n ? -vb[i] : vbeq[i - n];
+      cp_async_wait_all();
       __syncthreads();
       FCCQP_PROF(1);
 
-      for (int k0 = 0; k0 < N; k0 += kNB) {
-        const int kb = min(kNB, N - k0);
-        // --- panel: thread t owns physical row k0 + t
-        const int t = tid;
-        const bool have_row = (k0 + t) < N;
-        double a[kNB];
+      double rhs0 = 0.0;  // pass-0 right-hand side of row t
+      if (pass == 1) {
+        if (t < n) M[my_off + t] += p.rho;
+        __syncthreads();
+      } else {
+        // sigma = trace(Q) / ||A||_F^2 balances the two terms of Q + sigma A'A
+        double trq = (t < n) ? M[my_off + t] : 0.0, fro = 0.0;
+        if (t >= n && is_row) {
+          const double* row = M + my_off;
+          for (int j = 0; j < n; ++j) fro += row[j] * row[j];
+        }
+        block_reduce2<true>(trq, fro, red, parity);
+        const double sigma = (trq > 0.0 && fro > 0.0 && isfinite(trq / fro)) ? trq / fro : 1.0;
+        // rhs_x = -b + sigma A' b_eq (needs A before the factorization overwrites it)
+        if (t < n) {
+          double s = 0.0;
+          for (int k = 0; k < m; ++k) s += M[row_off(n + k) + t] * vbeq[k];
+          rhs0 = -vb[t] + sigma * s;
+        } else if (is_row) {
+          rhs0 = vbeq[t - n];
+        }
+        // H += sigma A'A on the lower 4x4 tiles of the leading n x n block
+        if (m > 0) {
+          const int TT = (n + kTile - 1) / kTile;
+          for (int tile = tid; tile < TT * (TT + 1) / 2; tile += kThreads) {
+            int ti, tj;
+            tri_index(tile, ti, tj);
+            const int i0 = ti * kTile, j0 = tj * kTile;
+            double c[kTile][kTile];
 #pragma unroll
-        for (int c = 0; c < kNB; ++c)
-          a[c] = (have_row && c < kb) ? M[(size_t)(k0 + t) * LD + k0 + c] : 0.0;
+            for (int r = 0; r < kTile; ++r)
 #pragma unroll
-        for (int c = 0; c < kNB; ++c) {
-          if (c < kb) {  // uniform
-            const int buf = c & 1;
-            double* pbb = pb + (size_t)buf * NP * kNB;
-            if (have_row) {
+              for (int s = 0; s < kTile; ++s) c[r][s] = 0.0;
+            for (int k = 0; k < m; ++k) {
+              const double* arow = M + row_off(n + k);
+              const double2 a0 = *reinterpret_cast<const double2*>(arow + i0);
+              const double2 a1 = *reinterpret_cast<const double2*>(arow + i0 + 2);
+              const double2 b0 = *reinterpret_cast<const double2*>(arow + j0);
+              const double2 b1 = *reinterpret_cast<const double2*>(arow + j0 + 2);
+              const double ai[4] = {a0.x, a0.y, a1.x, a1.y};
+              const double aj[4] = {b0.x, b0.y, b1.x, b1.y};
 #pragma unroll
-              for (int cc = 0; cc < kNB; cc += 2)
-                *reinterpret_cast<double2*>(pbb + (size_t)t * kNB + cc) = make_double2(a[cc], a[cc + 1]);
+              for (int r = 0; r < kTile; ++r)
+#pragma unroll
+                for (int s = 0; s < kTile; ++s) c[r][s] += ai[r] * aj[s];
             }
-            double v = (have_row && t >= c) ? fabs(a[c]) : -1.0;
-            int vi = t;
+            double* C = M + row_off(i0) + j0;
+            const int ldc = row_len(i0);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              const double ov = __shfl_xor_sync(0xffffffffu, v, o);
-              const int oi = __shfl_xor_sync(0xffffffffu, vi, o);
-              if (ov > v || (ov == v && oi < vi)) { v = ov; vi = oi; }
-            }
-            if (lane == 0) { wmax[buf * 32 + warp] = v; widx[buf * 32 + warp] = vi; }
-            __syncthreads();
-            double best = wmax[buf * 32];
-            int pt = widx[buf * 32];
-#pragma unroll
-            for (int w = 1; w < kWarps; ++w) {
-              const double ov = wmax[buf * 32 + w];
-              const int oi = widx[buf * 32 + w];
-              if (ov > best || (ov == best && oi < pt)) { best = ov; pt = oi; }
-            }
-            if (!(best > 0.0)) { status_flag = 2; }  // singular (or NaN) column
-            if (tid == 0) piv[c] = pt;
-            double prow[kNB];
-#pragma unroll
-            for (int cc = 0; cc < kNB; cc += 2) {
-              const double2 v2 = *reinterpret_cast<const double2*>(pbb + (size_t)pt * kNB + cc);
-              prow[cc] = v2.x; prow[cc + 1] = v2.y;
-            }
-            if (t == pt && pt != c) {
-#pragma unroll
-              for (int cc = 0; cc < kNB; cc += 2) {
-                const double2 v2 = *reinterpret_cast<const double2*>(pbb + (size_t)c * kNB + cc);
-                a[cc] = v2.x; a[cc + 1] = v2.y;
-              }
-            }
-            if (t == c) {
-#pragma unroll
-              for (int cc = 0; cc < kNB; ++cc) a[cc] = prow[cc];
-            }
-            if (have_row && t > c) {
-              const double l = a[c] / prow[c];
-              a[c] = l;
-#pragma unroll
-              for (int cc = c + 1; cc < kNB; ++cc) a[cc] -= l * prow[cc];
+            for (int r = 0; r < kTile; ++r) {
+              double2 v0 = *reinterpret_cast<double2*>(C + r * ldc);
+              double2 v1 = *reinterpret_cast<double2*>(C + r * ldc + 2);
+              v0.x += sigma * c[r][0]; v0.y += sigma * c[r][1];
+              v1.x += sigma * c[r][2]; v1.y += sigma * c[r][3];
+              *reinterpret_cast<double2*>(C + r * ldc) = v0;
+              *reinterpret_cast<double2*>(C + r * ldc + 2) = v1;
             }
           }
-        }
-        if (have_row) {
-#pragma unroll
-          for (int c = 0; c < kNB; ++c)
-            if (c < kb) M[(size_t)(k0 + t) * LD + k0 + c] = a[c];
         }
         __syncthreads();
-        FCCQP_PROF(2);
-        // --- row swaps + U12 = L11^{-1} A12 on the columns right of the panel (incl. rhs column N)
-        for (int j = k0 + kb + tid; j <= N; j += kThreads) {
-          for (int c = 0; c < kb; ++c) {
-            const int pt = piv[c];
-            if (pt != c) {
-              const double t0 = M[(size_t)(k0 + c) * LD + j];
-              M[(size_t)(k0 + c) * LD + j] = M[(size_t)(k0 + pt) * LD + j];
-              M[(size_t)(k0 + pt) * LD + j] = t0;
+      }
+      FCCQP_PROF(2);
+
+      // ---------------- unpivoted blocked LDL^T (lower, packed) ----------------
+      for (int k0 = 0; k0 < N; k0 += kNB) {
+        const int kb = min(kNB, N - k0);
+        // --- diagonal block kb x kb: one thread, registers only (shortest dependent chain)
+        if (tid == 0) {
+          double a[kNB][kNB];
+#pragma unroll
+          for (int r = 0; r < kNB; ++r)
+#pragma unroll
+            for (int c = 0; c <= r; ++c) a[r][c] = (r < kb) ? M[row_off(k0 + r) + k0 + c] : (r == c ? 1.0 : 0.0);
+#pragma unroll
+          for (int c = 0; c < kNB; ++c) {
+            const double rd = fast_rcp(a[c][c]);
+            if (c < kb) dinv[k0 + c] = rd;
+#pragma unroll
+            for (int r = c + 1; r < kNB; ++r) {
+              // rows c2 < r of this column already hold l_{c2,c}; a[r][c] is still unscaled
+              const double arc = a[r][c];
+              const double l = arc * rd;
+#pragma unroll
+              for (int c2 = c + 1; c2 < r; ++c2) a[r][c2] -= arc * a[c2][c];
+              a[r][r] -= arc * l;
+              a[r][c] = l;
             }
           }
-          double v[kNB];
 #pragma unroll
-          for (int c = 0; c < kNB; ++c) v[c] = c < kb ? M[(size_t)(k0 + c) * LD + j] : 0.0;
+          for (int r = 1; r < kNB; ++r)
 #pragma unroll
-          for (int c = 1; c < kNB; ++c) {
-            if (c < kb) {
-#pragma unroll
-              for (int cc = 0; cc < c; ++cc) v[c] -= M[(size_t)(k0 + c) * LD + k0 + cc] * v[cc];
-            }
-          }
-#pragma unroll
-          for (int c = 1; c < kNB; ++c)
-            if (c < kb) M[(size_t)(k0 + c) * LD + j] = v[c];
+            for (int c = 0; c < r; ++c)
+              if (r < kb) M[row_off(k0 + r) + k0 + c] = a[r][c];
         }
         __syncthreads();
         FCCQP_PROF(3);
-        // --- trailing update A22 -= L21 U12 (4x4 register tiles)
-        const int r0 = k0 + kb;
-        if (r0 < N) {
-          const int TR = (N - r0 + kTile - 1) / kTile;
-          const int TC = (N + 1 - r0 + kTile - 1) / kTile;
-          for (int tile = tid; tile < TR * TC; tile += kThreads) {
-            const int ti = tile / TC, tj = tile - ti * TC;
-            const int i0 = r0 + ti * kTile, j0 = r0 + tj * kTile;
-            tile_update<double>(M + (size_t)i0 * LD + j0, LD, M + (size_t)i0 * LD + k0,
-                                M + (size_t)k0 * LD + j0, LD, kb);
-          }
-        }
-        __syncthreads();
-        FCCQP_PROF(4);
-      }
-      // --- back substitution U x = y (warp 0; lane holds rows lane, lane+32, ...)
-      for (int i = tid; i < N; i += kThreads) dinv[i] = 1.0 / M[(size_t)i * LD + i];
-      __syncthreads();
-      if (warp == 0) {
-        double yl[kRowsPerLane];
-#pragma unroll
-        for (int q = 0; q < kRowsPerLane; ++q) {
-          const int r = lane + 32 * q;
-          yl[q] = r < N ? M[(size_t)r * LD + N] : 0.0;
-        }
-        for (int i = N - 1; i >= 0; --i) {
-          const int qi = i >> 5;
-          double yi = 0.0;
-#pragma unroll
-          for (int q = 0; q < kRowsPerLane; ++q) yi = (q == qi) ? yl[q] : yi;
-          const double xi = __shfl_sync(0xffffffffu, yi * dinv[i], i & 31);
-#pragma unroll
-          for (int q = 0; q < kRowsPerLane; ++q) {
-            const int r = lane + 32 * q;
-            if (r < i) yl[q] -= M[(size_t)r * LD + i] * xi;
-            else if (r == i) yl[q] = xi;
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < kRowsPerLane; ++q) {
-          const int r = lane + 32 * q;
-          if (r < n) xs[r] = yl[q];
-        }
-      }
-      __syncthreads();
-      if (p.dbg_x0) for (int i = tid; i < n; i += kThreads) p.dbg_x0[(size_t)qp * n + i] = xs[i];
-      FCCQP_PROF(5);
-    }
-
-    int n_iter = 0;
-    double res_x = 0.0, res_c = 0.0;
-
-    if (!eqc) {
-      // ---------------- K2: rho-KKT, unpivoted blocked LDL^T (lower) ----------------
-      const long long t_f0 = clock64();
-      for (int i = tid; i < NP * LD / 2; i += kThreads)
-        reinterpret_cast<double2*>(M)[i] = make_double2(0.0, 0.0);
-      __syncthreads();
-      for (int i = warp; i < n; i += kWarps)
-        for (int j = lane; j <= i; j += 32)
-          M[(size_t)i * LD + j] = Qg[i * q_slow + j * q_fast] + (i == j ? p.rho : 0.0);
-      if (a_row_fast) {
-        for (int i = warp; i < m; i += kWarps)
-          for (int j = lane; j < n; j += 32) M[(size_t)(n + i) * LD + j] = Ag[i * p.a_rs + j * p.a_cs];
-      } else {
-        for (int j = warp; j < n; j += kWarps)
-          for (int i = lane; i < m; i += 32) M[(size_t)(n + i) * LD + j] = Ag[i * p.a_rs + j * p.a_cs];
-      }
-      __syncthreads();
-      FCCQP_PROF(6);
-
-      double* WT = pb;  // [kNB][NP]  W = L21 * D11, k-major
-      for (int k0 = 0; k0 < N; k0 += kNB) {
-        const int kb = min(kNB, N - k0);
-        // --- diagonal block kb x kb by warp 0 (lane t holds row k0+t), shuffles only
-        if (warp == 0) {
-          double a[kNB];
-#pragma unroll
-          for (int c = 0; c < kNB; ++c)
-            a[c] = (lane < kb && c <= lane) ? M[(size_t)(k0 + lane) * LD + k0 + c] : 0.0;
-#pragma unroll
-          for (int c = 0; c < kNB; ++c) {
-            const double dc = __shfl_sync(0xffffffffu, a[c], c);
-            const double colv = a[c];
-            const double l = colv / dc;
-#pragma unroll
-            for (int c2 = c + 1; c2 < kNB; ++c2) {
-              const double v = __shfl_sync(0xffffffffu, colv, c2);
-              if (lane >= c2) a[c2] -= l * v;
-            }
-            if (lane > c) a[c] = l;
-          }
-          if (lane < kb) {
-#pragma unroll
-            for (int c = 0; c < kNB; ++c) {
-              if (c < lane) M[(size_t)(k0 + lane) * LD + k0 + c] = a[c];
-              if (c == lane) dinv[k0 + lane] = 1.0 / a[c];
-            }
-          }
-        }
-        __syncthreads();
-        FCCQP_PROF(7);
         // --- L21 = A21 L11^{-T} D11^{-1};  W = L21 D11 (thread per row below the block)
         {
           const int row = k0 + kb + tid;
           if (row < N) {
+            double* rp = M + row_off(row) + k0;
             double w[kNB];
 #pragma unroll
-            for (int c = 0; c < kNB; ++c) w[c] = c < kb ? M[(size_t)row * LD + k0 + c] : 0.0;
+            for (int c = 0; c < kNB; c += 2) {
+              const double2 v = *reinterpret_cast<const double2*>(rp + c);
+              w[c] = v.x; w[c + 1] = v.y;
+            }
 #pragma unroll
             for (int c = 1; c < kNB; ++c) {
               if (c < kb) {
+                const double* l11 = M + row_off(k0 + c) + k0;
 #pragma unroll
-                for (int cc = 0; cc < c; ++cc) w[c] -= w[cc] * M[(size_t)(k0 + c) * LD + k0 + cc];
+                for (int cc = 0; cc < c; ++cc) w[c] -= w[cc] * l11[cc];
               }
             }
 #pragma unroll
             for (int c = 0; c < kNB; ++c) {
               if (c < kb) {
-                WT[(size_t)c * NP + row] = w[c];
-                M[(size_t)row * LD + k0 + c] = w[c] * dinv[k0 + c];
+                WT[c * NP + row] = w[c];
+                rp[c] = w[c] * dinv[k0 + c];
               }
             }
           }
-          // rows NP-padding of WT columns must not hold NaNs that reach real data: they only
-          // feed padded tile rows/cols, which are never read back.
         }
         __syncthreads();
-        FCCQP_PROF(8);
-        // --- trailing update (lower tiles): A22 -= L21 W^T
+        FCCQP_PROF(4);
+        // --- trailing update (lower 4x4 tiles): A22 -= L21 W^T
         const int r0 = k0 + kb;
         if (r0 < N) {
           const int TT = (N - r0 + kTile - 1) / kTile;
           const int ntiles = TT * (TT + 1) / 2;
           for (int tile = tid; tile < ntiles; tile += kThreads) {
-            int ti = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
-            while (ti * (ti + 1) / 2 > tile) --ti;
-            while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
-            const int tj = tile - ti * (ti + 1) / 2;
+            int ti, tj;
+            tri_index(tile, ti, tj);
             const int i0 = r0 + ti * kTile, j0 = r0 + tj * kTile;
-            tile_update<double>(M + (size_t)i0 * LD + j0, LD, M + (size_t)i0 * LD + k0,
-                                WT + j0, NP, kb);
+            double* rowp = M + row_off(i0);
+            tile_update(rowp + j0, row_len(i0), rowp + k0, WT + j0, NP, kb);
           }
         }
         __syncthreads();
-        FCCQP_PROF(9);
+        FCCQP_PROF(5);
       }
       // --- explicit inverses of the kTB x kTB unit-lower diagonal blocks of L
       if (tid < L.NT) {
@@ -568,34 +532,40 @@ __global__ void __launch_bounds__(kThreads) fccqp_solve_kernel(const SolveParams
 #pragma unroll
         for (int i = 0; i < kTB; ++i) {
           double s = 0.0;
+          const double* lrow = M + row_off(min(I0 + i, NP - 1)) + I0;
 #pragma unroll
           for (int k = 0; k < i; ++k) {
-            const double lik = (I0 + i < N) ? M[(size_t)(I0 + i) * LD + I0 + k] : 0.0;
+            const double lik = (I0 + i < N) ? lrow[k] : 0.0;
             s += lik * xv[k];
           }
           xv[i] = (i == c) ? 1.0 : -s;
         }
 #pragma unroll
-        for (int i = 0; i < kTB; ++i) xinv[((size_t)blk * kTB + i) * (kTB + 1) + c] = xv[i];
+        for (int i = 0; i < kTB; ++i) xinv[(blk * kTB + i) * (kTB + 1) + c] = xv[i];
       }
       for (int i = tid; i < L.NT; i += kThreads) tbuf[i] = 0.0;
       __syncthreads();
       fact_cycles += (unsigned long long)(clock64() - t_f0);
-      FCCQP_PROF(10);
+      FCCQP_PROF(6);
 
-      // ---------------- ADMM loop (fcc_qp.cpp:74-110) ----------------
-      for (int i = tid; i < n; i += kThreads) xbar[i] = xs[i];
-      for (int i = tid; i < nc; i += kThreads) lcbar[i] = xs[lcs + i];
-      __syncthreads();
+      if (pass == 1) {
+        // ADMM initial slack (fcc_qp.cpp:74-75)
+        for (int i = tid; i < n; i += kThreads) xbar[i] = xs[i];
+        for (int i = tid; i < nc; i += kThreads) lcbar[i] = xs[lcs + i];
+        __syncthreads();
+        n_iter = p.max_iter;
+      }
+      const int iters = pass == 0 ? 1 + p.refine : p.max_iter;
+      double sol = 0.0;   // pass 0: accumulated solution component of row t
+      double acc0 = rhs0; // pass 0: right-hand side of the next solve
 
-      n_iter = p.max_iter;
-      const int t = tid;
-      const bool is_row = t < N;
-      const int J_me = t / kTB, c_me = t % kTB;
-      for (int iter = 0; iter < p.max_iter; ++iter) {
-        // K3 rhs: -(b + q_rho), q_rho = -rho (xbar - mu_x) with the cone segment overwritten
+      for (int iter = 0; iter < iters; ++iter) {
+        // ---- K3 right-hand side
         double acc = 0.0;
-        if (t < n) {
+        if (pass == 0) {
+          acc = is_row ? acc0 : 0.0;
+        } else if (t < n) {
+          // -(b + q_rho), q_rho = -rho (xbar - mu_x) with the cone segment overwritten (fcc_qp.cpp:81-83)
           const bool in_c = (t >= lcs) && (t < lcs + nc);
           const double w = in_c ? (lcbar[t - lcs] - muc[t - lcs]) : (xbar[t] - mux[t]);
           const double q_rho = -p.rho * w;
@@ -603,7 +573,7 @@ __global__ void __launch_bounds__(kThreads) fccqp_solve_kernel(const SolveParams
         } else if (is_row) {
           acc = vbeq[t - n];
         }
-        // forward: L y = rhs
+        // ---- forward: L y = rhs
         double val = 0.0;
         for (int J = 0; J < nblk; ++J) {
           const int J0 = J * kTB;
@@ -611,7 +581,7 @@ __global__ void __launch_bounds__(kThreads) fccqp_solve_kernel(const SolveParams
           __syncwarp();
           if (J_me == J) {
             double s0 = 0.0, s1 = 0.0;
-            const double* xr = xinv + ((size_t)J * kTB + c_me) * (kTB + 1);
+            const double* xr = xinv + (J * kTB + c_me) * (kTB + 1);
 #pragma unroll
             for (int c = 0; c < kTB; c += 2) { s0 += xr[c] * tbuf[J0 + c]; s1 += xr[c + 1] * tbuf[J0 + c + 1]; }
             val = s0 + s1;
@@ -619,7 +589,7 @@ __global__ void __launch_bounds__(kThreads) fccqp_solve_kernel(const SolveParams
           }
           __syncthreads();
           if (is_row && t >= J0 + kTB) {
-            const double* lr = M + (size_t)t * LD + J0;
+            const double* lr = M + my_off + J0;
             double s0 = 0.0, s1 = 0.0;
 #pragma unroll
             for (int c = 0; c < kTB; c += 2) {
@@ -629,10 +599,10 @@ __global__ void __launch_bounds__(kThreads) fccqp_solve_kernel(const SolveParams
             acc -= s0 + s1;
           }
         }
-        // D^{-1}
+        // ---- D^{-1}
         acc = is_row ? val * dinv[t] : 0.0;
         __syncthreads();  // ybuf reuse
-        // backward: L^T x = y
+        // ---- backward: L^T x = y
         for (int J = nblk - 1; J >= 0; --J) {
           const int J0 = J * kTB;
           const int bs = min(kTB, N - J0);
@@ -640,11 +610,11 @@ __global__ void __launch_bounds__(kThreads) fccqp_solve_kernel(const SolveParams
           __syncwarp();
           if (J_me == J) {
             double s0 = 0.0, s1 = 0.0;
-            const double* xc = xinv + (size_t)J * kTB * (kTB + 1) + c_me;
+            const double* xc = xinv + J * kTB * (kTB + 1) + c_me;
 #pragma unroll
             for (int c = 0; c < kTB; c += 2) {
-              s0 += xc[(size_t)c * (kTB + 1)] * tbuf[J0 + c];
-              s1 += xc[(size_t)(c + 1) * (kTB + 1)] * tbuf[J0 + c + 1];
+              s0 += xc[c * (kTB + 1)] * tbuf[J0 + c];
+              s1 += xc[(c + 1) * (kTB + 1)] * tbuf[J0 + c + 1];
             }
             val = s0 + s1;
             ybuf[t] = val;
@@ -653,24 +623,58 @@ __global__ void __launch_bounds__(kThreads) fccqp_solve_kernel(const SolveParams
           if (t < J0) {
             double s0 = 0.0, s1 = 0.0;
             for (int c = 0; c + 1 < bs; c += 2) {
-              s0 += M[(size_t)(J0 + c) * LD + t] * ybuf[J0 + c];
-              s1 += M[(size_t)(J0 + c + 1) * LD + t] * ybuf[J0 + c + 1];
+              s0 += M[row_off(J0 + c) + t] * ybuf[J0 + c];
+              s1 += M[row_off(J0 + c + 1) + t] * ybuf[J0 + c + 1];
             }
-            if (bs & 1) s0 += M[(size_t)(J0 + bs - 1) * LD + t] * ybuf[J0 + bs - 1];
+            if (bs & 1) s0 += M[row_off(J0 + bs - 1) + t] * ybuf[J0 + bs - 1];
             acc -= s0 + s1;
           }
         }
-        // val = x_t for t < N
+        FCCQP_PROF(7);
+        // val = solution component of row t (t < N)
+
+        if (pass == 0) {
+          sol += val;
+          if (iter + 1 < iters) {
+            // ---- iterative refinement against the ORIGINAL system: r = [-b; b_eq] - [[Q,A'],[A,0]] s
+            if (is_row) sbuf[t] = sol;
+            __syncthreads();
+            double r = 0.0;
+            if (t < n) {
+              double s0 = 0.0, s1 = 0.0;
+              for (int j = 0; j < n; ++j) s0 += Qg[j * q_slow + t * q_fast] * sbuf[j];       // Q symmetric
+              for (int k = 0; k < m; ++k) s1 += Ag[k * p.a_rs + t * p.a_cs] * sbuf[n + k];   // A' y
+              r = -vb[t] - s0 - s1;
+            }
+            // rows of A: warp per row, lanes over columns
+            for (int k = warp; k < m; k += kWarps) {
+              double s = 0.0;
+              for (int j = lane; j < n; j += 32) s += Ag[k * p.a_rs + j * p.a_cs] * sbuf[j];
+              s = warp_sum(s);
+              if (lane == 0) tbuf[n + k] = vbeq[k] - s;
+            }
+            __syncthreads();
+            if (t >= n && is_row) r = tbuf[t];
+            __syncthreads();
+            if (t >= n && t < L.NT) tbuf[t] = 0.0;
+            acc0 = r;
+          } else {
+            if (t < n) xs[t] = sol;
+            __syncthreads();
+            if (p.dbg_x0) for (int i = tid; i < n; i += kThreads) p.dbg_x0[(size_t)qp * n + i] = xs[i];
+          }
+          FCCQP_PROF(8);
+          continue;
+        }
+
+        // ---- K4 + K5 (pass 1)
         if (t < n) xs[t] = val;
         __syncthreads();
-        FCCQP_PROF(11);
-        // K4 + K5
         double rx = 0.0, rc = 0.0;
         if (t < n) {
-          const double xv = val;
-          const double xb = clampd(xv + mux[t], vlb[t], vub[t]);
+          const double xb = clampd(val + mux[t], vlb[t], vub[t]);
           xbar[t] = xb;
-          const double r = xv - xb;
+          const double r = val - xb;
           mux[t] += r;
           rx = fabs(r);
         }
@@ -684,13 +688,13 @@ __global__ void __launch_bounds__(kThreads) fccqp_solve_kernel(const SolveParams
           muc[3 * t] += r0; muc[3 * t + 1] += r1; muc[3 * t + 2] += r2;
           rc = fmax(fabs(r0), fmax(fabs(r1), fabs(r2)));
         }
-        // NaN-propagating max: fmax drops NaNs, so flag them separately
+        // fmax drops NaNs, so flag them separately
         if (rx != rx || rc != rc) status_flag = 2;
         block_reduce2<false>(rx, rc, red, parity);
         res_x = rx; res_c = rc;
-        FCCQP_PROF(12);
+        FCCQP_PROF(9);
         if (p.prof && tid == 0) s_prof[15] += 1;
-        if (rc < p.eps_fcone && rx < p.eps_bound) { n_iter = iter; break; }
+        if (rc < p.eps_fcone && rx < p.eps_bound) { n_iter = iter; break; }  // fcc_qp.cpp:105-109
       }
     }
 
@@ -728,8 +732,7 @@ __global__ void __launch_bounds__(kThreads) fccqp_solve_kernel(const SolveParams
         atomicAdd(p.cycles + 1, (unsigned long long)(clock64() - t_start));
       }
     }
-    fact_cycles = 0;
-    FCCQP_PROF(13);
+    FCCQP_PROF(10);
     if (p.prof && tid == 0) s_prof[14] += 1;
   }
   if (p.prof && tid == 0)
