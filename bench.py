@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""Headline benchmark: QPs solved per second at batch 2^16 per GPU (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one cold batched Solve of 65 536 QPs per GPU: the 2019 logged Cassie walking QPs
+(tests/golden/walking_log_compact.npz) tiled to 2^16, solver settings of
+fcc_qp_test.py:78-83 (rho 5e-5, eps 1e-6, max_iter 100).  Weak scaling: every rank owns its own
+2^16 QPs, no data-path collective.
+
+`value`  : whole-job QP/s with inputs resident in HBM, CUDA events on the launching stream.
+`e2e`    : the same through the public API (FCCQPBatch.Solve on pinned HOST arrays -> C ABI),
+           host->device and device->host copies inside the timed region.
+`--impl reference` times the reference's own CPU implementation (oracle/_ref: the unmodified
+reference compiled from /root/reference; else the C restatement) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from fcc_qp_b200 import sharding  # noqa: E402
+from fcc_qp_b200.logdata import load_walking_log  # noqa: E402
+
+BATCH_PER_GPU = 1 << 16
+OPTS = dict(max_iter=100, rho=5e-5, eps_fcone=1e-6, eps_bound=1e-6)  # fcc_qp_test.py:78-83
+METRIC = "qps_solved_per_sec_batch_65536_cold"
+WORKLOAD = "walking_log_tiled_to_2^16_per_gpu_cold_fp64"
+
+
+def algorithmic_bytes_per_qp(n, m, nc):
+    """FP64 bytes in = 8(n^2 + mn + 3n + m + nc/3), out = 8n + 40."""
+    return 8 * (n * n + m * n + 3 * n + m + nc // 3) + 8 * n + 40
+
+
+def algorithmic_flops_per_qp(n, m, iters_executed, cold=True):
+    """(1/3)N^3 per factorization (x2 cold) + 2N^2 per executed iteration."""
+    N = n + m
+    return (2 if cold else 1) * N ** 3 / 3.0 + 2.0 * N * N * iters_executed
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"  # B200_PROFILING.md fallback
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(qp, sample, nthreads=None, kind=None):
+    """Cold all-core CPU solve of the first `sample` QPs; returns (qps_per_s, cores, kind, seconds)."""
+    from oracle import Oracle, colmajor_stack, have
+    if kind is None:
+        kind = "reference" if have("ref") else "port"
+    orc = Oracle("ref" if kind == "reference" else "port")
+    cores = nthreads or orc.hardware_threads()
+    sub = qp.take(np.arange(sample) % qp.batch)
+    prepared = (colmajor_stack(sub.Q), colmajor_stack(sub.A_eq))  # layout prep outside the timed region
+    r = orc.solve_batch(sub, warm_mode=0, nthreads=cores, prepared=prepared, **OPTS)
+    return sample / r["elapsed"], cores, kind, r["elapsed"]
+
+
+def run_reference_arm(args):
+    rank, _, world = sharding.env_rank_world()
+    if rank != 0:
+        return 0
+    qp = load_walking_log()
+    # calibrate, then size each step to a few seconds of all-core CPU work
+    rate, cores, kind, _ = cpu_reference_run(qp, 2019)
+    sample = int(min(BATCH_PER_GPU, max(2019, rate * 3.0)))
+    for _ in range(args.warmup):
+        cpu_reference_run(qp, min(sample, 4038))
+    t_tot, n_tot = 0.0, 0
+    for _ in range(args.steps):
+        r, cores, kind, secs = cpu_reference_run(qp, sample)
+        t_tot += secs; n_tot += sample
+    value = n_tot / t_tot
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "QP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "reference walking log (2019 logged Cassie QPs) tiled",
+        "config": {"workload": WORKLOAD, "sample_qps_per_step": sample, "solver": OPTS,
+                   "note": "CPU reference, one FCCQP object per thread, cold solves"},
+        "cpu_baseline": {"value": value, "unit": "QP/s", "cores": cores, "kind": kind,
+                         "sample": f"first {sample} QPs of the tiled log per step, cold, all host threads"},
+        "e2e": {"value": value, "unit": "QP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours(args):
+    import torch
+    from fcc_qp_b200 import _native as nat
+    from fcc_qp_b200.batch import FCCQPBatch, FCCQPOptionsB
+
+    rank, local_rank, world = sharding.init_process_group()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the solver has no CPU path (use --impl reference)")
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    log = load_walking_log()
+    n, m, nc, lcs = log.n, log.m, log.nc, log.lambda_c_start
+    B = BATCH_PER_GPU
+    # every rank tiles the log from a different offset so that shards are not byte-identical
+    idx = (np.arange(B) + rank * 997) % log.batch
+    qp = log.take(idx)
+    host = [qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub]
+    dev_args = [torch.as_tensor(a, device=dev) for a in host]
+    in_bytes = sum(a.nbytes for a in host)
+
+    solver = FCCQPBatch(n, m, nc, lcs, device=local_rank)
+    solver.set_options(FCCQPOptionsB(**OPTS))
+    solver.time_kernel = False
+    stream = torch.cuda.current_stream(dev)
+
+    # ---------------- device-resident throughput (`value`) ----------------
+    for _ in range(max(args.warmup, 3)):
+        solver.Solve(*dev_args)
+    torch.cuda.synchronize(dev)
+    sharding.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = nat.lib().fccqp_kernel_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    torch.cuda.synchronize(dev)
+    ev[0].record(stream)
+    for k in range(args.steps):
+        solver.Solve(*dev_args)          # asynchronous launch on the current torch stream
+        ev[k + 1].record(stream)
+    torch.cuda.synchronize(dev)
+    sharding.barrier()
+    launches = nat.lib().fccqp_kernel_launch_count() - launches0
+    step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    total_s = sharding.max_over_ranks(ev[0].elapsed_time(ev[-1]) * 1e-3, dev)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / total_s
+    sol = solver.GetSolution()
+    n_iter = sol.details.n_iter.cpu().numpy()
+    status = sol.details.solve_status.cpu().numpy()
+    iters_executed = float(np.where(n_iter == OPTS["max_iter"], OPTS["max_iter"], n_iter + 1).mean())
+    info = nat.last_launch_info()
+
+    # ---------------- end to end through the public API on pinned host arrays (`e2e`) ----------
+    pinned = [torch.from_numpy(a).pin_memory().numpy() for a in host]
+    hsolver = FCCQPBatch(n, m, nc, lcs, device=local_rank)
+    hsolver.set_options(FCCQPOptionsB(**OPTS))
+    for _ in range(2):
+        hsolver.Solve(*pinned)
+    torch.cuda.synchronize(dev)
+    sharding.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        hsolver.Solve(*pinned)           # H2D + solve + D2H, synchronous
+        zsum = float(hsolver.GetSolution().z[0, 0])
+    torch.cuda.synchronize(dev)
+    e2e_s = sharding.max_over_ranks(time.perf_counter() - t0, dev)
+    sharding.barrier()
+    e2e_value = world * B * args.steps / e2e_s
+    out_bytes = B * (8 * n * 2 + 8 * nc + 4 * 2 + 8 * 4)  # z/x, mu_x, mu_c, n_iter, status, 4 scalars
+
+    if rank != 0:
+        return 0
+
+    # ---------------- roofline + CPU baseline (rank 0) ----------------
+    peaks, peak_kind = measured_peaks()
+    kern_s = float(np.mean(step_ms)) * 1e-3
+    alg_bytes = algorithmic_bytes_per_qp(n, m, nc) * B
+    achieved = alg_bytes / kern_s / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("bytes_per_launch_at_batch_65536")
+        except Exception:
+            traffic = None
+    flops = algorithmic_flops_per_qp(n, m, iters_executed, cold=True) * B
+    fp64_peak = 148 * 64 * 2 * 1.965e9 / 1e12  # nominal vector FP64: SMs x lanes x 2 x max clock
+    line = {
+        "metric": METRIC, "value": value, "unit": "QP/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "reference walking log (2019 logged Cassie QPs, n=60 m=38 nc=12) tiled to 2^16 per GPU",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "n": n, "m": m, "nc": nc, "solver": OPTS,
+                   "l2": "inputs (3.2 GB per step) exceed the 126 MB L2; no flush needed",
+                   "launch": info, "mean_iterations_executed": iters_executed,
+                   "status_counts": {str(k): int(v) for k, v in zip(*np.unique(status, return_counts=True))}},
+        "e2e": {"value": e2e_value, "unit": "QP/s", "h2d_bytes_per_step": int(in_bytes),
+                "d2h_bytes_per_step": int(out_bytes), "ms_per_step": 1e3 * e2e_s / args.steps,
+                "api": "FCCQPBatch.Solve(numpy pinned) -> fccqp_batch_solve(FCCQP_MEM_HOST)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                     "frac": achieved / peaks.get("hbm_gbs"), "traffic": traffic, "peak_source": peak_kind,
+                     "kernel": "fccqp_solve_kernel", "kernel_ms": 1e3 * kern_s,
+                     "note": "latency/FP64-bound kernel: HBM fraction is low by construction; see fp64"},
+        "roofline_fp64": {"achieved_tflops": flops / kern_s / 1e12, "peak_tflops_nominal": fp64_peak,
+                          "frac": flops / kern_s / 1e12 / fp64_peak,
+                          "flops_model": "SURVEY 8d: 2 x N^3/3 + 2 N^2 x iterations_executed per cold QP"},
+        "latency": {"p50_ms_per_batch_launch": float(np.median(step_ms))},
+    }
+    # p50 latency of one warm Solve through the drop-in FCCQP object (fcc_qp_test.py loop)
+    try:
+        from fcc_qp_b200 import FCCQP, FCCQPOptions
+        s1 = FCCQP(n, m, nc, lcs)
+        o = FCCQPOptions(); o.max_iter, o.rho, o.eps_fcone, o.eps_bound = (OPTS[k] for k in ("max_iter", "rho", "eps_fcone", "eps_bound"))
+        s1.set_options(o)
+        lat = []
+        for i in range(200):
+            s1.set_warm_start(i > 0)
+            q = log.qp(i)
+            t1 = time.perf_counter()
+            s1.Solve(q["Q"], q["b"], q["A_eq"], q["b_eq"], q["friction_coeffs"], q["lb"], q["ub"])
+            s1.GetSolution()
+            lat.append(time.perf_counter() - t1)
+        line["latency"]["p50_us_single_solve_dropin"] = float(np.median(lat[20:]) * 1e6)
+    except Exception as e:  # pragma: no cover
+        line["latency"]["single_solve_error"] = repr(e)
+    if world == 1:
+        try:
+            rate, cores, kind, secs = cpu_reference_run(log, 2019)
+            sample = int(min(B, max(2019, rate * 12.0)))
+            rate, cores, kind, secs = cpu_reference_run(log, sample)
+            line["cpu_baseline"] = {"value": rate, "unit": "QP/s", "cores": cores, "kind": kind,
+                                    "sample": f"first {sample} QPs of the same tiled log, cold, {secs:.1f} s"}
+        except Exception as e:  # pragma: no cover
+            line["cpu_baseline"] = {"value": None, "unit": "QP/s", "cores": 0, "kind": "port", "sample": repr(e)}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

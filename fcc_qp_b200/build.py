@@ -2,7 +2,7 @@
 
 * ``libfccqp_b200.so``  -- CUDA kernels + C ABI (``csrc/fccqp_capi.cu``), nvcc, sm_100a only.
 * ``fcc_qp_solver*.so`` -- pybind11 module with the reference's class names
-  (``csrc/pybind_module.cpp`` over ``csrc/fcc_qp.cpp``), g++, links the C ABI library.
+  (``csrc/pybind_module.cpp`` over the header-only ``include/fcc_qp.hpp``), g++, links the C ABI library.
 
 Everything lands next to this file so that it travels with the repository
 snapshot to the GPU box; nothing is JIT-compiled at import time.
@@ -51,14 +51,14 @@ def build_cuda(force=False, verbose=False, extra=()):
 def build_pybind(force=False, verbose=False):
     import pybind11
     tgt = pybind_target()
-    srcs = [os.path.join(CSRC, f) for f in ("pybind_module.cpp", "fcc_qp.cpp", "fcc_qp.hpp")] + \
-           [os.path.join(ROOT, "include", "fccqp.h"), LIB]
+    srcs = [os.path.join(CSRC, "pybind_module.cpp"), os.path.join(ROOT, "include", "fcc_qp.hpp"),
+            os.path.join(ROOT, "include", "fccqp.h"), LIB]
     if force or _stale(tgt, srcs):
         cxx = os.environ.get("CXX", "g++")
         _run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden",
               "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"],
               "-I", os.path.join(ROOT, "include"),
-              os.path.join(CSRC, "pybind_module.cpp"), os.path.join(CSRC, "fcc_qp.cpp"),
+              os.path.join(CSRC, "pybind_module.cpp"),
               "-L", HERE, "-lfccqp_b200", "-Wl,-rpath,$ORIGIN", "-o", tgt], verbose)
     return tgt
 

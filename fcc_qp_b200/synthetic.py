@@ -1,0 +1,151 @@
+"""Synthetic whole-body-control QPs of the shapes named in BASELINE.json.
+
+The generator mirrors the structure of the logged Cassie OSC QPs (SURVEY.md 8d;
+``fccqp.pdf`` section 4): decision vector ``x = [vdot(nv) u(nu) lambda_h(nh)
+lambda_c(nc) eps(ne)]``, cost on task-space acceleration error plus small
+regularisation, dynamics / holonomic / soft-contact equality rows, torque box
+bounds and one Coulomb cone per 3-D contact force.
+
+    Q = blkdiag(Jy' W Jy + 1e-5 I, 1e-4 I, 0, 1e-6 I, 80 I)
+    b = [-Jy' W ydd_cmd; 0]
+    A = [[M, -B, -Jh', -Jc', 0], [Jh, 0, 0, 0, 0], [Jc, 0, 0, 0, I]]
+    b_eq = [-C; -gamma_h; -gamma_c]
+
+All arrays are float64, C-contiguous and deterministic in ``seed``.
+"""
+from __future__ import annotations
+
+import dataclasses
+
+import numpy as np
+
+from .logdata import QPBatch
+
+
+@dataclasses.dataclass(frozen=True)
+class Shape:
+    name: str
+    nv: int
+    nu: int
+    nh: int
+    nc: int
+    seed: int
+    joint_scale: float = 0.1  # size of the joint columns of the contact Jacobian (tunes how often cones bind)
+
+    @property
+    def ne(self) -> int:
+        return self.nc
+
+    @property
+    def n(self) -> int:
+        return self.nv + self.nu + self.nh + self.nc + self.ne
+
+    @property
+    def m(self) -> int:
+        return self.nv + self.nh + self.ne
+
+    @property
+    def lambda_c_start(self) -> int:
+        return self.nv + self.nu + self.nh
+
+
+# SURVEY.md 8d configs 3, 4, 5 (+ the Cassie shape of the walking log for reference)
+HUMANOID = Shape("humanoid", nv=36, nu=30, nh=0, nc=12, seed=20241, joint_scale=0.1)        # n=90  m=48 N=138
+QUADRUPED = Shape("quadruped", nv=18, nu=12, nh=0, nc=12, seed=20242, joint_scale=0.05)      # n=54  m=30 N=84
+MULTICONTACT = Shape("multicontact", nv=36, nu=30, nh=6, nc=24, seed=20243, joint_scale=0.03)  # n=120 m=66 N=186
+CASSIE_LIKE = Shape("cassie_like", nv=22, nu=10, nh=6, nc=12, seed=20240, joint_scale=0.05)  # n=60  m=38 N=98
+SHAPES = {s.name: s for s in (HUMANOID, QUADRUPED, MULTICONTACT, CASSIE_LIKE)}
+
+
+def make_batch(shape: Shape, batch: int, seed: int | None = None, u_max: float = 300.0,
+               ydd_sigma: float = 1.0, bias_sigma: float = 1.0, joint_scale: float | None = None,
+               height: float = 0.75, weight: float = 300.0) -> QPBatch:
+    """B synthetic QPs of ``shape``.  Defaults are tuned (against the reference solver, rho=5e-5,
+    eps=1e-6, max_iter=100) so that most pre-solve points are feasible, 15-30 % of the QPs need
+    ADMM iterations and a few per cent run to max_iter -- the mix seen on the walking log."""
+    joint_scale = shape.joint_scale if joint_scale is None else joint_scale
+    rng = np.random.default_rng(shape.seed if seed is None else seed)
+    B, nv, nu, nh, nc, ne = batch, shape.nv, shape.nu, shape.nh, shape.nc, shape.ne
+    n, m, ncon = shape.n, shape.m, nc // 3
+    ny = max(nv - 4, 1)
+
+    G = rng.standard_normal((B, nv, nv))
+    Mass = G @ G.transpose(0, 2, 1) / nv
+    Mass[:, np.arange(nv), np.arange(nv)] += rng.uniform(0.05, 3.0, (B, nv))
+    Bsel = np.zeros((nv, nu))
+    Bsel[nv - nu:, :] = np.eye(nu)  # floating base (first nv - nu dofs) is unactuated
+
+    # Point contacts around the floating base: J_c = [I3, -[p]x, J_joints].  With the gravity-like
+    # bias below, the (almost cost-free) contact forces mostly come out inside their cones, like
+    # the logged walking QPs; larger commands / fewer stance feet make the cones active.
+    # Contacts sit at the corners of a support rectangle (two rings when ncon > 4); a QP is in
+    # full support or on one diagonal pair, so the weight can be carried by normal forces alone.
+    corner = np.array([[1.0, 1.0], [1.0, -1.0], [-1.0, 1.0], [-1.0, -1.0]])
+    pos = np.zeros((B, ncon, 3))
+    for c in range(ncon):
+        ring = 1.0 + 0.5 * (c // 4)
+        pos[:, c, :2] = corner[c % 4] * np.array([0.25, 0.15]) * ring + rng.uniform(-0.03, 0.03, (B, 2))
+    pos[:, :, 2] = -rng.uniform(0.8, 1.2, (B, ncon)) * height
+    pattern = rng.integers(0, 4, B)  # 0,1: all feet; 2: diagonal {0,3}; 3: diagonal {1,2}
+    stance = np.ones((B, ncon), dtype=bool)
+    for c in range(ncon):
+        stance[:, c] &= ~((pattern == 2) & (c % 4 in (1, 2))) & ~((pattern == 3) & (c % 4 in (0, 3)))
+    Jc = np.zeros((B, ncon, 3, nv))
+    Jc[:, :, np.arange(3), np.arange(3)] = 1.0
+    px, py, pz = pos[..., 0], pos[..., 1], pos[..., 2]
+    zero = np.zeros_like(px)
+    skew = np.stack([np.stack([zero, -pz, py], -1), np.stack([pz, zero, -px], -1),
+                     np.stack([-py, px, zero], -1)], -2)  # [p]x
+    Jc[:, :, :, 3:6] = -skew
+    if nv > 6:
+        Jj = rng.standard_normal((B, ncon, 3, nv - 6)) * joint_scale
+        Jj *= rng.random((B, ncon, 3, nv - 6)) < 0.5
+        Jc[:, :, :, 6:] = Jj
+    Jc = Jc.reshape(B, nc, nv) * np.repeat(stance, 3, axis=1)[:, :, None]
+    Jh = rng.standard_normal((B, nh, nv)) * 0.5 if nh else np.zeros((B, 0, nv))
+    if nh:
+        Jh[:, :, :6] = 0.0  # hand/loop constraints act on joints only
+
+    Jy = rng.standard_normal((B, ny, nv))
+    W = rng.uniform(0.1, 20.0, (B, ny))
+    ydd = rng.standard_normal((B, ny)) * ydd_sigma
+
+    Q = np.zeros((B, n, n))
+    Q[:, :nv, :nv] = np.einsum("bki,bk,bkj->bij", Jy, W, Jy)
+    d = np.concatenate([np.full(nv, 1e-5), np.full(nu, 1e-4), np.zeros(nh), np.full(nc, 1e-6), np.full(ne, 80.0)])
+    Q[:, np.arange(n), np.arange(n)] += d
+    Q = 0.5 * (Q + Q.transpose(0, 2, 1))
+    b = np.zeros((B, n))
+    b[:, :nv] = -np.einsum("bki,bk->bi", Jy, W * ydd)
+
+    o_u, o_h, o_c, o_e = nv, nv + nu, nv + nu + nh, nv + nu + nh + nc
+    A = np.zeros((B, m, n))
+    A[:, :nv, :nv] = Mass
+    A[:, :nv, o_u:o_h] = -Bsel
+    if nh:
+        A[:, :nv, o_h:o_c] = -Jh.transpose(0, 2, 1)
+        A[:, nv:nv + nh, :nv] = Jh
+    A[:, :nv, o_c:o_e] = -Jc.transpose(0, 2, 1)
+    A[:, nv + nh:, :nv] = Jc
+    A[:, nv + nh:, o_e:] = np.eye(ne)
+
+    Cg = rng.standard_normal((B, nv)) * bias_sigma
+    Cg[:, :6] *= 0.25
+    Cg[:, 2] += weight  # weight on the vertical floating-base coordinate
+    beq = np.concatenate([-Cg, -rng.standard_normal((B, nh)) * 0.1, -rng.standard_normal((B, ne)) * 0.1], axis=1)
+
+    lb = np.full((B, n), -np.inf)
+    ub = np.full((B, n), np.inf)
+    lb[:, o_u:o_h] = -u_max
+    ub[:, o_u:o_h] = u_max
+    mu = rng.uniform(0.4, 1.0, (B, ncon))
+    c = np.ascontiguousarray
+    return QPBatch(n, m, nc, shape.lambda_c_start, c(Q), c(b), c(A), c(beq), c(mu), c(lb), c(ub))
+
+
+def random_walk(qp: QPBatch, rng: np.random.Generator, sigma: float = 0.02) -> QPBatch:
+    """Next step of a sequential warm-started scenario: b and b_eq
+    take a 2 % multiplicative random-walk step, everything else is carried over."""
+    b = qp.b * (1.0 + sigma * rng.standard_normal(qp.b.shape))
+    beq = qp.b_eq * (1.0 + sigma * rng.standard_normal(qp.b_eq.shape))
+    return dataclasses.replace(qp, b=np.ascontiguousarray(b), b_eq=np.ascontiguousarray(beq))

@@ -1,0 +1,177 @@
+// fcc_qp.hpp -- C++ host class with the reference's surface, over the CUDA C ABI.
+//
+// Drop-in for the reference header `src/fcc_qp.hpp` (class fcc_qp::FCCQP,
+// FCCQPOptions, FCCQPDetails, FCCQPSolution, FCCQPSolveStatus): same names,
+// same constructor / setter / Solve / GetSolution signatures and meaning.  The
+// arithmetic runs on a B200 through libfccqp_b200.so (include/fccqp.h); there
+// is no CPU fallback -- construction throws std::runtime_error without a GPU.
+//
+// Header-only on purpose: when <Eigen/Dense> has been included BEFORE this
+// header, the Eigen-typed overloads of the reference (Ref<const MatrixXd>, ...,
+// FCCQPSolution::z as VectorXd) are enabled, so a C++ caller of the reference
+// recompiles unchanged; without Eigen the same methods take the light views
+// below (plain pointers + strides) and z is a std::vector<double>.
+#pragma once
+
+#include <cstddef>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "fccqp.h"
+
+#if defined(EIGEN_CORE_H) || defined(EIGEN_CORE_MODULE_H)
+#define FCC_QP_HAVE_EIGEN 1
+#endif
+
+namespace fcc_qp {
+
+// src/fcc_qp.hpp:14-17 (+ kNumericalIssue: the GPU path reports a broken KKT solve
+// instead of returning NaNs silently)
+enum FCCQPSolveStatus { kSuccess = 0, kMaxIterations = 1, kNumericalIssue = 2 };
+
+// src/fcc_qp.hpp:19-28
+struct FCCQPDetails {
+  int n_iter{};
+  double admm_residual_bounds{};
+  double admm_residual_friction_cone{};
+  double solve_time{};
+  double factorization_time{};
+  double bounds_viol{};
+  double friction_cone_viol{};
+  FCCQPSolveStatus solve_status{kSuccess};
+};
+
+// src/fcc_qp.hpp:30-35
+struct FCCQPOptions {
+  int max_iter = 1000;
+  double rho = 1e-6;
+  double eps_fcone = 1e-3;
+  double eps_bound = 1e-6;
+};
+
+// src/fcc_qp.hpp:37-40
+struct FCCQPSolution {
+  FCCQPDetails details{};
+#ifdef FCC_QP_HAVE_EIGEN
+  Eigen::VectorXd z;
+#else
+  std::vector<double> z;
+#endif
+};
+
+// Non-owning views used when Eigen is not available (and by the pybind module).
+struct ConstMatrixView {
+  const double* data;
+  int rows, cols;
+  std::ptrdiff_t row_stride, col_stride;  // element (i,j) at data[i*row_stride + j*col_stride]
+};
+struct ConstVectorView {
+  const double* data;
+  int size;
+};
+
+class FCCQP {
+ public:
+  // src/fcc_qp.hpp:73 / src/fcc_qp.cpp:24-55.  `device` is an extension (CUDA ordinal).
+  FCCQP(int num_vars, int num_equality_constraints, int nc, int lambda_c_start, int device = 0)
+      : n_vars_(num_vars), n_eq_(num_equality_constraints), nc_(nc), lambda_c_start_(lambda_c_start) {
+    check(fccqp_create(num_vars, num_equality_constraints, nc, lambda_c_start, device, &h_));
+  }
+  ~FCCQP() { fccqp_destroy(h_); }
+  FCCQP(const FCCQP&) = delete;
+  FCCQP& operator=(const FCCQP&) = delete;
+  FCCQP(FCCQP&& o) noexcept
+      : h_(o.h_), n_vars_(o.n_vars_), n_eq_(o.n_eq_), nc_(o.nc_), lambda_c_start_(o.lambda_c_start_) {
+    o.h_ = nullptr;
+  }
+
+  // src/fcc_qp.hpp:75-91.  The reference asserts rho > 0 / n > 0 (compiled out in Release);
+  // here the same conditions throw std::invalid_argument.
+  void set_rho(double rho) { check(fccqp_set_rho(h_, rho)); }
+  void set_max_iter(int n) { check(fccqp_set_max_iter(h_, n)); }
+  void set_options(FCCQPOptions opt) {
+    fccqp_options o;
+    o.max_iter = opt.max_iter; o.reserved = 0; o.rho = opt.rho;
+    o.eps_fcone = opt.eps_fcone; o.eps_bound = opt.eps_bound;
+    check(fccqp_set_options(h_, &o));
+  }
+  void set_warm_start(bool warm_start) { check(fccqp_set_warm_start(h_, warm_start ? 1 : 0)); }
+
+  // src/fcc_qp.hpp:114-117.  Shape mismatches (asserts in the reference, UB in Release)
+  // throw std::invalid_argument; too few friction coefficients throws std::out_of_range
+  // like the reference's friction_coeffs.at(i) (src/constraint_utils.cpp:32).
+  void Solve(ConstMatrixView Q, ConstVectorView b, ConstMatrixView A_eq, ConstVectorView b_eq,
+             const std::vector<double>& friction_coeffs, ConstVectorView lb, ConstVectorView ub) {
+    if (Q.rows != n_vars_ || Q.cols != n_vars_) throw std::invalid_argument("Q must be num_vars x num_vars");
+    if (b.size != n_vars_) throw std::invalid_argument("b must have num_vars entries");
+    if (A_eq.cols != n_vars_ && !(n_eq_ == 0 && A_eq.rows == 0))
+      throw std::invalid_argument("A_eq must have num_vars columns");
+    if (A_eq.rows != n_eq_ || b_eq.size != n_eq_)
+      throw std::invalid_argument("A_eq / b_eq must have num_equality_constraints rows");
+    if (lb.size != n_vars_ || ub.size != n_vars_) throw std::invalid_argument("lb / ub must have num_vars entries");
+    if (static_cast<int>(friction_coeffs.size()) < nc_ / 3)
+      throw std::out_of_range("friction_coeffs has fewer than nc/3 entries");
+    for (int i = 0; i < n_vars_; ++i)
+      if (lb.data[i] > ub.data[i]) throw std::invalid_argument("lb > ub (validate_bounds, src/constraint_utils.cpp:67-75)");
+    check(fccqp_solve(h_, Q.data, Q.row_stride, Q.col_stride, b.data, A_eq.data, A_eq.row_stride,
+                      A_eq.col_stride, b_eq.data, friction_coeffs.data(),
+                      static_cast<int>(friction_coeffs.size()), lb.data, ub.data));
+  }
+
+#ifdef FCC_QP_HAVE_EIGEN
+  // The reference's exact signature (column-major Refs, arbitrary outer stride).
+  void Solve(const Eigen::Ref<const Eigen::MatrixXd>& Q, const Eigen::Ref<const Eigen::VectorXd>& b,
+             const Eigen::Ref<const Eigen::MatrixXd>& A_eq, const Eigen::Ref<const Eigen::VectorXd>& b_eq,
+             const std::vector<double>& friction_coeffs, const Eigen::Ref<const Eigen::VectorXd>& lb,
+             const Eigen::Ref<const Eigen::VectorXd>& ub) {
+    Solve(ConstMatrixView{Q.data(), (int)Q.rows(), (int)Q.cols(), 1, (std::ptrdiff_t)Q.outerStride()},
+          ConstVectorView{b.data(), (int)b.size()},
+          ConstMatrixView{A_eq.data(), (int)A_eq.rows(), (int)A_eq.cols(), 1, (std::ptrdiff_t)A_eq.outerStride()},
+          ConstVectorView{b_eq.data(), (int)b_eq.size()}, friction_coeffs,
+          ConstVectorView{lb.data(), (int)lb.size()}, ConstVectorView{ub.data(), (int)ub.size()});
+  }
+#endif
+
+  // src/fcc_qp.cpp:194-207
+  FCCQPSolution GetSolution() const {
+    FCCQPSolution out;
+    out.z.resize(n_vars_);
+    fccqp_details d;
+    check(fccqp_get_solution(h_, out.z.data(), &d));
+    out.details.n_iter = d.n_iter;
+    out.details.admm_residual_bounds = d.admm_residual_bounds;
+    out.details.admm_residual_friction_cone = d.admm_residual_friction_cone;
+    out.details.solve_time = d.solve_time;
+    out.details.factorization_time = d.factorization_time;
+    out.details.bounds_viol = d.bounds_viol;
+    out.details.friction_cone_viol = d.friction_cone_viol;
+    out.details.solve_status = static_cast<FCCQPSolveStatus>(d.solve_status);
+    return out;
+  }
+
+  int contact_vars_start() const { return lambda_c_start_; }  // src/fcc_qp.hpp:121
+
+  // Extensions: the warm-start state the reference keeps private (src/fcc_qp.hpp:147-153).
+  void GetWarmState(double* x, double* mu_x, double* mu_lambda_c) const {
+    check(fccqp_get_warm_state(h_, x, mu_x, mu_lambda_c));
+  }
+  void SetWarmState(const double* x, const double* mu_x, const double* mu_lambda_c) {
+    check(fccqp_set_warm_state(h_, x, mu_x, mu_lambda_c));
+  }
+  int num_vars() const { return n_vars_; }
+  int num_equality_constraints() const { return n_eq_; }
+  int num_contact_vars() const { return nc_; }
+
+ private:
+  static void check(int rc) {
+    if (rc == FCCQP_OK) return;
+    const std::string msg = fccqp_last_error();
+    if (rc == FCCQP_E_INVALID) throw std::invalid_argument(msg);
+    throw std::runtime_error(msg);
+  }
+  fccqp_handle h_ = nullptr;
+  const int n_vars_, n_eq_, nc_, lambda_c_start_;
+};
+
+}  // namespace fcc_qp

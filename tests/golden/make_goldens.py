@@ -39,5 +39,61 @@ def main():
     save("walking_cold_paper.npz", ref.solve_batch(qp, warm_mode=0, **paper), paper)
 
 
+def make_synthetic():
+    """Goldens for the synthetic shapes.  Inputs are regenerated from
+    the seeded generator at test time; `in_sum` guards against generator drift."""
+    from fcc_qp_b200 import synthetic as syn
+    ref = Oracle("ref")
+    for shp, B in ((syn.HUMANOID, 192), (syn.QUADRUPED, 192), (syn.MULTICONTACT, 96)):
+        qp = syn.make_batch(shp, B)
+        chk = np.array([qp.Q.sum(), qp.A_eq.sum(), qp.b.sum(), qp.b_eq.sum(), qp.friction_coeffs.sum()])
+        save(f"synthetic_{shp.name}_cold.npz", ref.solve_batch(qp, warm_mode=0, nthreads=8, **LOG_OPTS),
+             LOG_OPTS, dict(in_sum=chk))
+    # config 5: multi-contact humanoid, T sequential warm-started batches with lane-wise state
+    shp, B, T = syn.MULTICONTACT, 48, 6
+    qp = syn.make_batch(shp, B, seed=shp.seed + 1)
+    rng = np.random.default_rng(shp.seed + 2)
+    lanes = ref.lanes(B, qp.n, qp.m, qp.nc, qp.lambda_c_start)
+    lanes.set_options(**LOG_OPTS)
+    zs, its, sts = [], [], []
+    for t in range(T):
+        r = lanes.solve(qp, warm=t > 0)
+        zs.append(r["z"]); its.append(r["n_iter"]); sts.append(r["status"])
+        qp = syn.random_walk(qp, rng)
+    np.savez_compressed(os.path.join(HERE, "synthetic_multicontact_warmseq.npz"), z=np.stack(zs),
+                        n_iter=np.stack(its), status=np.stack(sts),
+                        opts=np.array([LOG_OPTS["max_iter"], LOG_OPTS["rho"], LOG_OPTS["eps_fcone"], LOG_OPTS["eps_bound"]]))
+    print("warmseq n_iter per step:", [int((a > 0).sum()) for a in its])
+
+
+def make_kats():
+    """Known-answer vectors of SURVEY section 4, taken from the compiled reference."""
+    ref = Oracle("ref")
+    out = {}
+    # min 1/2 |x - f|^2  s.t. x in F(mu = 0.5): one contact, n = 3, no equality rows
+    fs = np.array([[1, 0, 1], [3, 4, 1], [1, 0, -3], [0, 0, 2], [1, 1, 0]], dtype=np.float64)
+    zs = []
+    for f in fs:
+        s = ref.solver(3, 0, 3, 0)
+        s.set_options(2000, 1.0, 1e-10, 1e-10)
+        s.Solve(np.eye(3), -f, np.zeros((0, 3)), np.zeros(0), [0.5], np.full(3, -np.inf), np.full(3, np.inf))
+        zs.append(s.GetSolution()["z"])
+    out["cone_f"], out["cone_z"] = fs, np.array(zs)
+    # equality-only problem: closed-form KKT solution with n_iter = 0
+    rng = np.random.default_rng(7)
+    n, m = 12, 5
+    G = rng.standard_normal((n, n)); Q = G @ G.T + np.eye(n); A = rng.standard_normal((m, n))
+    b = rng.standard_normal(n); beq = rng.standard_normal(m)
+    s = ref.solver(n, m, 0, 0)
+    s.set_options(100, 1e-3, 1e-6, 1e-6)
+    s.Solve(Q, b, A, beq, [], np.full(n, -np.inf), np.full(n, np.inf))
+    r = s.GetSolution()
+    out.update(eq_Q=Q, eq_A=A, eq_b=b, eq_beq=beq, eq_z=r["z"], eq_n_iter=np.array(r["n_iter"]))
+    np.savez_compressed(os.path.join(HERE, "kats.npz"), **out)
+    print("kats cone_z:\n", out["cone_z"], "\neq n_iter", r["n_iter"])
+
+
 if __name__ == "__main__":
     main()
+    make_synthetic()
+    make_kats()

@@ -1,0 +1,147 @@
+"""Edge cases of the reference's behaviour, on the GPU through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import LOG_OPTS
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def batch_solver(n, m, nc, lcs, **opts):
+    from fcc_qp_b200.batch import FCCQPBatch, FCCQPOptionsB
+    s = FCCQPBatch(n, m, nc, lcs)
+    s.set_options(FCCQPOptionsB(**opts))
+    return s
+
+
+INF3 = (np.full(3, -np.inf), np.full(3, np.inf))
+
+
+def test_cone_known_answers():
+    k = np.load(os.path.join(G, "kats.npz"))
+    f = k["cone_f"]
+    B = f.shape[0]
+    s = batch_solver(3, 0, 3, 0, max_iter=2000, rho=1.0, eps_fcone=1e-10, eps_bound=1e-10)
+    s.Solve(np.tile(np.eye(3), (B, 1, 1)), -f, np.zeros((B, 0, 3)), np.zeros((B, 0)), [0.5], *INF3)
+    z = s.GetSolution().z
+    assert np.abs(z - k["cone_z"]).max() < 1e-7
+    assert np.abs(z[4]).max() == 0.0     # f_z == 0 quirk: projects to the origin (constraint_utils.cpp:20-23)
+
+
+def test_equality_only_closed_form():
+    k = np.load(os.path.join(G, "kats.npz"))
+    n, m = k["eq_Q"].shape[0], k["eq_A"].shape[0]
+    s = batch_solver(n, m, 0, 0, max_iter=100, rho=1e-3, eps_fcone=1e-6, eps_bound=1e-6)
+    s.Solve(k["eq_Q"][None], k["eq_b"][None], k["eq_A"][None], k["eq_beq"][None], np.zeros(0), np.full(n, -np.inf),
+            np.full(n, np.inf))
+    r = s.GetSolution()
+    assert r.details.n_iter[0] == 0 and r.details.solve_status[0] == 0
+    assert np.abs(r.z[0] - k["eq_z"]).max() < 1e-9
+    assert r.details.eps_bounds[0] == 0.0 and r.details.eps_friction_cone[0] == 0.0
+
+
+def test_empty_and_single_batches(walking_log):
+    qp = walking_log
+    s = batch_solver(qp.n, qp.m, qp.nc, qp.lambda_c_start, **LOG_OPTS)
+    e = qp.take(np.arange(0))
+    s.Solve(e.Q, e.b, e.A_eq, e.b_eq, qp.friction_coeffs[0], qp.lb[0], qp.ub[0])
+    assert s.GetSolution().z.shape == (0, qp.n)
+    gold = np.load(os.path.join(G, "walking_cold.npz"))
+    one = qp.take(np.array([17]))
+    s.Solve(one.Q, one.b, one.A_eq, one.b_eq, one.friction_coeffs, one.lb, one.ub)
+    assert np.abs(s.GetSolution().z[0] - gold["z"][17]).max() / np.abs(gold["z"][17]).max() < 1e-6
+
+
+def test_no_contacts_with_finite_bounds():
+    """nc = 0 with finite bounds segfaults the reference in Release (fcc_qp.cpp:98); here the
+    infinity norm of an empty residual is 0 and the box-constrained QP is solved."""
+    rng = np.random.default_rng(3)
+    B, n, m = 5, 8, 3
+    G_ = rng.standard_normal((B, n, n)); Q = G_ @ G_.transpose(0, 2, 1) + np.eye(n)
+    A = rng.standard_normal((B, m, n)); b = rng.standard_normal((B, n)) * 3; beq = rng.standard_normal((B, m))
+    lb, ub = np.full(n, -0.3), np.full(n, 0.3)
+    opts = dict(max_iter=4000, rho=1.0, eps_fcone=1e-9, eps_bound=1e-9)
+    s = batch_solver(n, m, 0, 0, **opts)
+    s.Solve(Q, b, A, beq, np.zeros(0), lb, ub)
+    r = s.GetSolution()
+    from fcc_qp_b200.logdata import QPBatch
+    ref = oracle.Oracle("port").solve_batch(QPBatch(n, m, 0, 0, Q, b, A, beq, np.zeros((B, 0)), np.tile(lb, (B, 1)),
+                                                    np.tile(ub, (B, 1))), warm_mode=0, **opts)
+    assert np.abs(r.z - ref["z"]).max() < 1e-7
+    assert np.array_equal(r.details.n_iter, ref["n_iter"])
+    assert (r.details.eps_friction_cone == 0).all()
+
+
+def test_no_equality_rows():
+    rng = np.random.default_rng(5)
+    B, n = 4, 9
+    G_ = rng.standard_normal((B, n, n)); Q = G_ @ G_.transpose(0, 2, 1) + np.eye(n)
+    b = rng.standard_normal((B, n)) * 2
+    opts = dict(max_iter=3000, rho=0.5, eps_fcone=1e-9, eps_bound=1e-9)
+    s = batch_solver(n, 0, 9, 0, **opts)
+    mu = rng.uniform(0.3, 0.9, (B, 3))
+    s.Solve(Q, b, np.zeros((B, 0, n)), np.zeros((B, 0)), mu, np.full(n, -np.inf), np.full(n, np.inf))
+    r = s.GetSolution()
+    from fcc_qp_b200.logdata import QPBatch
+    ref = oracle.Oracle("port").solve_batch(QPBatch(n, 0, 9, 0, Q, b, np.zeros((B, 0, n)), np.zeros((B, 0)), mu,
+                                                    np.full((B, n), -np.inf), np.full((B, n), np.inf)), warm_mode=0, **opts)
+    assert np.abs(r.z - ref["z"]).max() < 1e-7 and np.array_equal(r.details.n_iter, ref["n_iter"])
+
+
+def test_max_iter_boundaries(walking_log):
+    """n_iter is 0-based and status derives from n_iter == max_iter (fcc_qp.cpp:107,203): a QP that
+    converges on the last permitted iteration is a success."""
+    gold = np.load(os.path.join(G, "walking_cold.npz"))
+    i6 = int(np.nonzero(gold["n_iter"] == 6)[0][0])
+    one = walking_log.take(np.array([i6]))
+    for mi, want_it, want_st in ((7, 6, 0), (6, 6, 1), (1, 1, 1)):
+        s = batch_solver(60, 38, 12, 38, **dict(LOG_OPTS, max_iter=mi))
+        s.Solve(one.Q, one.b, one.A_eq, one.b_eq, one.friction_coeffs, one.lb, one.ub)
+        d = s.GetSolution().details
+        assert (d.n_iter[0], d.solve_status[0]) == (want_it, want_st), mi
+
+
+def test_strided_device_inputs(walking_log):
+    """Column-major A_eq and non-contiguous Q stacks are consumed in place on the device."""
+    import torch
+    gold = np.load(os.path.join(G, "walking_cold.npz"))
+    qp = walking_log.take(np.arange(64))
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.as_tensor(a, device=dev)
+    A_cm = t(np.ascontiguousarray(qp.A_eq.transpose(0, 2, 1))).transpose(1, 2)      # [B,m,n] view, column-major
+    Qpad = torch.zeros((64, 60, 64), dtype=torch.float64, device=dev); Qpad[:, :, :60] = t(qp.Q)
+    s = batch_solver(60, 38, 12, 38, **LOG_OPTS)
+    s.Solve(Qpad[:, :, :60], t(qp.b), A_cm, t(qp.b_eq), t(qp.friction_coeffs[0]), t(qp.lb[0]), t(qp.ub[0]))
+    z = s.GetSolution().z.cpu().numpy()
+    err = np.abs(z - gold["z"][:64]).max(1) / np.maximum(1, np.abs(gold["z"][:64]).max(1))
+    assert err.max() <= 1e-6
+    assert np.array_equal(s.GetSolution().details.n_iter.cpu().numpy(), gold["n_iter"][:64])
+
+
+def test_singular_kkt_is_flagged():
+    """Duplicate equality rows make the KKT matrix singular.  The reference's COD returns a
+    minimum-norm answer; the GPU path reports FCCQP_STATUS_NUMERICAL_ISSUE or a finite answer that
+    still satisfies the constraints -- never silent NaNs with a success status."""
+    rng = np.random.default_rng(11)
+    n, m = 6, 3
+    Q = np.eye(n)[None]; A = rng.standard_normal((1, m, n)); A[0, 2] = A[0, 1]
+    beq = np.array([[0.3, -0.2, -0.2]]); b = rng.standard_normal((1, n))
+    s = batch_solver(n, m, 0, 0, max_iter=10, rho=1e-3, eps_fcone=1e-6, eps_bound=1e-6)
+    s.Solve(Q, b, A, beq, np.zeros(0), np.full(n, -np.inf), np.full(n, np.inf))
+    r = s.GetSolution()
+    ok = np.isfinite(r.z).all() and np.abs(A[0] @ r.z[0] - beq[0]).max() < 1e-6
+    assert r.details.solve_status[0] == 2 or ok
+
+
+def test_too_large_problem_is_refused():
+    from fcc_qp_b200 import FCCQPError
+    n, m = 300, 100
+    s = batch_solver(n, m, 0, 0, **LOG_OPTS)
+    with pytest.raises(FCCQPError) as e:
+        s.Solve(np.tile(np.eye(n), (1, 1, 1)), np.zeros((1, n)), np.zeros((1, m, n)), np.zeros((1, m)), np.zeros(0),
+                np.full(n, -np.inf), np.full(n, np.inf))
+    assert e.value.code == -3
