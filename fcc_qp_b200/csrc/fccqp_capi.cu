@@ -102,13 +102,13 @@ int pick_kernel(const DeviceCtx& ctx, int n, int m, int nc, KernelFn* fn, int* t
   if (N < 1) return fail(FCCQP_E_INVALID, "n + m must be >= 1");
   fccqp::Layout l(n, m, nc);
   *smem = l.bytes();
-  if (N > 256 || *smem > (size_t)ctx.max_smem_optin)
+  if (l.N8 > 256 || *smem > (size_t)ctx.max_smem_optin)
     return fail(FCCQP_E_UNSUPPORTED,
-                "n + m = %d needs %zu B of shared memory per QP (limit %d B, 256 rows): too large for the "
-                "shared-memory-resident kernels", N, *smem, ctx.max_smem_optin);
-  if (N <= 128) { *threads = 128; *fn = (KernelFn)fccqp::fccqp_solve_kernel<128, 4>; }
-  else if (N <= 192) { *threads = 192; *fn = (KernelFn)fccqp::fccqp_solve_kernel<192, 2>; }
-  else { *threads = 256; *fn = (KernelFn)fccqp::fccqp_solve_kernel<256, 1>; }
+                "n + m = %d (padded %d) needs %zu B of shared memory per QP (limit %d B, 256 rows): too large "
+                "for the shared-memory-resident kernels", N, l.N8, *smem, ctx.max_smem_optin);
+  // one thread per padded KKT row; 4 CTAs/SM for the <= 128-row shapes (Cassie, quadruped)
+  if (l.N8 <= 128) { *threads = 128; *fn = (KernelFn)fccqp::fccqp_solve_kernel<128, 4>; }
+  else { *threads = 256; *fn = (KernelFn)fccqp::fccqp_solve_kernel<256, 2>; }
   return FCCQP_OK;
 }
 
@@ -138,6 +138,8 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream) {
     p.work_counter = ctx.counters + ctx.next_counter;
     ctx.next_counter = (ctx.next_counter + 1) % kCounterRing;
   }
+  static const int cta_cap = getenv("FCCQP_CTAS_PER_SM") ? atoi(getenv("FCCQP_CTAS_PER_SM")) : 0;  // developer aid
+  if (cta_cap > 0 && cta_cap < ctas_per_sm) ctas_per_sm = cta_cap;
   int grid = ctas_per_sm * ctx.num_sms;
   if (grid > p.B) grid = p.B;
   CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned int), stream));
