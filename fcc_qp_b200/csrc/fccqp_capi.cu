@@ -119,6 +119,7 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream) {
   KernelFn fn; int threads; size_t smem;
   int rc = pick_kernel(ctx, p.n, p.m, p.nc, &fn, &threads, &smem);
   if (rc) return rc;
+  p.lay = fccqp::Layout(p.n, p.m, p.nc);
   static const int refine = getenv("FCCQP_PRESOLVE_REFINE") ? atoi(getenv("FCCQP_PRESOLVE_REFINE")) : 1;
   p.refine = refine < 0 ? 0 : refine;
   int ctas_per_sm = 0;
@@ -150,16 +151,35 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream) {
     CUDA_TRY(cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), stream));
     p.prof = d_prof;
   }
+  static const char* trace_path = getenv("FCCQP_TRACE");  // developer aid: per-warp event trace of CTA 0
+  unsigned long long* d_trace = nullptr;
+  if (trace_path) {
+    CUDA_TRY(cudaMalloc(&d_trace, 8 * 4096 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(d_trace, 0, 8 * 4096 * sizeof(unsigned long long), stream));
+    p.trace = d_trace;
+  }
   fn<<<grid, threads, smem, stream>>>(p);
   CUDA_TRY(cudaGetLastError());
+  if (trace_path) {
+    std::vector<unsigned long long> h(8 * 4096);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), d_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    CUDA_TRY(cudaFree(d_trace));
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (int w = 0; w < 8; ++w)
+        for (int e = 0; e < 4096 && h[w * 4096 + e]; ++e)
+          fprintf(f, "%d %llu %llu\n", w, h[w * 4096 + e] >> 8, h[w * 4096 + e] & 255ull);
+      fclose(f);
+    }
+  }
   if (profile) {
     unsigned long long h[16];
     CUDA_TRY(cudaMemcpyAsync(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     CUDA_TRY(cudaFree(d_prof));
-    static const char* names[14] = {"stage-in", "assemble", "sigma-syrk/rho", "ldlt-diag", "ldlt-trsm",
-                                    "ldlt-trailing", "xinv", "kkt-solve", "presolve-refine", "admm-project",
-                                    "epilogue", "-", "-", "-"};
+    static const char* names[14] = {"stage-in", "assemble", "sigma/rhs0", "ldlt-acc+diag", "ldlt-trsm",
+                                    "-", "xinv32", "kkt-solve", "presolve-refine", "admm-project",
+                                    "epilogue", "B-work-w0w2", "B-work-w1w3", "B-barrier-w0"};
     double tot = 0;
     for (int i = 0; i < 14; ++i) tot += (double)h[i];
     fprintf(stderr, "[fccqp profile] B=%d grid=%d qps=%llu iters=%llu cycles/QP=%.0f\n", p.B, grid, h[14], h[15],

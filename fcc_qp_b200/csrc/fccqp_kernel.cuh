@@ -1,4 +1,4 @@
-// fccqp_kernel.cuh -- sm_100a device code of the batched FCCQP solve (v3: FP64 tensor-core tiles).
+// fccqp_kernel.cuh -- sm_100a device code of the batched FCCQP solve (FP64 tensor-core tiles).
 //
 // One CTA solves one QP at a time; persistent CTAs pull QP indices from a global
 // work counter, so the 1-2 % of QPs that run to max_iter do not stall the rest of
@@ -26,10 +26,14 @@
 //     unpivoted LDL^T exists; one step of iterative refinement against the ORIGINAL system
 //     removes the sigma-dependent rounding.
 //   * K2 is the same unpivoted blocked LDL^T on [[Q + rho I, A'],[A,0]].
-//   * Blocked right-looking LDL^T, panel width 8.  Per panel: (P1) one thread factors the 8x8
-//     diagonal tile in registers and inverts its unit-lower factor; (P2) every sub-diagonal tile
-//     becomes L = A * inv(L11)' * inv(D) with two DMMAs; (P3) the trailing tiles get
-//     C -= (L D) L' with two DMMAs each, operands read straight from the tile storage.
+//   * Blocked LEFT-looking LDL^T on 8x8 tiles, one tile column at a time.  Warp w owns the tile
+//     rows i = w (mod #warps).  (A) every warp accumulates its tiles of column j in registers,
+//     C_ij = A_ij - sum_{k<j} L_ik D_k L_jk' (two DMMAs per term, operands read straight from the
+//     tile storage; nothing is written back in between, which keeps the shared-memory traffic
+//     at about a third of a right-looking update); the owner of the diagonal tile then factors
+//     it with ONE thread in registers and inverts its unit-lower factor; (B) every sub-diagonal
+//     tile becomes L_ij = C_ij inv(L_jj)' inv(D_j) with two more DMMAs and is stored once.
+//     The sigma A'A term of K1 and the rho I term of K2 are folded into step (A).
 //   * K3.  The 8x8 inverses are composed (again with DMMAs) into explicit inverses of the 32x32
 //     diagonal blocks of L, stored in place.  A triangular solve is then ceil(N/32) steps of
 //     "one warp applies a 32x32 inverse, the others subtract a 32-column slab" instead of N
@@ -41,12 +45,49 @@
 // r*8 + (((c/2) ^ (r/2)) & 3)*2 + (c&1): the 16-byte chunks of a row are XOR-swizzled by r/2
 // (the TMA SWIZZLE_64B pattern), which makes the tensor-core fragment access (row = lane/4,
 // column pair = lane%4), the row-per-thread access of the forward solve and the
-// column-per-thread access of the backward solve all bank-conflict-free within a tile.
+// column-per-thread access of the backward solve bank-conflict-free within a tile.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace fccqp {
+
+// Shared-memory carve-up (offsets in doubles).  Computed on the host, passed by value in the
+// kernel parameters (constant bank), so the kernel never recomputes it.
+struct Layout {
+  int n, m, nc;
+  int n8, m8, N8;   // padded sizes (multiples of 8)
+  int NB, NBx;      // number of 8-tiles per side; tiles covering the variable rows
+  int NB32, NT;     // 32-row solve blocks; padded vector length (NB32 * 32)
+  int NBT;          // number of stored tiles
+  int off_M, off_dinv, off_dneg, off_tbuf, off_ybuf, off_sbuf, off_xs, off_lcbar, off_muc, off_mu;
+  int off_red, off_int;
+  int doubles_total;
+  static inline int up2(int v) { return (v + 1) & ~1; }
+  Layout() = default;
+  Layout(int n_, int m_, int nc_) {
+    n = n_; m = m_; nc = nc_;
+    n8 = (n + 7) & ~7; m8 = (m + 7) & ~7; N8 = n8 + m8;
+    NB = N8 >> 3; NBx = n8 >> 3;
+    NB32 = (N8 + 31) >> 5; NT = NB32 * 32;
+    NBT = NB * (NB + 1) / 2;
+    int o = 0;
+    off_M = o;     o += NBT * 64;
+    off_dinv = o;  o += NT;
+    off_dneg = o;  o += NT;
+    off_tbuf = o;  o += NT;
+    off_ybuf = o;  o += NT;
+    off_sbuf = o;  o += NT;
+    off_xs = o;    o += n8 + 8;
+    off_lcbar = o; o += up2(nc + 2);
+    off_muc = o;   o += up2(nc + 2);
+    off_mu = o;    o += up2(nc / 3 + 2);
+    off_red = o;   o += 4 * 32;   // block_reduce2 scratch: 2 buffers x 2 values x 32 warps
+    off_int = o;   o += 32;       // ints: work index, profiling slots
+    doubles_total = o;
+  }
+  size_t bytes() const { return (size_t)doubles_total * sizeof(double); }
+};
 
 struct SolveParams {
   int B, n, m, nc, lcs;
@@ -67,39 +108,8 @@ struct SolveParams {
   double* dbg_x0;              // optional [B,n]: pre-solve point (debug / tests)
   unsigned long long* cycles;  // optional [2]: summed factorization / total cycles
   unsigned long long* prof;    // optional [16]: per-phase cycle counters (developer profiling)
-};
-
-// Shared-memory carve-up, identical on host (sizing) and device (pointers).
-struct Layout {
-  int n, m, nc;
-  int n8, m8, N8;   // padded sizes (multiples of 8)
-  int NB, NBx;      // number of 8-tiles per side; tiles covering the variable rows
-  int NB32, NT;     // 32-row solve blocks; padded vector length (NB32 * 32)
-  size_t off_M, off_dinv, off_dneg, off_tbuf, off_ybuf, off_sbuf, off_xs, off_lcbar, off_muc, off_mu;
-  size_t off_red, off_int;
-  size_t doubles_total;
-  __host__ __device__ static inline size_t up2(size_t v) { return (v + 1) & ~size_t(1); }
-  __host__ __device__ Layout(int n_, int m_, int nc_) {
-    n = n_; m = m_; nc = nc_;
-    n8 = (n + 7) & ~7; m8 = (m + 7) & ~7; N8 = n8 + m8;
-    NB = N8 >> 3; NBx = n8 >> 3;
-    NB32 = (N8 + 31) >> 5; NT = NB32 * 32;
-    size_t o = 0;
-    off_M = o;     o += (size_t)(NB * (NB + 1) / 2) * 64;
-    off_dinv = o;  o += NT;
-    off_dneg = o;  o += NT;
-    off_tbuf = o;  o += NT;
-    off_ybuf = o;  o += NT;
-    off_sbuf = o;  o += NT;
-    off_xs = o;    o += n8 + 8;
-    off_lcbar = o; o += up2(nc + 2);
-    off_muc = o;   o += up2(nc + 2);
-    off_mu = o;    o += up2(nc / 3 + 2);
-    off_red = o;   o += 4 * 32;   // block_reduce2 scratch: 2 buffers x 2 values x 32 warps
-    off_int = o;   o += 32;       // ints: work index, profiling slots
-    doubles_total = o;
-  }
-  __host__ __device__ size_t bytes() const { return doubles_total * sizeof(double); }
+  unsigned long long* trace;   // optional [8][4096]: (clock << 8 | tag) events of CTA 0's first QP (developer tracing)
+  Layout lay;                  // filled in by launch_solve
 };
 
 __device__ __forceinline__ double warp_max(double v) {
@@ -116,7 +126,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Block-wide reduction of two values (max or sum).  `red` holds 2 x 2 x 32 doubles;
 // `parity` alternates between the two halves so one barrier per call suffices.
 template <bool kSum>
-__device__ __forceinline__ void block_reduce2(double& a, double& b, double* red, int& parity) {
+__device__ __noinline__ void block_reduce2(double& a, double& b, double* red, int& parity) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   if (kSum) { a = warp_sum(a); b = warp_sum(b); } else { a = warp_max(a); b = warp_max(b); }
   double* r = red + parity * 64;
@@ -185,8 +195,8 @@ __host__ __device__ __forceinline__ int mat_off(int i, int j) { return tile_off(
 // FP64 tensor-core step: C(8x8) += A(8x4) B(4x8).  Fragments (PTX ISA, m8n8k4 .f64): lane l holds
 // A[l/4][l%4], B[l%4][l/4], C[l/4][2(l%4)], C[l/4][2(l%4)+1].
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 // C(8x8) += Aop(8x8) Bop(8x8) with the contraction index split as k = 2(l%4)+s over two DMMAs:
 //   a = (Aop[l/4][2q], Aop[l/4][2q+1]),  b = (Bop[2q][l/4], Bop[2q+1][l/4]),  q = l%4.
@@ -199,24 +209,47 @@ __device__ __forceinline__ void mma8(double2& c, const double2 a, const double2 
   dmma(c.x, c.y, a.x, b.x);
   dmma(c.x, c.y, a.y, b.y);
 }
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
 
-// LDL^T of one 8x8 tile by ONE thread, all in registers (shortest dependent chain), followed by
-// the in-place inverse of its unit-lower factor.  Writes inv(L11) (zeros above, ones on the
-// diagonal) back into the tile, 1/d and -d into dinv / dneg.
+// LDL^T of one 8x8 tile by ONE thread, all in registers, plus the in-place inverse of its
+// unit-lower factor.  Writes inv(L11) (zeros above, ones on the diagonal) back into the tile, 1/d
+// and -d into dinv / dneg.  A warp issues in order, so the statement order below IS the schedule:
+// the pivot chain (reciprocal -> first multiplier -> next pivot) goes first in every column and
+// the independent work (remaining multipliers, trailing updates, the row of the inverse that just
+// became computable, its stores) is placed right behind it to fill the reciprocal's latency.
 __device__ __forceinline__ void factor_diag_tile(double* __restrict__ tile, double* __restrict__ dinv,
                                                  double* __restrict__ dneg) {
   double a[8][8];
+  // lower triangle incl. diagonal: 16-byte chunks 0..r/2 of row r
 #pragma unroll
   for (int r = 0; r < 8; ++r)
 #pragma unroll
-    for (int c = 0; c <= r; ++c) a[r][c] = tile[el_off(r, c)];
-  double rd[8];
+    for (int cc = 0; cc <= (r >> 1); ++cc) {
+      const double2 v = ld2(tile + el_off(r, 2 * cc));
+      a[r][2 * cc] = v.x;
+      if (2 * cc + 1 <= r) a[r][2 * cc + 1] = v.y;
+    }
+  double rd[8], dg[8];
+  rd[0] = fast_rcp(a[0][0]);
+  dg[0] = a[0][0];
+  st2(tile + el_off(0, 0), make_double2(1.0, 0.0));
+#pragma unroll
+  for (int cc = 1; cc < 4; ++cc) st2(tile + el_off(0, 2 * cc), make_double2(0.0, 0.0));
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    rd[c] = fast_rcp(a[c][c]);
+    // --- chain: row c+1 gets its multiplier and its pivot, then the next reciprocal starts
+    if (c + 1 < 8) {
+      const double arc = a[c + 1][c];
+      const double l = arc * rd[c];
+      a[c + 1][c + 1] -= arc * l;
+      a[c + 1][c] = l;
+      dg[c + 1] = a[c + 1][c + 1];
+      rd[c + 1] = fast_rcp(a[c + 1][c + 1]);
+    }
+    // --- off the chain: rows r >= c+2 (a[r][c] still unscaled = l_rc d_c; rows c2 < r hold l_{c2,c})
 #pragma unroll
-    for (int r = c + 1; r < 8; ++r) {
-      // rows c2 < r of this column already hold l_{c2,c}; a[r][c] is still unscaled (= l_rc d_c)
+    for (int r = c + 2; r < 8; ++r) {
       const double arc = a[r][c];
       const double l = arc * rd[c];
 #pragma unroll
@@ -224,66 +257,103 @@ __device__ __forceinline__ void factor_diag_tile(double* __restrict__ tile, doub
       a[r][r] -= arc * l;
       a[r][c] = l;
     }
+    // --- row c+1 of L is final: row c+1 of X = inv(L):  X[i][j] = -(L[i][j] + sum_{j<k<i} L[i][k] X[k][j])
+    if (c + 1 < 8) {
+      const int i = c + 1;
+      double x[8];
+#pragma unroll
+      for (int j = 0; j < i; ++j) {
+        double sm = a[i][j];
+#pragma unroll
+        for (int k = j + 1; k < i; ++k) sm += a[i][k] * a[k][j];
+        x[j] = -sm;
+      }
+#pragma unroll
+      for (int j = 0; j < i; ++j) a[i][j] = x[j];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c0 = 2 * cc, c1 = 2 * cc + 1;
+        const double v0 = c0 < i ? a[i][c0] : (c0 == i ? 1.0 : 0.0);
+        const double v1 = c1 < i ? a[i][c1] : (c1 == i ? 1.0 : 0.0);
+        st2(tile + el_off(i, c0), make_double2(v0, v1));
+      }
+    }
   }
 #pragma unroll
   for (int c = 0; c < 8; c += 2) {
-    *reinterpret_cast<double2*>(dinv + c) = make_double2(rd[c], rd[c + 1]);
-    *reinterpret_cast<double2*>(dneg + c) = make_double2(-a[c][c], -a[c + 1][c + 1]);
+    st2(dinv + c, make_double2(rd[c], rd[c + 1]));
+    st2(dneg + c, make_double2(-dg[c], -dg[c + 1]));
   }
-  // X = inv(L), row by row: X[i][j] = -(L[i][j] + sum_{j<k<i} L[i][k] X[k][j])
+}
+
+// Step (A) of the left-looking factorization for the kOwn tiles (i = i_first + u * kStride, column j)
+// owned by this warp:  acc[u] -= sum_{k<j} L_ik D_k L_jk'.  Tiles of one tile row are contiguous
+// (64 doubles apart), so every operand pointer just advances.  Software-pipelined by hand (a warp
+// issues in order): the operands of step k+1 are loaded before the DMMAs of step k are issued,
+// and the two DMMAs of a tile product go to different accumulators so that no DMMA waits for the
+// one before it.  The prefetch of step j reads the column's own tiles: harmless, never used.
+template <int kOwn, int kStride>
+__device__ __forceinline__ void accumulate_column(double2 (&acc)[4], const double* __restrict__ M,
+                                                  const double* __restrict__ dneg, int j, int i_first,
+                                                  int fragC, int fq) {
+  const double* ap[kOwn];
+  double2 a[kOwn], accB[kOwn];
+  const double* bp = M + tile_off(j, 0) + fragC;
+  const double* dp = dneg + 2 * fq;
+  double2 b = ld2(bp), d = ld2(dp);
 #pragma unroll
-  for (int i = 1; i < 8; ++i) {
-    double x[8];
+  for (int u = 0; u < kOwn; ++u) {
+    ap[u] = M + tile_off(i_first + u * kStride, 0) + fragC;
+    a[u] = ld2(ap[u]);
+    accB[u] = make_double2(0.0, 0.0);
+  }
+#pragma unroll 2
+  for (int k = 0; k < j; ++k) {
+    bp += 64; dp += 8;
+    const double2 bn = ld2(bp), dn = ld2(dp);
+    double2 an[kOwn];
 #pragma unroll
-    for (int j = 0; j < i; ++j) {
-      double s = a[i][j];
+    for (int u = 0; u < kOwn; ++u) { ap[u] += 64; an[u] = ld2(ap[u]); }
+    const double bx = b.x * d.x, by = b.y * d.y;
 #pragma unroll
-      for (int k = j + 1; k < i; ++k) s += a[i][k] * a[k][j];
-      x[j] = -s;
-    }
+    for (int u = 0; u < kOwn; ++u) dmma(acc[u].x, acc[u].y, a[u].x, bx);
 #pragma unroll
-    for (int j = 0; j < i; ++j) a[i][j] = x[j];
+    for (int u = 0; u < kOwn; ++u) dmma(accB[u].x, accB[u].y, a[u].y, by);
+    b = bn; d = dn;
+#pragma unroll
+    for (int u = 0; u < kOwn; ++u) a[u] = an[u];
   }
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      const int c0 = 2 * cc, c1 = 2 * cc + 1;
-      const double v0 = c0 < r ? a[r][c0] : (c0 == r ? 1.0 : 0.0);
-      const double v1 = c1 < r ? a[r][c1] : (c1 == r ? 1.0 : 0.0);
-      *reinterpret_cast<double2*>(tile + el_off(r, c0)) = make_double2(v0, v1);
-    }
-  }
+  for (int u = 0; u < kOwn; ++u) { acc[u].x += accB[u].x; acc[u].y += accB[u].y; }
 }
 
 // ---------------------------------------------------------------------------
 // The fused solve kernel.  kThreads >= padded KKT size N8 (one thread per KKT row in the
-// triangular solves and all vector work).
+// triangular solves and all vector work); at most kMaxOwn tile rows per warp.
 // ---------------------------------------------------------------------------
 template <int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const SolveParams p) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kWarps = kThreads / 32;
+  constexpr int kMaxOwn = 4;   // N8 <= kThreads  =>  NB <= 4 * kWarps
   const int n = p.n, m = p.m, nc = p.nc, lcs = p.lcs;
-  const Layout L(n, m, nc);
-  const int n8 = L.n8, N8 = L.N8, NB = L.NB, NBx = L.NBx, NB32 = L.NB32;
-  const int NBT = NB * (NB + 1) / 2;
+  const int n8 = p.lay.n8, N8 = p.lay.N8, NB = p.lay.NB, NBx = p.lay.NBx, NB32 = p.lay.NB32;
 
-  double* M = smem + L.off_M;
-  double* dinv = smem + L.off_dinv;
-  double* dneg = smem + L.off_dneg;
-  double* tbuf = smem + L.off_tbuf;
-  double* ybuf = smem + L.off_ybuf;
-  double* sbuf = smem + L.off_sbuf;
-  double* xs = smem + L.off_xs;
-  double* lcbar = smem + L.off_lcbar;
-  double* muc = smem + L.off_muc;
-  double* vmu = smem + L.off_mu;
-  double* red = smem + L.off_red;
-  int* ibuf = reinterpret_cast<int*>(smem + L.off_int);
-  int* s_work = ibuf;  // [1]
-  unsigned long long* s_prof = reinterpret_cast<unsigned long long*>(ibuf + 2);  // [16]
+  double* const M = smem + p.lay.off_M;
+  double* const dinv = smem + p.lay.off_dinv;
+  double* const dneg = smem + p.lay.off_dneg;
+  double* const tbuf = smem + p.lay.off_tbuf;
+  double* const ybuf = smem + p.lay.off_ybuf;
+  double* const sbuf = smem + p.lay.off_sbuf;
+  double* const xs = smem + p.lay.off_xs;
+  double* const lcbar = smem + p.lay.off_lcbar;
+  double* const muc = smem + p.lay.off_muc;
+  double* const vmu = smem + p.lay.off_mu;
+  double* const red = smem + p.lay.off_red;
+  int* const ibuf = reinterpret_cast<int*>(smem + p.lay.off_int);
+  int* const s_work = ibuf;  // [1]
+  unsigned long long* const s_prof = reinterpret_cast<unsigned long long*>(ibuf + 2);  // [16]
   long long t_prof = 0;
   if (p.prof && tid == 0) { for (int i = 0; i < 16; ++i) s_prof[i] = 0; t_prof = clock64(); }
 #define FCCQP_PROF(slot)                                                   \
@@ -295,6 +365,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
     }                                                                      \
   } while (0)
 
+  // developer tracing: lane 0 of every warp of CTA 0 logs (clock, tag) for the first QP it solves
+  unsigned long long* trbuf = (p.trace && blockIdx.x == 0) ? p.trace + warp * 4096 : nullptr;
+  int trn = 0;
+#define TR(tag)                                                                                      \
+  do {                                                                                               \
+    if (trbuf && lane == 0 && trn < 4096) trbuf[trn++] = ((unsigned long long)clock64() << 8) | (unsigned)(tag); \
+  } while (0)
+
   int parity = 0;
   // thread-per-row identity: rows [0,n) variables, [n,n8) pads, [n8,n8+m) constraints, rest pads
   const int t = tid;
@@ -303,10 +381,16 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
   const bool is_row = t < N8;
   const bool in_cone = is_x && t >= lcs && t < lcs + nc;
   const int tb = t >> 3, tr = t & 7, tf = tr >> 1;  // tile row, row in tile, row swizzle
+  const int colo = tr & 1, colc = tr >> 1;          // column-per-thread access: element (r, tr) of a tile
+  const int flip = tb & 1, flip8 = flip << 3;       // odd tile columns walk row pairs swapped (bank spread)
   // tensor-core fragment coordinates of this lane
   const int fr = lane >> 2, fq = lane & 3;
   const int fragC = (fr << 3) + (((fq ^ (fr >> 1)) & 3) << 1);                       // (fr, 2fq..2fq+1)
   const int fragT = ((2 * fq) << 3) + ((((fr >> 1) ^ fq) & 3) << 1) + (fr & 1);      // (2fq, fr); +8 for (2fq+1, fr)
+
+  // Q is symmetric: walk it along whichever stride is contiguous.
+  const long long q_slow = p.q_cs <= p.q_rs ? p.q_rs : p.q_cs;
+  const long long q_fast = p.q_cs <= p.q_rs ? p.q_cs : p.q_rs;
 
   for (;;) {
     __syncthreads();  // previous QP fully retired (smem reuse) before taking new work
@@ -314,14 +398,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
     __syncthreads();
     const int qp = *s_work;
     if (qp >= p.B) break;
+    TR(1);
 
     const double* Qg = p.Q + (size_t)qp * p.q_bs;
     const double* Ag = p.A + (size_t)qp * p.a_bs;
-    // Q is symmetric: walk it along whichever stride is contiguous.
-    const long long q_slow = p.q_cs <= p.q_rs ? p.q_rs : p.q_cs;
-    const long long q_fast = p.q_cs <= p.q_rs ? p.q_cs : p.q_rs;
-    const bool q_vec = q_fast == 1 && ((reinterpret_cast<uintptr_t>(Qg) | (uintptr_t)(q_slow * 8)) & 15) == 0;
-    const bool a_vec = p.a_cs == 1 && ((reinterpret_cast<uintptr_t>(Ag) | (uintptr_t)(p.a_rs * 8)) & 15) == 0;
+    // 16-byte copies need contiguous rows, 16-byte aligned row starts and an even n
+    const bool q_vec = q_fast == 1 && (n & 1) == 0 &&
+                       ((reinterpret_cast<uintptr_t>(Qg) | (uintptr_t)(q_slow * 8)) & 15) == 0;
+    const bool a_vec = p.a_cs == 1 && (n & 1) == 0 &&
+                       ((reinterpret_cast<uintptr_t>(Ag) | (uintptr_t)(p.a_rs * 8)) & 15) == 0;
 
     // ---------------- K0: vectors (one register per row and vector) ----------------
     double v_b = 0.0;       // b (variable rows) or b_eq (constraint rows)
@@ -351,6 +436,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
     int n_iter = 0;
     double res_x = 0.0, res_c = 0.0;
     FCCQP_PROF(0);
+    TR(2);
 
     // pass 0: cold pre-solve on [[Q + sigma A'A, A'],[A,0]];  pass 1: ADMM on [[Q + rho I, A'],[A,0]]
     for (int pass = presolve ? 0 : 1; pass < 2; ++pass) {
@@ -358,192 +444,206 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
       const long long t_f0 = clock64();
 
       // ---------------- assemble the lower tiles of the padded KKT matrix ----------------
-      // one warp per tile, lane = (row fr, column pair 2fq): 8 x 64-byte row segments from HBM/L2
+      // one warp per tile, lane = (row fr, column pair 2fq): 8 x 64-byte row segments from HBM/L2.
+      // Three uniform loops (Q tiles, A tiles, zero tiles), tile rows outer, warps strided over columns.
       {
-        int I = 0, J = warp;
-        while (J > I) { J -= I + 1; ++I; }
-        for (int idx = warp; idx < NBT; idx += kWarps) {
-          double* dst = M + tile_off(I, J) + fragC;
-          const int gi = 8 * I + fr, gc = 8 * J + 2 * fq;
-          if (J >= NBx) {
-            // (2,2) block: zero; decoupled unit pivots on the constraint pads
-            const int k = gi - n8;
-            *reinterpret_cast<double2*>(dst) =
-                make_double2((gi == gc && k >= m) ? 1.0 : 0.0, (gi == gc + 1 && k >= m) ? 1.0 : 0.0);
-          } else if (I < NBx) {
-            // Q (symmetric; row gi read along the contiguous direction), unit pivots on the pads
-            const bool e0 = gi < n && gc < n, e1 = gi < n && gc + 1 < n;
-            const double* src = Qg + gi * q_slow + gc * q_fast;
-            if (e1 && q_vec) {
-              cp_async16(dst, src);
+        const int gc0 = 2 * fq;
+        // Q (symmetric; row read along the contiguous direction), unit pivots on the pads
+        const double* qrow = Qg + fr * q_slow + gc0 * q_fast;
+        for (int I = 0; I < NBx; ++I, qrow += 8 * q_slow) {
+          const int gi = 8 * I + fr;
+          double* dst = M + tile_off(I, warp) + fragC;
+          const double* src = qrow + (8 * warp) * q_fast;
+          for (int J = warp; J <= I; J += kWarps, dst += 64 * kWarps, src += 8 * kWarps * q_fast) {
+            const int gc = 8 * J + gc0;
+            if (q_vec) {
+              if (gi < n && gc < n) cp_async16(dst, src);
+              else st2(dst, make_double2(gi == gc ? 1.0 : 0.0, gi == gc + 1 ? 1.0 : 0.0));
             } else {
-              if (e0) cp_async8(dst, src); else dst[0] = (gi == gc) ? 1.0 : 0.0;
-              if (e1) cp_async8(dst + 1, src + q_fast); else dst[1] = (gi == gc + 1) ? 1.0 : 0.0;
-            }
-          } else {
-            // A rows
-            const int k = gi - n8;
-            const bool e0 = k < m && gc < n, e1 = k < m && gc + 1 < n;
-            const double* src = Ag + k * p.a_rs + gc * p.a_cs;
-            if (e1 && a_vec) {
-              cp_async16(dst, src);
-            } else {
-              if (e0) cp_async8(dst, src); else dst[0] = 0.0;
-              if (e1) cp_async8(dst + 1, src + p.a_cs); else dst[1] = 0.0;
+              if (gi < n && gc < n) cp_async8(dst, src); else dst[0] = (gi == gc) ? 1.0 : 0.0;
+              if (gi < n && gc + 1 < n) cp_async8(dst + 1, src + q_fast); else dst[1] = (gi == gc + 1) ? 1.0 : 0.0;
             }
           }
-          J += kWarps;
-          while (J > I) { J -= I + 1; ++I; }
+        }
+        // A rows below it
+        const double* arow = Ag + (long long)fr * p.a_rs + gc0 * p.a_cs;
+        for (int I = NBx; I < NB; ++I, arow += 8 * p.a_rs) {
+          const int k = 8 * (I - NBx) + fr;
+          double* dst = M + tile_off(I, warp) + fragC;
+          const double* src = arow + (8 * warp) * p.a_cs;
+          for (int J = warp; J < NBx; J += kWarps, dst += 64 * kWarps, src += 8 * kWarps * p.a_cs) {
+            const int gc = 8 * J + gc0;
+            if (a_vec) {
+              if (k < m && gc < n) cp_async16(dst, src); else st2(dst, make_double2(0.0, 0.0));
+            } else {
+              if (k < m && gc < n) cp_async8(dst, src); else dst[0] = 0.0;
+              if (k < m && gc + 1 < n) cp_async8(dst + 1, src + p.a_cs); else dst[1] = 0.0;
+            }
+          }
+          // (2,2) block: zero; decoupled unit pivots on the constraint pads
+          dst = M + tile_off(I, NBx + warp) + fragC;
+          for (int J = NBx + warp; J <= I; J += kWarps, dst += 64 * kWarps) {
+            const bool dg = J == I && k >= m;
+            st2(dst, make_double2((dg && fr == gc0) ? 1.0 : 0.0, (dg && fr == gc0 + 1) ? 1.0 : 0.0));
+          }
         }
       }
+      TR(3);
       cp_async_wait_all();
       __syncthreads();
       FCCQP_PROF(1);
+      TR(4);
 
-      double rhs0 = 0.0;  // pass-0 right-hand side of row t
-      if (pass == 1) {
-        if (is_x) M[mat_off(t, t)] += p.rho;
-        __syncthreads();
-      } else {
+      double rhs0 = 0.0;   // pass-0 right-hand side of row t
+      double sigma = 0.0;  // pass-0 augmented-Lagrangian weight
+      if (pass == 0) {
         // sigma = trace(Q) / ||A||_F^2 balances the two terms of Q + sigma A'A
         double trq = is_x ? M[mat_off(t, t)] : 0.0, fro = 0.0;
         if (is_c) {
           tbuf[t] = v_b;
           for (int jb = 0; jb < NBx; ++jb) {
-            const double2* row = reinterpret_cast<const double2*>(M + tile_off(tb, jb) + tr * 8);
+            const double* row = M + tile_off(tb, jb) + tr * 8;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { const double2 v = row[c ^ tf]; fro += v.x * v.x + v.y * v.y; }
+            for (int c = 0; c < 4; ++c) { const double2 v = ld2(row + 2 * (c ^ tf)); fro += v.x * v.x + v.y * v.y; }
           }
         }
         block_reduce2<true>(trq, fro, red, parity);
-        const double sigma = (trq > 0.0 && fro > 0.0 && isfinite(trq / fro)) ? trq / fro : 1.0;
+        sigma = (trq > 0.0 && fro > 0.0 && isfinite(trq / fro)) ? trq / fro : 1.0;
         // rhs_x = -b + sigma A' b_eq (needs A before the factorization overwrites it)
         if (is_x) {
           double s0 = 0.0, s1 = 0.0;
-          const int colo = tr & 1, colc = tr >> 1;
           for (int ib = NBx; ib < NB; ++ib) {
             const double* tl = M + tile_off(ib, tb) + colo;
             const double* bq = tbuf + ib * 8;
 #pragma unroll
             for (int r = 0; r < 8; r += 2) {
-              s0 += tl[r * 8 + (((colc ^ (r >> 1)) & 3) << 1)] * bq[r];
-              s1 += tl[(r + 1) * 8 + (((colc ^ (r >> 1)) & 3) << 1)] * bq[r + 1];
+              const int sw = ((colc ^ (r >> 1)) & 3) << 1;
+              s0 += tl[r * 8 + flip8 + sw] * bq[r + flip];
+              s1 += tl[(r + 1) * 8 - flip8 + sw] * bq[r + 1 - flip];
             }
           }
           rhs0 = -v_b + sigma * (s0 + s1);
         } else if (is_c) {
           rhs0 = v_b;
         }
-        // H += sigma A'A, tile by tile on the tensor cores (lower tiles of the variable block)
-        if (NB > NBx) {
-          const int TT = NBx * (NBx + 1) / 2;
-          const int lo = TT * warp / kWarps, hi = TT * (warp + 1) / kWarps;
-          int I = 0, J = lo;
-          while (J > I) { J -= I + 1; ++I; }
-          for (int idx = lo; idx < hi; ++idx) {
-            double2 acc0 = make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
-            int kb = NBx;
-            for (; kb + 1 < NB; kb += 2) {
-              const double* ai = M + tile_off(kb, I) + fragT;
-              const double* aj = M + tile_off(kb, J) + fragT;
-              const double* ai2 = M + tile_off(kb + 1, I) + fragT;
-              const double* aj2 = M + tile_off(kb + 1, J) + fragT;
-              const double2 a0 = make_double2(ai[0], ai[8]), b0 = make_double2(aj[0], aj[8]);
-              const double2 a1 = make_double2(ai2[0], ai2[8]), b1 = make_double2(aj2[0], aj2[8]);
-              mma8(acc0, a0, b0);
-              mma8(acc1, a1, b1);
-            }
-            if (kb < NB) {
-              const double* ai = M + tile_off(kb, I) + fragT;
-              const double* aj = M + tile_off(kb, J) + fragT;
-              mma8(acc0, make_double2(ai[0], ai[8]), make_double2(aj[0], aj[8]));
-            }
-            double2* cp = reinterpret_cast<double2*>(M + tile_off(I, J) + fragC);
-            double2 c = *cp;
-            c.x += sigma * (acc0.x + acc1.x);
-            c.y += sigma * (acc0.y + acc1.y);
-            *cp = c;
-            if (++J > I) { J = 0; ++I; }
-          }
-        }
-        __syncthreads();
       }
       FCCQP_PROF(2);
+      TR(5);
 
-      // ---------------- unpivoted blocked LDL^T on 8x8 tiles ----------------
-      for (int k = 0; k < NB; ++k) {
-        const int k0 = k * 8;
-        double* dtile = M + tile_off(k, k);
-        // --- P1: diagonal tile, one thread (rotating over the warps), registers only
-        if (tid == ((k % kWarps) << 5)) factor_diag_tile(dtile, dinv + k0, dneg + k0);
+      // ---------------- unpivoted blocked left-looking LDL^T on 8x8 tiles ----------------
+      for (int j = 0; j < NB; ++j) {
+        const int j0 = j * 8;
+        const int i_first = j + ((warp - j) & (kWarps - 1));   // first own tile row >= j
+        const bool own_diag = i_first == j;
+        const int nown = i_first < NB ? (NB - i_first + kWarps - 1) / kWarps : 0;   // own tiles in column j
+        TR(10);
+        // --- (A) accumulate the own tiles of column j in registers
+        double2 acc[kMaxOwn];
+        {
+          int i = i_first;
+#pragma unroll
+          for (int u = 0; u < kMaxOwn; ++u, i += kWarps)
+            acc[u] = u < nown ? ld2(M + tile_off(i, j) + fragC) : make_double2(0.0, 0.0);
+        }
+        if (pass == 0 && j < NBx) {
+          // + sigma A'A on the tiles of the variable block (A is still unfactored in columns >= j);
+          // operands of the next A tile row are loaded before the DMMAs of this one
+          double2 accB[kMaxOwn];
+#pragma unroll
+          for (int u = 0; u < kMaxOwn; ++u) accB[u] = make_double2(0.0, 0.0);
+          const double* arow = M + tile_off(NBx, 0) + fragT;
+          double2 b = make_double2(arow[64 * j], arow[64 * j + 8]);
+          double2 av[kMaxOwn];
+          {
+            int i = i_first;
+#pragma unroll
+            for (int u = 0; u < kMaxOwn; ++u, i += kWarps) {
+              const int ie = i < NBx ? i : j;   // clamp: tiles outside the variable block are masked below
+              av[u] = make_double2(arow[64 * ie], arow[64 * ie + 8]);
+            }
+          }
+#pragma unroll 1
+          for (int kb = NBx; kb < NB; ++kb) {
+            arow += 64 * (kb + 1);            // next tile row (over-read after the last one: harmless)
+            const double2 bn = make_double2(arow[64 * j], arow[64 * j + 8]);
+            double2 an[kMaxOwn];
+            int i = i_first;
+#pragma unroll
+            for (int u = 0; u < kMaxOwn; ++u, i += kWarps) {
+              const int ie = i < NBx ? i : j;
+              an[u] = make_double2(arow[64 * ie], arow[64 * ie + 8]);
+            }
+            const double bx = sigma * b.x, by = sigma * b.y;
+            i = i_first;
+#pragma unroll
+            for (int u = 0; u < kMaxOwn; ++u, i += kWarps) if (i < NBx) dmma(acc[u].x, acc[u].y, av[u].x, bx);
+            i = i_first;
+#pragma unroll
+            for (int u = 0; u < kMaxOwn; ++u, i += kWarps) if (i < NBx) dmma(accB[u].x, accB[u].y, av[u].y, by);
+            b = bn;
+#pragma unroll
+            for (int u = 0; u < kMaxOwn; ++u) av[u] = an[u];
+          }
+#pragma unroll
+          for (int u = 0; u < kMaxOwn; ++u) { acc[u].x += accB[u].x; acc[u].y += accB[u].y; }
+        }
+        switch (nown) {
+          case 1: accumulate_column<1, kWarps>(acc, M, dneg, j, i_first, fragC, fq); break;
+          case 2: accumulate_column<2, kWarps>(acc, M, dneg, j, i_first, fragC, fq); break;
+          case 3: accumulate_column<3, kWarps>(acc, M, dneg, j, i_first, fragC, fq); break;
+          case 4: accumulate_column<4, kWarps>(acc, M, dneg, j, i_first, fragC, fq); break;
+          default: break;
+        }
+        TR(11);
+        // --- diagonal tile: + rho (pass 1), then one thread factors it in registers
+        if (own_diag) {
+          if (pass == 1 && j0 + fr < n) {
+            if (fr == 2 * fq) acc[0].x += p.rho;
+            if (fr == 2 * fq + 1) acc[0].y += p.rho;
+          }
+          st2(M + tile_off(j, j) + fragC, acc[0]);
+          __syncwarp();
+          if (lane == 0) factor_diag_tile(M + tile_off(j, j), dinv + j0, dneg + j0);
+          TR(12);
+        }
         __syncthreads();
         FCCQP_PROF(3);
-        if (k + 1 < NB) {
-          // --- P2: L_ik = A_ik inv(L11)' inv(D11) for the tiles below the diagonal one
+        TR(13);
+        // --- (B) L_ij = C_ij inv(L_jj)' inv(D_j) for the own tiles below the diagonal
+        if (j + 1 < NB) {
+          const double2 li = ld2(M + tile_off(j, j) + fragC);
+          const double2 di = ld2(dinv + j0 + 2 * fq);
+          double2 wa[kMaxOwn], wb[kMaxOwn];
+#pragma unroll
+          for (int u = 0; u < kMaxOwn; ++u) { wa[u] = make_double2(0.0, 0.0); wb[u] = make_double2(0.0, 0.0); }
+#pragma unroll
+          for (int u = 0; u < kMaxOwn; ++u) if (u < nown) dmma(wa[u].x, wa[u].y, acc[u].x, li.x);
+#pragma unroll
+          for (int u = 0; u < kMaxOwn; ++u) if (u < nown) dmma(wb[u].x, wb[u].y, acc[u].y, li.y);
           {
-            const double2 li = *reinterpret_cast<const double2*>(dtile + fragC);
-            const double2 di = *reinterpret_cast<const double2*>(dinv + k0 + 2 * fq);
-            for (int i = k + 1 + warp; i < NB; i += kWarps) {
-              double2* ap = reinterpret_cast<double2*>(M + tile_off(i, k) + fragC);
-              double2 w = make_double2(0.0, 0.0);
-              mma8(w, *ap, li);
-              *ap = make_double2(w.x * di.x, w.y * di.y);
-            }
+            int i = i_first;
+#pragma unroll
+            for (int u = 0; u < kMaxOwn; ++u, i += kWarps)
+              if (u < nown && i > j)
+                st2(M + tile_off(i, j) + fragC, make_double2((wa[u].x + wb[u].x) * di.x, (wa[u].y + wb[u].y) * di.y));
           }
+          TR(14);
           __syncthreads();
-          FCCQP_PROF(4);
-          // --- P3: trailing tiles C_ij -= (L_ik D) L_jk', k < j <= i, split evenly over the warps
-          {
-            const int R = NB - 1 - k, T = R * (R + 1) / 2;
-            const int lo = T * warp / kWarps, hi = T * (warp + 1) / kWarps;
-            const double2 dn = *reinterpret_cast<const double2*>(dneg + k0 + 2 * fq);
-            int ri = 0, rj = lo;
-            while (rj > ri) { rj -= ri + 1; ++ri; }
-            int idx = lo;
-            while (idx < hi) {
-              const int cnt = min(ri - rj + 1, hi - idx);
-              const int i = k + 1 + ri;
-              double2 a = *reinterpret_cast<const double2*>(M + tile_off(i, k) + fragC);
-              a.x *= dn.x; a.y *= dn.y;   // -(L_ik D)
-              double* cp = M + tile_off(i, k + 1 + rj) + fragC;   // consecutive j: +64 doubles
-              int j = k + 1 + rj;
-              int c = 0;
-              for (; c + 1 < cnt; c += 2, j += 2, cp += 128) {
-                const double2 b0 = *reinterpret_cast<const double2*>(M + tile_off(j, k) + fragC);
-                const double2 b1 = *reinterpret_cast<const double2*>(M + tile_off(j + 1, k) + fragC);
-                double2 c0 = *reinterpret_cast<const double2*>(cp);
-                double2 c1 = *reinterpret_cast<const double2*>(cp + 64);
-                mma8(c0, a, b0);
-                mma8(c1, a, b1);
-                *reinterpret_cast<double2*>(cp) = c0;
-                *reinterpret_cast<double2*>(cp + 64) = c1;
-              }
-              if (c < cnt) {
-                const double2 b0 = *reinterpret_cast<const double2*>(M + tile_off(j, k) + fragC);
-                double2 c0 = *reinterpret_cast<const double2*>(cp);
-                mma8(c0, a, b0);
-                *reinterpret_cast<double2*>(cp) = c0;
-              }
-              idx += cnt;
-              rj += cnt;
-              if (rj > ri) { rj = 0; ++ri; }
-            }
-          }
-          __syncthreads();
-          FCCQP_PROF(5);
+          TR(15);
         }
+        FCCQP_PROF(4);
       }
       // ---------------- explicit inverses of the 32x32 diagonal blocks of L, in place ----------------
-      // level 1: 16x16 = [[X1,0],[-X2 L21 X1, X2]] from the 8x8 inverses left by P1
+      // level 1: 16x16 = [[X1,0],[-X2 L21 X1, X2]] from the 8x8 inverses left by the factorization
       for (int a = warp; 2 * a + 1 < NB; a += kWarps) {
         const double* x1 = M + tile_off(2 * a, 2 * a) + fragT;
-        double2* l21 = reinterpret_cast<double2*>(M + tile_off(2 * a + 1, 2 * a) + fragC);
-        const double2 x2 = *reinterpret_cast<const double2*>(M + tile_off(2 * a + 1, 2 * a + 1) + fragC);
+        double* l21 = M + tile_off(2 * a + 1, 2 * a) + fragC;
+        const double2 x2 = ld2(M + tile_off(2 * a + 1, 2 * a + 1) + fragC);
         double2 tt = make_double2(0.0, 0.0);                 // fragC((L21 X1)') = fragT(L21 X1)
-        mma8(tt, make_double2(x1[0], x1[8]), *l21);          // X1' L21'
+        mma8(tt, make_double2(x1[0], x1[8]), ld2(l21));      // X1' L21'
         double2 r = make_double2(0.0, 0.0);
         mma8(r, x2, tt);                                     // X2 (L21 X1)
-        *l21 = make_double2(-r.x, -r.y);
+        st2(l21, make_double2(-r.x, -r.y));
       }
       __syncthreads();
       // level 2: 32x32 = [[A,0],[-B L A, B]] with 16x16 A, B; one warp per (block, tile column).
@@ -558,17 +658,17 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
         if (act) {
           // T(:,col) = L A(:,col), kept transposed in registers
           double2 t0 = make_double2(0.0, 0.0), t1 = make_double2(0.0, 0.0);
-          const double2 l01 = *reinterpret_cast<const double2*>(M + tile_off(q4 + 2, q4 + 1) + fragC);
+          const double2 l01 = ld2(M + tile_off(q4 + 2, q4 + 1) + fragC);
           double2 l11 = make_double2(0.0, 0.0);
-          if (two) l11 = *reinterpret_cast<const double2*>(M + tile_off(q4 + 3, q4 + 1) + fragC);
+          if (two) l11 = ld2(M + tile_off(q4 + 3, q4 + 1) + fragC);
           if (col == 0) {
-            const double2 l00 = *reinterpret_cast<const double2*>(M + tile_off(q4 + 2, q4) + fragC);
+            const double2 l00 = ld2(M + tile_off(q4 + 2, q4) + fragC);
             const double* a00 = M + tile_off(q4, q4) + fragT;
             const double* a10 = M + tile_off(q4 + 1, q4) + fragT;
             const double2 f00 = make_double2(a00[0], a00[8]), f10 = make_double2(a10[0], a10[8]);
             mma8(t0, f00, l00); mma8(t0, f10, l01);          // T00' = A00' L00' + A10' L01'
             if (two) {
-              const double2 l10 = *reinterpret_cast<const double2*>(M + tile_off(q4 + 3, q4) + fragC);
+              const double2 l10 = ld2(M + tile_off(q4 + 3, q4) + fragC);
               mma8(t1, f00, l10); mma8(t1, f10, l11);        // T10'
             }
           } else {
@@ -578,24 +678,22 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
             if (two) mma8(t1, f11, l11);                     // T11'
           }
           // R(:,col) = B T(:,col)
-          const double2 b00 = *reinterpret_cast<const double2*>(M + tile_off(q4 + 2, q4 + 2) + fragC);
-          mma8(r0, b00, t0);
+          mma8(r0, ld2(M + tile_off(q4 + 2, q4 + 2) + fragC), t0);
           if (two) {
-            const double2 b10 = *reinterpret_cast<const double2*>(M + tile_off(q4 + 3, q4 + 2) + fragC);
-            const double2 b11 = *reinterpret_cast<const double2*>(M + tile_off(q4 + 3, q4 + 3) + fragC);
-            mma8(r1, b10, t0); mma8(r1, b11, t1);
+            mma8(r1, ld2(M + tile_off(q4 + 3, q4 + 2) + fragC), t0);
+            mma8(r1, ld2(M + tile_off(q4 + 3, q4 + 3) + fragC), t1);
           }
         }
         __syncthreads();
         if (act) {
-          *reinterpret_cast<double2*>(M + tile_off(q4 + 2, q4 + col) + fragC) = make_double2(-r0.x, -r0.y);
-          if (two)
-            *reinterpret_cast<double2*>(M + tile_off(q4 + 3, q4 + col) + fragC) = make_double2(-r1.x, -r1.y);
+          st2(M + tile_off(q4 + 2, q4 + col) + fragC, make_double2(-r0.x, -r0.y));
+          if (two) st2(M + tile_off(q4 + 3, q4 + col) + fragC, make_double2(-r1.x, -r1.y));
         }
       }
       __syncthreads();
       fact_cycles += (unsigned long long)(clock64() - t_f0);
       FCCQP_PROF(6);
+      TR(20);
 
       if (pass == 1) {
         // ADMM initial slack (fcc_qp.cpp:74-75): x_bar = x, lambda_c_bar = x[lambda_c segment]
@@ -621,6 +719,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
         } else if (is_c) {
           acc = v_b;
         }
+        TR(30);
         // ---- forward: L y = rhs, 32 rows per step (warp J applies inv(L_JJ), later warps subtract)
         double val = 0.0;
         for (int J = 0; J < NB32; ++J) {
@@ -628,81 +727,95 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
           if (warp == J) {
             tbuf[t] = acc;
             __syncwarp();
-            double s0 = 0.0, s1 = 0.0;
-            if (is_row) {
-              for (int jb = Jb0; jb <= tb; ++jb) {
-                const double2* xr = reinterpret_cast<const double2*>(M + tile_off(tb, jb) + tr * 8);
-                const double2* tv = reinterpret_cast<const double2*>(tbuf + jb * 8);
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {   // logical chunk c lives at physical chunk c ^ tf
-                  const double2 x = xr[c ^ tf], v = tv[c];
-                  s0 += x.x * v.x; s1 += x.y * v.y;
-                }
+            for (int u = 0; u < 4; ++u) {
+              const int jb = Jb0 + u;
+              if (jb <= tb && is_row) {
+                const double* xr = M + tile_off(tb, jb) + tr * 8;
+                const double* tv = tbuf + jb * 8;
+                const double2 x0 = ld2(xr + 2 * (0 ^ tf)), x1 = ld2(xr + 2 * (1 ^ tf));
+                const double2 x2 = ld2(xr + 2 * (2 ^ tf)), x3 = ld2(xr + 2 * (3 ^ tf));
+                const double2 v0 = ld2(tv), v1 = ld2(tv + 2), v2 = ld2(tv + 4), v3 = ld2(tv + 6);
+                s0 += x0.x * v0.x; s1 += x0.y * v0.y; s2 += x1.x * v1.x; s3 += x1.y * v1.y;
+                s0 += x2.x * v2.x; s1 += x2.y * v2.y; s2 += x3.x * v3.x; s3 += x3.y * v3.y;
               }
             }
-            val = s0 + s1;
+            val = (s0 + s1) + (s2 + s3);
             ybuf[t] = val;
           }
+          TR(31);
           __syncthreads();
+          TR(32);
           if (warp > J && is_row) {
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
-              const double2* lr = reinterpret_cast<const double2*>(M + tile_off(tb, Jb0 + jj) + tr * 8);
-              const double2* yv = reinterpret_cast<const double2*>(ybuf + (Jb0 + jj) * 8);
-#pragma unroll
-              for (int c = 0; c < 4; c += 2) {
-                const double2 l0 = lr[c ^ tf], y0 = yv[c];
-                const double2 l1 = lr[(c + 1) ^ tf], y1 = yv[c + 1];
-                s0 += l0.x * y0.x; s1 += l0.y * y0.y;
-                s2 += l1.x * y1.x; s3 += l1.y * y1.y;
-              }
+              const double* lr = M + tile_off(tb, Jb0 + jj) + tr * 8;
+              const double* yv = ybuf + (Jb0 + jj) * 8;
+              const double2 l0 = ld2(lr + 2 * (0 ^ tf)), l1 = ld2(lr + 2 * (1 ^ tf));
+              const double2 l2 = ld2(lr + 2 * (2 ^ tf)), l3 = ld2(lr + 2 * (3 ^ tf));
+              const double2 y0 = ld2(yv), y1 = ld2(yv + 2), y2 = ld2(yv + 4), y3 = ld2(yv + 6);
+              s0 += l0.x * y0.x; s1 += l0.y * y0.y; s2 += l1.x * y1.x; s3 += l1.y * y1.y;
+              s0 += l2.x * y2.x; s1 += l2.y * y2.y; s2 += l3.x * y3.x; s3 += l3.y * y3.y;
             }
             acc -= (s0 + s1) + (s2 + s3);
           }
         }
         // ---- D^{-1}
         acc = is_row ? val * dinv[t] : 0.0;
-        // ---- backward: L' x = y
+        // ---- backward: L' x = y (column-per-thread reads; odd tile columns take row pairs swapped)
         for (int J = NB32 - 1; J >= 0; --J) {
           const int Jb0 = J * 4, Jb1 = min(Jb0 + 4, NB);
-          const int colo = tr & 1, colc = tr >> 1;
           if (warp == J) {
             tbuf[t] = acc;
             __syncwarp();
-            double s0 = 0.0, s1 = 0.0;
-            if (is_row) {
-              for (int ib = tb; ib < Jb1; ++ib) {
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int ib = tb + u;
+              if (ib < Jb1 && is_row) {
                 const double* xc = M + tile_off(ib, tb) + colo;
                 const double* tv = tbuf + ib * 8;
 #pragma unroll
-                for (int r = 0; r < 8; r += 2) {
-                  s0 += xc[r * 8 + (((colc ^ (r >> 1)) & 3) << 1)] * tv[r];
-                  s1 += xc[(r + 1) * 8 + (((colc ^ (r >> 1)) & 3) << 1)] * tv[r + 1];
+                for (int r = 0; r < 8; r += 4) {
+                  const int sw0 = ((colc ^ (r >> 1)) & 3) << 1, sw1 = ((colc ^ ((r + 2) >> 1)) & 3) << 1;
+                  s0 += xc[r * 8 + flip8 + sw0] * tv[r + flip];
+                  s1 += xc[(r + 1) * 8 - flip8 + sw0] * tv[r + 1 - flip];
+                  s2 += xc[(r + 2) * 8 + flip8 + sw1] * tv[r + 2 + flip];
+                  s3 += xc[(r + 3) * 8 - flip8 + sw1] * tv[r + 3 - flip];
                 }
               }
             }
-            val = s0 + s1;
+            val = (s0 + s1) + (s2 + s3);
             ybuf[t] = val;
           }
+          TR(33);
           __syncthreads();
+          TR(34);
           if (warp < J) {
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            for (int ib = Jb0; ib < Jb1; ++ib) {
-              const double* lc = M + tile_off(ib, tb) + colo;
-              const double* yv = ybuf + ib * 8;
 #pragma unroll
-              for (int r = 0; r < 8; r += 4) {
-                s0 += lc[r * 8 + (((colc ^ (r >> 1)) & 3) << 1)] * yv[r];
-                s1 += lc[(r + 1) * 8 + (((colc ^ (r >> 1)) & 3) << 1)] * yv[r + 1];
-                s2 += lc[(r + 2) * 8 + (((colc ^ ((r + 2) >> 1)) & 3) << 1)] * yv[r + 2];
-                s3 += lc[(r + 3) * 8 + (((colc ^ ((r + 2) >> 1)) & 3) << 1)] * yv[r + 3];
+            for (int u = 0; u < 4; ++u) {
+              const int ib = Jb0 + u;
+              if (ib < Jb1) {
+                const double* lc = M + tile_off(ib, tb) + colo;
+                const double* yv = ybuf + ib * 8;
+#pragma unroll
+                for (int r = 0; r < 8; r += 4) {
+                  const int sw0 = ((colc ^ (r >> 1)) & 3) << 1, sw1 = ((colc ^ ((r + 2) >> 1)) & 3) << 1;
+                  s0 += lc[r * 8 + flip8 + sw0] * yv[r + flip];
+                  s1 += lc[(r + 1) * 8 - flip8 + sw0] * yv[r + 1 - flip];
+                  s2 += lc[(r + 2) * 8 + flip8 + sw1] * yv[r + 2 + flip];
+                  s3 += lc[(r + 3) * 8 - flip8 + sw1] * yv[r + 3 - flip];
+                }
               }
             }
             acc -= (s0 + s1) + (s2 + s3);
           }
         }
         FCCQP_PROF(7);
+        TR(35);
         // val = solution component of row t (t < N8)
 
         if (pass == 0) {
@@ -713,24 +826,47 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
             __syncthreads();
             double r = 0.0;
             if (is_x) {
-              double s0 = 0.0, s1 = 0.0;
-#pragma unroll 10
-              for (int j = 0; j < n; ++j) s0 += Qg[j * q_slow + t * q_fast] * sbuf[j];           // Q symmetric
-#pragma unroll 10
-              for (int k = 0; k < m; ++k) s1 += Ag[k * p.a_rs + t * p.a_cs] * sbuf[n8 + k];      // A' y
-              r = -v_b - s0 - s1;
-            }
-            // rows of A: warp per row pair, lanes over columns
-            for (int k = 2 * warp; k < m; k += 2 * kWarps) {
-              double s0 = 0.0, s1 = 0.0;
-              const bool two = k + 1 < m;
-              for (int j = lane; j < n; j += 32) {
-                const double xj = sbuf[j];
-                s0 += Ag[k * p.a_rs + j * p.a_cs] * xj;
-                if (two) s1 += Ag[(k + 1) * p.a_rs + j * p.a_cs] * xj;
+              // 16 independent L2 loads in flight per thread; Q symmetric: column t == row t
+              double sacc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+              for (int part = 0; part < 2; ++part) {
+                const double* gp = part == 0 ? Qg + t * q_fast : Ag + t * p.a_cs;
+                const long long gs = part == 0 ? q_slow : p.a_rs;
+                const double* sv = part == 0 ? sbuf : sbuf + n8;
+                const int cnt = part == 0 ? n : m;
+                int j = 0;
+#pragma unroll 1
+                for (; j + 16 <= cnt; j += 16, sv += 16) {
+                  double v[16];
+#pragma unroll
+                  for (int u = 0; u < 16; ++u) { v[u] = *gp; gp += gs; }
+#pragma unroll
+                  for (int u = 0; u < 16; ++u) sacc[u & 3] += v[u] * sv[u];
+                }
+#pragma unroll 1
+                for (; j < cnt; ++j, gp += gs, ++sv) sacc[0] += *gp * *sv;
               }
-              s0 = warp_sum(s0); s1 = warp_sum(s1);
-              if (lane == 0) { ybuf[n8 + k] = s0; if (two) ybuf[n8 + k + 1] = s1; }
+              r = -v_b - ((sacc[0] + sacc[1]) + (sacc[2] + sacc[3]));
+            }
+            // rows of A: four rows per warp at a time, lanes over columns
+#pragma unroll 1
+            for (int k = 4 * warp; k < m; k += 4 * kWarps) {
+              double sr[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+              for (int jc = lane; jc < n; jc += 32) {
+                const double xj = sbuf[jc];
+                const double* gp = Ag + (long long)k * p.a_rs + jc * p.a_cs;
+#pragma unroll
+                for (int u = 0; u < 4; ++u, gp += p.a_rs)
+                  if (k + u < m) sr[u] += *gp * xj;
+              }
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) sr[u] += __shfl_xor_sync(0xffffffffu, sr[u], o);
+              }
+              if (lane < 4 && k + lane < m)
+                ybuf[n8 + k + lane] = lane == 0 ? sr[0] : lane == 1 ? sr[1] : lane == 2 ? sr[2] : sr[3];
             }
             __syncthreads();
             if (is_c) r = v_b - ybuf[t];
@@ -742,6 +878,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
             __syncthreads();
           }
           FCCQP_PROF(8);
+          TR(41);
           continue;
         }
 
@@ -768,14 +905,21 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
         }
         // fmax drops NaNs, so flag them separately
         if (rx != rx || rc != rc) status_flag = 2;
-        block_reduce2<false>(rx, rc, red, parity);
-        res_x = rx; res_c = rc;
+        // exit test (fcc_qp.cpp:105-109) as one hardware barrier-reduction; the infinity norms
+        // themselves are only needed for the iteration that ends the loop
+        const int conv = __syncthreads_and((rc < p.eps_fcone) && (rx < p.eps_bound));
         FCCQP_PROF(9);
+        TR(51);
         if (p.prof && tid == 0) s_prof[15] += 1;
-        if (rc < p.eps_fcone && rx < p.eps_bound) { n_iter = iter; break; }  // fcc_qp.cpp:105-109
+        if (conv || iter + 1 == iters) {
+          block_reduce2<false>(rx, rc, red, parity);
+          res_x = rx; res_c = rc;
+          if (conv) { n_iter = iter; break; }
+        }
       }
     }
 
+    TR(60);
     // ---------------- K6: epilogue ----------------
     __syncthreads();
     double bv = 0.0, fv = 0.0;
@@ -810,11 +954,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
       }
     }
     FCCQP_PROF(10);
+    TR(61);
+    trbuf = nullptr;
     if (p.prof && tid == 0) s_prof[14] += 1;
   }
   if (p.prof && tid == 0)
     for (int i = 0; i < 16; ++i) atomicAdd(p.prof + i, s_prof[i]);
 #undef FCCQP_PROF
+#undef TR
 }
 
 }  // namespace fccqp
