@@ -43,8 +43,11 @@ def build_cuda(force=False, verbose=False, extra=()):
            [os.path.join(ROOT, "include", "fccqp.h")]
     if force or _stale(LIB, srcs):
         nvcc = os.environ.get("NVCC", "nvcc")
+        # FCCQP_DEV=1 compiles the developer instrumentation in (FCCQP_PROFILE / FCCQP_TRACE); the
+        # production build leaves it out: the hot loops have to fit the instruction cache.
+        dev = ["-DFCCQP_DEV"] if os.environ.get("FCCQP_DEV") else []
         _run([nvcc, *NVCC_ARCH, "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
-              *extra, "-o", LIB, os.path.join(CSRC, "fccqp_capi.cu")], verbose)
+              *dev, *extra, "-o", LIB, os.path.join(CSRC, "fccqp_capi.cu")], verbose)
     return LIB
 
 

@@ -286,57 +286,89 @@ __device__ __forceinline__ void factor_diag_tile(double* __restrict__ tile, doub
   }
 }
 
-// Step (A) of the left-looking factorization for the kOwn tiles (i = i_first + u * kStride, column j)
-// owned by this warp:  acc[u] -= sum_{k<j} L_ik D_k L_jk'.  Tiles of one tile row are contiguous
-// (64 doubles apart), so every operand pointer just advances.  Software-pipelined by hand (a warp
-// issues in order): the operands of step k+1 are loaded before the DMMAs of step k are issued,
-// and the two DMMAs of a tile product go to different accumulators so that no DMMA waits for the
-// one before it.  The prefetch of step j reads the column's own tiles: harmless, never used.
-template <int kOwn, int kStride>
-__device__ __forceinline__ void accumulate_column(double2 (&acc)[4], const double* __restrict__ M,
-                                                  const double* __restrict__ dneg, int j, int i_first,
-                                                  int fragC, int fq) {
-  const double* ap[kOwn];
-  double2 a[kOwn], accB[kOwn];
-  const double* bp = M + tile_off(j, 0) + fragC;
-  const double* dp = dneg + 2 * fq;
-  double2 b = ld2(bp), d = ld2(dp);
-#pragma unroll
-  for (int u = 0; u < kOwn; ++u) {
-    ap[u] = M + tile_off(i_first + u * kStride, 0) + fragC;
-    a[u] = ld2(ap[u]);
-    accB[u] = make_double2(0.0, 0.0);
-  }
-#pragma unroll 2
-  for (int k = 0; k < j; ++k) {
-    bp += 64; dp += 8;
-    const double2 bn = ld2(bp), dn = ld2(dp);
-    double2 an[kOwn];
-#pragma unroll
-    for (int u = 0; u < kOwn; ++u) { ap[u] += 64; an[u] = ld2(ap[u]); }
-    const double bx = b.x * d.x, by = b.y * d.y;
-#pragma unroll
-    for (int u = 0; u < kOwn; ++u) dmma(acc[u].x, acc[u].y, a[u].x, bx);
-#pragma unroll
-    for (int u = 0; u < kOwn; ++u) dmma(accB[u].x, accB[u].y, a[u].y, by);
-    b = bn; d = dn;
-#pragma unroll
-    for (int u = 0; u < kOwn; ++u) a[u] = an[u];
-  }
-#pragma unroll
-  for (int u = 0; u < kOwn; ++u) { acc[u].x += accB[u].x; acc[u].y += accB[u].y; }
+// Named barriers (ids 1..15; 0 is __syncthreads): producer warps arrive, consumer warps sync,
+// `count` = all threads taking part either way.  The fence makes the producer's shared-memory
+// writes visible before the arrival is counted.
+__device__ __forceinline__ void bar_arrive(int id, int count) {
+  __threadfence_block();
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
+__device__ __forceinline__ void bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// In-place left-looking update of ONE tile:  C(i,c) -= sum_{k<kend} L_ik D_k L_ck'.
+// Tiles of one tile row are contiguous (64 doubles apart), so the operand pointers just advance.
+// The two DMMAs of a tile product go to different accumulators (no DMMA waits for the one
+// before it) and the loop is unrolled twice so that loads run ahead of the DMMAs.
+__device__ __forceinline__ void update_tile(double* __restrict__ M, const double* __restrict__ dneg, int i, int c,
+                                            int kend, int fragC, int fq) {
+  double* cp = M + tile_off(i, c) + fragC;
+  const double* ap = M + tile_off(i, 0) + fragC;
+  const double* bp = M + tile_off(c, 0) + fragC;
+  const double* dp = dneg + 2 * fq;
+  double2 ca = ld2(cp), cb = make_double2(0.0, 0.0);
+#pragma unroll 2
+  for (int k = 0; k < kend; ++k, ap += 64, bp += 64, dp += 8) {
+    const double2 a = ld2(ap), b = ld2(bp), d = ld2(dp);
+    dmma(ca.x, ca.y, a.x, b.x * d.x);
+    dmma(cb.x, cb.y, a.y, b.y * d.y);
+  }
+  st2(cp, make_double2(ca.x + cb.x, ca.y + cb.y));
+}
+
+// Row-per-thread dot product over one tile: sum_c T[row][c] * v[c]   (trow = tile + row*8, tf = row/2)
+__device__ __forceinline__ double row_dot8(const double* __restrict__ trow, int tf, const double* __restrict__ v) {
+  const double2 x0 = ld2(trow + 2 * (0 ^ tf)), x1 = ld2(trow + 2 * (1 ^ tf));
+  const double2 x2 = ld2(trow + 2 * (2 ^ tf)), x3 = ld2(trow + 2 * (3 ^ tf));
+  const double2 v0 = ld2(v), v1 = ld2(v + 2), v2 = ld2(v + 4), v3 = ld2(v + 6);
+  return ((x0.x * v0.x + x0.y * v0.y) + (x1.x * v1.x + x1.y * v1.y)) +
+         ((x2.x * v2.x + x2.y * v2.y) + (x3.x * v3.x + x3.y * v3.y));
+}
+// Column-per-thread dot product over one tile: sum_r T[r][col] * v[r]   (tcol = tile + (col&1), colc = col/2).
+// flip (0/1) swaps the rows of every row pair: odd tile columns start on the other half of the banks.
+__device__ __forceinline__ double col_dot8(const double* __restrict__ tcol, int colc, int flip,
+                                           const double* __restrict__ v) {
+  double s0 = 0.0, s1 = 0.0;
+  const int f8 = flip << 3;
+#pragma unroll
+  for (int r = 0; r < 8; r += 2) {
+    const int sw = ((colc ^ (r >> 1)) & 3) << 1;
+    s0 += tcol[r * 8 + f8 + sw] * v[r + flip];
+    s1 += tcol[(r + 1) * 8 - f8 + sw] * v[r + 1 - flip];
+  }
+  return s0 + s1;
+}
+
+#ifdef FCCQP_DEV
+#define FCCQP_PROF(slot)                                                   \
+  do {                                                                     \
+    if (p.prof && tid == 0) {                                              \
+      const long long t_now = clock64();                                   \
+      s_prof[slot] += (unsigned long long)(t_now - t_prof);                \
+      t_prof = t_now;                                                      \
+    }                                                                      \
+  } while (0)
+#define TR(tag)                                                                                      \
+  do {                                                                                               \
+    if (trbuf && lane == 0 && trn < 4096) trbuf[trn++] = ((unsigned long long)clock64() << 8) | (unsigned)(tag); \
+  } while (0)
+#else
+#define FCCQP_PROF(slot) do { } while (0)
+#define TR(tag) do { } while (0)
+#endif
 
 // ---------------------------------------------------------------------------
 // The fused solve kernel.  kThreads >= padded KKT size N8 (one thread per KKT row in the
-// triangular solves and all vector work); at most kMaxOwn tile rows per warp.
+// triangular solves and all vector work).  Warp 0 is the factorization's critical-path warp,
+// warps 1.. are its helpers.
 // ---------------------------------------------------------------------------
 template <int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const SolveParams p) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kWarps = kThreads / 32;
-  constexpr int kMaxOwn = 4;   // N8 <= kThreads  =>  NB <= 4 * kWarps
+  constexpr int kHelpers = kWarps - 1;
   const int n = p.n, m = p.m, nc = p.nc, lcs = p.lcs;
   const int n8 = p.lay.n8, N8 = p.lay.N8, NB = p.lay.NB, NBx = p.lay.NBx, NB32 = p.lay.NB32;
 
@@ -353,25 +385,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
   double* const red = smem + p.lay.off_red;
   int* const ibuf = reinterpret_cast<int*>(smem + p.lay.off_int);
   int* const s_work = ibuf;  // [1]
+#ifdef FCCQP_DEV
   unsigned long long* const s_prof = reinterpret_cast<unsigned long long*>(ibuf + 2);  // [16]
   long long t_prof = 0;
   if (p.prof && tid == 0) { for (int i = 0; i < 16; ++i) s_prof[i] = 0; t_prof = clock64(); }
-#define FCCQP_PROF(slot)                                                   \
-  do {                                                                     \
-    if (p.prof && tid == 0) {                                              \
-      const long long t_now = clock64();                                   \
-      s_prof[slot] += (unsigned long long)(t_now - t_prof);                \
-      t_prof = t_now;                                                      \
-    }                                                                      \
-  } while (0)
-
   // developer tracing: lane 0 of every warp of CTA 0 logs (clock, tag) for the first QP it solves
   unsigned long long* trbuf = (p.trace && blockIdx.x == 0) ? p.trace + warp * 4096 : nullptr;
   int trn = 0;
-#define TR(tag)                                                                                      \
-  do {                                                                                               \
-    if (trbuf && lane == 0 && trn < 4096) trbuf[trn++] = ((unsigned long long)clock64() << 8) | (unsigned)(tag); \
-  } while (0)
+#endif
 
   int parity = 0;
   // thread-per-row identity: rows [0,n) variables, [n,n8) pads, [n8,n8+m) constraints, rest pads
@@ -382,7 +403,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
   const bool in_cone = is_x && t >= lcs && t < lcs + nc;
   const int tb = t >> 3, tr = t & 7, tf = tr >> 1;  // tile row, row in tile, row swizzle
   const int colo = tr & 1, colc = tr >> 1;          // column-per-thread access: element (r, tr) of a tile
-  const int flip = tb & 1, flip8 = flip << 3;       // odd tile columns walk row pairs swapped (bank spread)
+  const int flip = tb & 1;                          // odd tile columns walk row pairs swapped (bank spread)
+  const int tbe = tb < NB ? tb : NB - 1;            // clamped tile row (threads beyond N8 read valid data, masked)
   // tensor-core fragment coordinates of this lane
   const int fr = lane >> 2, fq = lane & 3;
   const int fragC = (fr << 3) + (((fq ^ (fr >> 1)) & 3) << 1);                       // (fr, 2fq..2fq+1)
@@ -445,15 +467,17 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
 
       // ---------------- assemble the lower tiles of the padded KKT matrix ----------------
       // one warp per tile, lane = (row fr, column pair 2fq): 8 x 64-byte row segments from HBM/L2.
-      // Three uniform loops (Q tiles, A tiles, zero tiles), tile rows outer, warps strided over columns.
+      // Tile rows outer, warps strided over the tile columns.
       {
         const int gc0 = 2 * fq;
         // Q (symmetric; row read along the contiguous direction), unit pivots on the pads
         const double* qrow = Qg + fr * q_slow + gc0 * q_fast;
+#pragma unroll 1
         for (int I = 0; I < NBx; ++I, qrow += 8 * q_slow) {
           const int gi = 8 * I + fr;
           double* dst = M + tile_off(I, warp) + fragC;
           const double* src = qrow + (8 * warp) * q_fast;
+#pragma unroll 1
           for (int J = warp; J <= I; J += kWarps, dst += 64 * kWarps, src += 8 * kWarps * q_fast) {
             const int gc = 8 * J + gc0;
             if (q_vec) {
@@ -467,10 +491,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
         }
         // A rows below it
         const double* arow = Ag + (long long)fr * p.a_rs + gc0 * p.a_cs;
+#pragma unroll 1
         for (int I = NBx; I < NB; ++I, arow += 8 * p.a_rs) {
           const int k = 8 * (I - NBx) + fr;
           double* dst = M + tile_off(I, warp) + fragC;
           const double* src = arow + (8 * warp) * p.a_cs;
+#pragma unroll 1
           for (int J = warp; J < NBx; J += kWarps, dst += 64 * kWarps, src += 8 * kWarps * p.a_cs) {
             const int gc = 8 * J + gc0;
             if (a_vec) {
@@ -482,6 +508,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
           }
           // (2,2) block: zero; decoupled unit pivots on the constraint pads
           dst = M + tile_off(I, NBx + warp) + fragC;
+#pragma unroll 1
           for (int J = NBx + warp; J <= I; J += kWarps, dst += 64 * kWarps) {
             const bool dg = J == I && k >= m;
             st2(dst, make_double2((dg && fr == gc0) ? 1.0 : 0.0, (dg && fr == gc0 + 1) ? 1.0 : 0.0));
@@ -495,146 +522,128 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
       TR(4);
 
       double rhs0 = 0.0;   // pass-0 right-hand side of row t
-      double sigma = 0.0;  // pass-0 augmented-Lagrangian weight
-      if (pass == 0) {
+      if (pass == 1) {
+        if (is_x) M[mat_off(t, t)] += p.rho;
+      } else {
         // sigma = trace(Q) / ||A||_F^2 balances the two terms of Q + sigma A'A
         double trq = is_x ? M[mat_off(t, t)] : 0.0, fro = 0.0;
         if (is_c) {
           tbuf[t] = v_b;
+#pragma unroll 1
           for (int jb = 0; jb < NBx; ++jb) {
             const double* row = M + tile_off(tb, jb) + tr * 8;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { const double2 v = ld2(row + 2 * (c ^ tf)); fro += v.x * v.x + v.y * v.y; }
+            for (int c = 0; c < 4; ++c) { const double2 v = ld2(row + 2 * c); fro += v.x * v.x + v.y * v.y; }
           }
         }
         block_reduce2<true>(trq, fro, red, parity);
-        sigma = (trq > 0.0 && fro > 0.0 && isfinite(trq / fro)) ? trq / fro : 1.0;
+        const double sigma = (trq > 0.0 && fro > 0.0 && isfinite(trq / fro)) ? trq / fro : 1.0;
         // rhs_x = -b + sigma A' b_eq (needs A before the factorization overwrites it)
         if (is_x) {
-          double s0 = 0.0, s1 = 0.0;
-          for (int ib = NBx; ib < NB; ++ib) {
-            const double* tl = M + tile_off(ib, tb) + colo;
-            const double* bq = tbuf + ib * 8;
-#pragma unroll
-            for (int r = 0; r < 8; r += 2) {
-              const int sw = ((colc ^ (r >> 1)) & 3) << 1;
-              s0 += tl[r * 8 + flip8 + sw] * bq[r + flip];
-              s1 += tl[(r + 1) * 8 - flip8 + sw] * bq[r + 1 - flip];
-            }
-          }
-          rhs0 = -v_b + sigma * (s0 + s1);
+          double s = 0.0;
+#pragma unroll 1
+          for (int ib = NBx; ib < NB; ++ib) s += col_dot8(M + tile_off(ib, tb) + colo, colc, flip, tbuf + ib * 8);
+          rhs0 = -v_b + sigma * s;
         } else if (is_c) {
           rhs0 = v_b;
         }
+        // H += sigma A'A on the tiles of the variable block, in place, one tile per warp at a time
+        {
+          int I = 0, J = warp;
+          while (J > I) { J -= I + 1; ++I; }
+#pragma unroll 1
+          for (; I < NBx;) {
+            double2 sa = make_double2(0.0, 0.0), sb = make_double2(0.0, 0.0);
+            const double* ai = M + tile_off(NBx, I) + fragT;
+            const double* aj = M + tile_off(NBx, J) + fragT;
+#pragma unroll 2
+            for (int kb = NBx; kb < NB; ++kb) {
+              dmma(sa.x, sa.y, ai[0], aj[0]);
+              dmma(sb.x, sb.y, ai[8], aj[8]);
+              ai += 64 * (kb + 1); aj += 64 * (kb + 1);
+            }
+            double* cp = M + tile_off(I, J) + fragC;
+            const double2 c = ld2(cp);
+            st2(cp, make_double2(c.x + sigma * (sa.x + sb.x), c.y + sigma * (sa.y + sb.y)));
+            J += kWarps;
+            while (J > I) { J -= I + 1; ++I; }
+          }
+        }
       }
+      __syncthreads();
       FCCQP_PROF(2);
       TR(5);
 
       // ---------------- unpivoted blocked left-looking LDL^T on 8x8 tiles ----------------
-      for (int j = 0; j < NB; ++j) {
-        const int j0 = j * 8;
-        const int i_first = j + ((warp - j) & (kWarps - 1));   // first own tile row >= j
-        const bool own_diag = i_first == j;
-        const int nown = i_first < NB ? (NB - i_first + kWarps - 1) / kWarps : 0;   // own tiles in column j
-        TR(10);
-        // --- (A) accumulate the own tiles of column j in registers
-        double2 acc[kMaxOwn];
-        {
-          int i = i_first;
-#pragma unroll
-          for (int u = 0; u < kMaxOwn; ++u, i += kWarps)
-            acc[u] = u < nown ? ld2(M + tile_off(i, j) + fragC) : make_double2(0.0, 0.0);
-        }
-        if (pass == 0 && j < NBx) {
-          // + sigma A'A on the tiles of the variable block (A is still unfactored in columns >= j);
-          // operands of the next A tile row are loaded before the DMMAs of this one
-          double2 accB[kMaxOwn];
-#pragma unroll
-          for (int u = 0; u < kMaxOwn; ++u) accB[u] = make_double2(0.0, 0.0);
-          const double* arow = M + tile_off(NBx, 0) + fragT;
-          double2 b = make_double2(arow[64 * j], arow[64 * j + 8]);
-          double2 av[kMaxOwn];
-          {
-            int i = i_first;
-#pragma unroll
-            for (int u = 0; u < kMaxOwn; ++u, i += kWarps) {
-              const int ie = i < NBx ? i : j;   // clamp: tiles outside the variable block are masked below
-              av[u] = make_double2(arow[64 * ie], arow[64 * ie + 8]);
-            }
-          }
+      // Warp 0 runs the critical path: factor the diagonal tile (one thread, registers), turn the
+      // tile below it into L, bring the next diagonal tile up to date, signal.  The helper warps
+      // stay one tile column behind: they finish the L tiles of column j, then accumulate column
+      // j+1 (and the part of the diagonal tile j+2 that does not need column j+1) in place.
+      if (warp == 0) {
 #pragma unroll 1
-          for (int kb = NBx; kb < NB; ++kb) {
-            arow += 64 * (kb + 1);            // next tile row (over-read after the last one: harmless)
-            const double2 bn = make_double2(arow[64 * j], arow[64 * j + 8]);
-            double2 an[kMaxOwn];
-            int i = i_first;
-#pragma unroll
-            for (int u = 0; u < kMaxOwn; ++u, i += kWarps) {
-              const int ie = i < NBx ? i : j;
-              an[u] = make_double2(arow[64 * ie], arow[64 * ie + 8]);
-            }
-            const double bx = sigma * b.x, by = sigma * b.y;
-            i = i_first;
-#pragma unroll
-            for (int u = 0; u < kMaxOwn; ++u, i += kWarps) if (i < NBx) dmma(acc[u].x, acc[u].y, av[u].x, bx);
-            i = i_first;
-#pragma unroll
-            for (int u = 0; u < kMaxOwn; ++u, i += kWarps) if (i < NBx) dmma(accB[u].x, accB[u].y, av[u].y, by);
-            b = bn;
-#pragma unroll
-            for (int u = 0; u < kMaxOwn; ++u) av[u] = an[u];
-          }
-#pragma unroll
-          for (int u = 0; u < kMaxOwn; ++u) { acc[u].x += accB[u].x; acc[u].y += accB[u].y; }
-        }
-        switch (nown) {
-          case 1: accumulate_column<1, kWarps>(acc, M, dneg, j, i_first, fragC, fq); break;
-          case 2: accumulate_column<2, kWarps>(acc, M, dneg, j, i_first, fragC, fq); break;
-          case 3: accumulate_column<3, kWarps>(acc, M, dneg, j, i_first, fragC, fq); break;
-          case 4: accumulate_column<4, kWarps>(acc, M, dneg, j, i_first, fragC, fq); break;
-          default: break;
-        }
-        TR(11);
-        // --- diagonal tile: + rho (pass 1), then one thread factors it in registers
-        if (own_diag) {
-          if (pass == 1 && j0 + fr < n) {
-            if (fr == 2 * fq) acc[0].x += p.rho;
-            if (fr == 2 * fq + 1) acc[0].y += p.rho;
-          }
-          st2(M + tile_off(j, j) + fragC, acc[0]);
+        for (int j = 0; j < NB; ++j) {
+          double* dt = M + tile_off(j, j);
+          if (lane == 0) factor_diag_tile(dt, dinv + 8 * j, dneg + 8 * j);
           __syncwarp();
-          if (lane == 0) factor_diag_tile(M + tile_off(j, j), dinv + j0, dneg + j0);
           TR(12);
-        }
-        __syncthreads();
-        FCCQP_PROF(3);
-        TR(13);
-        // --- (B) L_ij = C_ij inv(L_jj)' inv(D_j) for the own tiles below the diagonal
-        if (j + 1 < NB) {
-          const double2 li = ld2(M + tile_off(j, j) + fragC);
-          const double2 di = ld2(dinv + j0 + 2 * fq);
-          double2 wa[kMaxOwn], wb[kMaxOwn];
-#pragma unroll
-          for (int u = 0; u < kMaxOwn; ++u) { wa[u] = make_double2(0.0, 0.0); wb[u] = make_double2(0.0, 0.0); }
-#pragma unroll
-          for (int u = 0; u < kMaxOwn; ++u) if (u < nown) dmma(wa[u].x, wa[u].y, acc[u].x, li.x);
-#pragma unroll
-          for (int u = 0; u < kMaxOwn; ++u) if (u < nown) dmma(wb[u].x, wb[u].y, acc[u].y, li.y);
-          {
-            int i = i_first;
-#pragma unroll
-            for (int u = 0; u < kMaxOwn; ++u, i += kWarps)
-              if (u < nown && i > j)
-                st2(M + tile_off(i, j) + fragC, make_double2((wa[u].x + wb[u].x) * di.x, (wa[u].y + wb[u].y) * di.y));
+          if (j > 0) bar_sync(3 + ((j - 1) & 1), kThreads);   // helpers finished step j-1
+          if (j + 1 < NB) {
+            const double2 li = ld2(dt + fragC), di = ld2(dinv + 8 * j + 2 * fq);
+            double* lp = M + tile_off(j + 1, j) + fragC;
+            const double2 c = ld2(lp);
+            double2 t1 = ld2(lp + 64);                       // tile (j+1, j+1)
+            double2 wa = make_double2(0.0, 0.0), wb = make_double2(0.0, 0.0);
+            dmma(wa.x, wa.y, c.x, li.x);
+            dmma(wb.x, wb.y, c.y, li.y);
+            const double wx = wa.x + wb.x, wy = wa.y + wb.y;   // L D
+            const double2 l = make_double2(wx * di.x, wy * di.y);
+            st2(lp, l);
+            double2 t2 = make_double2(0.0, 0.0);
+            dmma(t1.x, t1.y, -wx, l.x);
+            dmma(t2.x, t2.y, -wy, l.y);
+            st2(lp + 64, make_double2(t1.x + t2.x, t1.y + t2.y));
           }
-          TR(14);
-          __syncthreads();
-          TR(15);
+          bar_arrive(1 + (j & 1), kThreads);                  // column j: inv(L_jj), D_j, L_{j+1,j} ready
+          TR(13);
         }
-        FCCQP_PROF(4);
+        bar_sync(3 + ((NB - 1) & 1), kThreads);
+      } else {
+#pragma unroll 1
+        for (int j = 0; j < NB; ++j) {
+          bar_sync(1 + (j & 1), kThreads);
+          TR(10);
+          const double2 li = ld2(M + tile_off(j, j) + fragC), di = ld2(dinv + 8 * j + 2 * fq);
+          // own tile rows i >= j+2, i = warp-1 (mod kHelpers)
+          int i0 = j + 2;
+          i0 += (warp - 1 - i0 % kHelpers + kHelpers) % kHelpers;
+          // --- (B) L_ij = C_ij inv(L_jj)' inv(D_j)
+#pragma unroll 1
+          for (int i = i0; i < NB; i += kHelpers) {
+            double* cp = M + tile_off(i, j) + fragC;
+            const double2 c = ld2(cp);
+            double2 wa = make_double2(0.0, 0.0), wb = make_double2(0.0, 0.0);
+            dmma(wa.x, wa.y, c.x, li.x);
+            dmma(wb.x, wb.y, c.y, li.y);
+            st2(cp, make_double2((wa.x + wb.x) * di.x, (wa.y + wb.y) * di.y));
+          }
+          __syncwarp();
+          TR(14);
+          // --- (A) column j+1, terms k <= j; plus the diagonal tile j+2
+#pragma unroll 1
+          for (int i = i0; i < NB; i += kHelpers) {
+            update_tile(M, dneg, i, j + 1, j + 1, fragC, fq);
+            if (i == j + 2) update_tile(M, dneg, i, i, j + 1, fragC, fq);
+          }
+          TR(11);
+          bar_arrive(3 + (j & 1), kThreads);
+        }
       }
+      __syncthreads();
+      FCCQP_PROF(3);
+      TR(15);
       // ---------------- explicit inverses of the 32x32 diagonal blocks of L, in place ----------------
       // level 1: 16x16 = [[X1,0],[-X2 L21 X1, X2]] from the 8x8 inverses left by the factorization
+#pragma unroll 1
       for (int a = warp; 2 * a + 1 < NB; a += kWarps) {
         const double* x1 = M + tile_off(2 * a, 2 * a) + fragT;
         double* l21 = M + tile_off(2 * a + 1, 2 * a) + fragC;
@@ -649,6 +658,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
       // level 2: 32x32 = [[A,0],[-B L A, B]] with 16x16 A, B; one warp per (block, tile column).
       // Both columns of a block read tiles the other one overwrites: all products first, one
       // barrier, then the stores (the two columns of a block always share a round).
+#pragma unroll 1
       for (int base = 0; base < 2 * NB32; base += kWarps) {
         const int w = base + warp;
         const int q4 = (w >> 1) * 4, col = w & 1;
@@ -706,6 +716,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
       double sol = 0.0;   // pass 0: accumulated solution component of row t
       double acc0 = rhs0; // pass 0: right-hand side of the next solve
 
+#pragma unroll 1
       for (int iter = 0; iter < iters; ++iter) {
         // ---- K3 right-hand side
         double acc = 0.0;
@@ -720,98 +731,55 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
           acc = v_b;
         }
         TR(30);
-        // ---- forward: L y = rhs, 32 rows per step (warp J applies inv(L_JJ), later warps subtract)
+        // ---- forward: L y = rhs, 32 rows per step (warp J applies inv(L_JJ), later warps subtract).
+        // Tiles of a tile row are contiguous; tiles beyond the diagonal are clamped and masked.
         double val = 0.0;
+        const double* lrow = M + tile_off(tbe, 0) + tr * 8;
+#pragma unroll 1
         for (int J = 0; J < NB32; ++J) {
           const int Jb0 = J * 4;
           if (warp == J) {
             tbuf[t] = acc;
             __syncwarp();
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int jb = Jb0 + u;
-              if (jb <= tb && is_row) {
-                const double* xr = M + tile_off(tb, jb) + tr * 8;
-                const double* tv = tbuf + jb * 8;
-                const double2 x0 = ld2(xr + 2 * (0 ^ tf)), x1 = ld2(xr + 2 * (1 ^ tf));
-                const double2 x2 = ld2(xr + 2 * (2 ^ tf)), x3 = ld2(xr + 2 * (3 ^ tf));
-                const double2 v0 = ld2(tv), v1 = ld2(tv + 2), v2 = ld2(tv + 4), v3 = ld2(tv + 6);
-                s0 += x0.x * v0.x; s1 += x0.y * v0.y; s2 += x1.x * v1.x; s3 += x1.y * v1.y;
-                s0 += x2.x * v2.x; s1 += x2.y * v2.y; s2 += x3.x * v3.x; s3 += x3.y * v3.y;
-              }
-            }
-            val = (s0 + s1) + (s2 + s3);
+            double s = 0.0;
+#pragma unroll 1
+            for (int jb = Jb0; jb <= tbe; ++jb) s += row_dot8(lrow + 64 * jb, tf, tbuf + jb * 8);
+            val = is_row ? s : 0.0;
             ybuf[t] = val;
           }
           TR(31);
           __syncthreads();
           TR(32);
           if (warp > J && is_row) {
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const double* lr = M + tile_off(tb, Jb0 + jj) + tr * 8;
-              const double* yv = ybuf + (Jb0 + jj) * 8;
-              const double2 l0 = ld2(lr + 2 * (0 ^ tf)), l1 = ld2(lr + 2 * (1 ^ tf));
-              const double2 l2 = ld2(lr + 2 * (2 ^ tf)), l3 = ld2(lr + 2 * (3 ^ tf));
-              const double2 y0 = ld2(yv), y1 = ld2(yv + 2), y2 = ld2(yv + 4), y3 = ld2(yv + 6);
-              s0 += l0.x * y0.x; s1 += l0.y * y0.y; s2 += l1.x * y1.x; s3 += l1.y * y1.y;
-              s0 += l2.x * y2.x; s1 += l2.y * y2.y; s2 += l3.x * y3.x; s3 += l3.y * y3.y;
-            }
-            acc -= (s0 + s1) + (s2 + s3);
+            double s = 0.0;
+#pragma unroll 2
+            for (int jb = Jb0; jb < Jb0 + 4; ++jb) s += row_dot8(lrow + 64 * jb, tf, ybuf + jb * 8);
+            acc -= s;
           }
         }
         // ---- D^{-1}
         acc = is_row ? val * dinv[t] : 0.0;
         // ---- backward: L' x = y (column-per-thread reads; odd tile columns take row pairs swapped)
+#pragma unroll 1
         for (int J = NB32 - 1; J >= 0; --J) {
           const int Jb0 = J * 4, Jb1 = min(Jb0 + 4, NB);
           if (warp == J) {
             tbuf[t] = acc;
             __syncwarp();
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int ib = tb + u;
-              if (ib < Jb1 && is_row) {
-                const double* xc = M + tile_off(ib, tb) + colo;
-                const double* tv = tbuf + ib * 8;
-#pragma unroll
-                for (int r = 0; r < 8; r += 4) {
-                  const int sw0 = ((colc ^ (r >> 1)) & 3) << 1, sw1 = ((colc ^ ((r + 2) >> 1)) & 3) << 1;
-                  s0 += xc[r * 8 + flip8 + sw0] * tv[r + flip];
-                  s1 += xc[(r + 1) * 8 - flip8 + sw0] * tv[r + 1 - flip];
-                  s2 += xc[(r + 2) * 8 + flip8 + sw1] * tv[r + 2 + flip];
-                  s3 += xc[(r + 3) * 8 - flip8 + sw1] * tv[r + 3 - flip];
-                }
-              }
-            }
-            val = (s0 + s1) + (s2 + s3);
+            double s = 0.0;
+#pragma unroll 1
+            for (int ib = tbe; ib < Jb1; ++ib) s += col_dot8(M + tile_off(ib, tbe) + colo, colc, flip, tbuf + ib * 8);
+            val = is_row ? s : 0.0;
             ybuf[t] = val;
           }
           TR(33);
           __syncthreads();
           TR(34);
           if (warp < J) {
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int ib = Jb0 + u;
-              if (ib < Jb1) {
-                const double* lc = M + tile_off(ib, tb) + colo;
-                const double* yv = ybuf + ib * 8;
-#pragma unroll
-                for (int r = 0; r < 8; r += 4) {
-                  const int sw0 = ((colc ^ (r >> 1)) & 3) << 1, sw1 = ((colc ^ ((r + 2) >> 1)) & 3) << 1;
-                  s0 += lc[r * 8 + flip8 + sw0] * yv[r + flip];
-                  s1 += lc[(r + 1) * 8 - flip8 + sw0] * yv[r + 1 - flip];
-                  s2 += lc[(r + 2) * 8 + flip8 + sw1] * yv[r + 2 + flip];
-                  s3 += lc[(r + 3) * 8 - flip8 + sw1] * yv[r + 3 - flip];
-                }
-              }
-            }
-            acc -= (s0 + s1) + (s2 + s3);
+            double s = 0.0;
+#pragma unroll 2
+            for (int ib = Jb0; ib < Jb1; ++ib) s += col_dot8(M + tile_off(ib, tb) + colo, colc, flip, ybuf + ib * 8);
+            acc -= s;
           }
         }
         FCCQP_PROF(7);
@@ -834,17 +802,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
                 const long long gs = part == 0 ? q_slow : p.a_rs;
                 const double* sv = part == 0 ? sbuf : sbuf + n8;
                 const int cnt = part == 0 ? n : m;
-                int j = 0;
 #pragma unroll 1
-                for (; j + 16 <= cnt; j += 16, sv += 16) {
+                for (int j = 0; j < cnt; j += 16, sv += 16) {
                   double v[16];
 #pragma unroll
-                  for (int u = 0; u < 16; ++u) { v[u] = *gp; gp += gs; }
+                  for (int u = 0; u < 16; ++u) { v[u] = j + u < cnt ? *gp : 0.0; gp += gs; }
 #pragma unroll
-                  for (int u = 0; u < 16; ++u) sacc[u & 3] += v[u] * sv[u];
+                  for (int u = 0; u < 16; ++u) sacc[u & 3] += v[u] * (j + u < cnt ? sv[u] : 0.0);
                 }
-#pragma unroll 1
-                for (; j < cnt; ++j, gp += gs, ++sv) sacc[0] += *gp * *sv;
               }
               r = -v_b - ((sacc[0] + sacc[1]) + (sacc[2] + sacc[3]));
             }
@@ -910,7 +875,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
         const int conv = __syncthreads_and((rc < p.eps_fcone) && (rx < p.eps_bound));
         FCCQP_PROF(9);
         TR(51);
+#ifdef FCCQP_DEV
         if (p.prof && tid == 0) s_prof[15] += 1;
+#endif
         if (conv || iter + 1 == iters) {
           block_reduce2<false>(rx, rc, red, parity);
           res_x = rx; res_c = rc;
@@ -919,8 +886,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
       }
     }
 
-    TR(60);
     // ---------------- K6: epilogue ----------------
+    TR(60);
     __syncthreads();
     double bv = 0.0, fv = 0.0;
     int bad = 0;
@@ -955,11 +922,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
     }
     FCCQP_PROF(10);
     TR(61);
-    trbuf = nullptr;
+#ifdef FCCQP_DEV
     if (p.prof && tid == 0) s_prof[14] += 1;
+    trbuf = nullptr;
+#endif
   }
+#ifdef FCCQP_DEV
   if (p.prof && tid == 0)
     for (int i = 0; i < 16; ++i) atomicAdd(p.prof + i, s_prof[i]);
+#endif
 #undef FCCQP_PROF
 #undef TR
 }
