@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfccqp_b200.so")
+# FCCQP_LIB: developer override (e.g. an instrumented -DFCCQP_DEV build of the same sources)
+LIB_PATH = os.environ.get("FCCQP_LIB") or os.path.join(_HERE, "libfccqp_b200.so")
 
 ABI_VERSION = 1
 MEM_HOST, MEM_DEVICE = 0, 1
@@ -70,6 +71,7 @@ EXPORTS = [
     "fccqp_set_max_iter", "fccqp_set_warm_start", "fccqp_contact_vars_start", "fccqp_solve",
     "fccqp_get_solution", "fccqp_get_warm_state", "fccqp_set_warm_state", "fccqp_batch_solve",
     "fccqp_release_workspaces", "fccqp_kernel_launch_count", "fccqp_last_launch_info",
+    "fccqp_alloc_pinned", "fccqp_free_pinned",
 ]
 
 _lib = None
@@ -103,6 +105,8 @@ def lib() -> C.CDLL:
     L.fccqp_batch_solve.argtypes = [C.POINTER(BatchDesc)]
     L.fccqp_kernel_launch_count.restype = C.c_int64
     L.fccqp_last_launch_info.argtypes = [_ip, _ip, _ip, _ip]
+    L.fccqp_alloc_pinned.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+    L.fccqp_free_pinned.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -116,3 +120,20 @@ def last_launch_info() -> dict:
     g, b, s, c = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
     lib().fccqp_last_launch_info(C.byref(g), C.byref(b), C.byref(s), C.byref(c))
     return dict(grid=g.value, block=b.value, smem_bytes=s.value, ctas_per_sm=c.value)
+
+
+def pinned_empty(shape, dtype):
+    """numpy array in page-locked host memory (``fccqp_alloc_pinned``): the batched host path
+    moves such arrays by asynchronous DMA.  Freed when the array (and its views) are collected."""
+    import weakref
+
+    import numpy as np
+    dtype = np.dtype(dtype)
+    count = int(np.prod(shape, dtype=np.int64))
+    nbytes = max(count * dtype.itemsize, 1)
+    ptr = C.c_void_p()
+    check(lib().fccqp_alloc_pinned(nbytes, C.byref(ptr)))
+    buf = (C.c_char * nbytes).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+    weakref.finalize(buf, lib().fccqp_free_pinned, ptr.value)
+    return arr

@@ -69,6 +69,8 @@ class FCCQPBatch:
         self.warm_start = False
         self.time_kernel = True
         self._state = None     # (x, mu_x, mu_c) arrays / tensors
+        self._host_out = None  # page-locked output buffers of the numpy path
+        self.zero_copy_outputs = False  # numpy path: GetSolution() returns views of those buffers
         self._sol: Optional[BatchSolution] = None
         nat.lib()              # fail loudly if the CUDA library is not built
 
@@ -156,13 +158,24 @@ class FCCQPBatch:
         n, m, nc = self.n, self.m, self.nc
         warm = self.warm_start
         st = self._state
-        if warm and st is not None and not _is_torch(st[0]) and st[0].shape == (B, n):
-            x, mux, muc = (np.ascontiguousarray(a, dtype=np.float64).copy() for a in st)
+        # Outputs live in solver-owned page-locked buffers (true asynchronous D2H), reused from
+        # call to call; x doubles as the carried warm-start state, exactly like the reference's x_.
+        ob = self._host_out
+        if ob is None or ob["x"].shape != (B, n):
+            pe = nat.pinned_empty
+            ob = self._host_out = dict(x=pe((B, n), np.float64), mux=pe((B, n), np.float64), muc=pe((B, nc), np.float64),
+                                       n_iter=pe((B,), np.int32), status=pe((B,), np.int32), res=pe((4, B), np.float64))
+            fresh = True
         else:
+            fresh = False
+        x, mux, muc = ob["x"], ob["mux"], ob["muc"]
+        if warm and st is not None and not _is_torch(st[0]) and st[0].shape == (B, n):
+            if st[0] is not x:
+                x[...], mux[...], muc[...] = st
+        elif warm or fresh:
             # a never-solved reference object warm-starts from the zero state (src/fcc_qp.cpp:48-52)
-            x, mux, muc = np.zeros((B, n)), np.zeros((B, n)), np.zeros((B, max(nc, 1)))[:, :nc].copy()
-        n_iter = np.zeros(B, np.int32); status = np.zeros(B, np.int32)
-        res = np.zeros((4, B))
+            x[...] = 0.0; mux[...] = 0.0; muc[...] = 0.0
+        n_iter, status, res = ob["n_iter"], ob["status"], ob["res"]
         d = self._desc(B, nat.MEM_HOST)
         d.warm_start = int(warm)
         p = lambda a: a.ctypes.data
@@ -182,8 +195,11 @@ class FCCQPBatch:
         nat.check(nat.lib().fccqp_batch_solve(C.byref(d)))
         wall = time.perf_counter() - t0
         self._state = (x, mux, muc)
-        self._sol = BatchSolution(BatchDetails(n_iter, res[0], res[1], res[2], res[3], status, wall, secs.value),
-                                  x.copy())
+        # zero_copy_outputs: z and the details are views of the solver-owned page-locked buffers,
+        # valid until the next Solve(); default: independent copies, like FCCQP::GetSolution.
+        cp = (lambda a: a) if self.zero_copy_outputs else (lambda a: a.copy())
+        self._sol = BatchSolution(BatchDetails(cp(n_iter), cp(res[0]), cp(res[1]), cp(res[2]), cp(res[3]), cp(status),
+                                               wall, secs.value), cp(x))
 
     def _solve_torch(self, Q, b, A_eq, b_eq, mu, lb, ub):
         import time

@@ -61,6 +61,10 @@ struct DeviceCtx {
   size_t stage_bytes = 0;
   cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // pinned bounce buffer for outputs whose destination is pageable host memory (grow only)
+  char* hstage = nullptr;
+  size_t hstage_bytes = 0;
+  cudaEvent_t chunk_ev[16] = {};
   std::mutex mu;       // guards counters / gscratch / occupancy cache
   std::mutex host_mu;  // serialises FCCQP_MEM_HOST calls (they share the staging buffer)
   std::map<std::pair<const void*, size_t>, int> occupancy;  // (kernel, smem) -> CTAs/SM
@@ -89,6 +93,7 @@ int get_ctx(int device, DeviceCtx** out) {
   for (auto& s : ctx->streams) CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&ctx->ev0));
   CUDA_TRY(cudaEventCreate(&ctx->ev1));
+  for (auto& e : ctx->chunk_ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   *out = ctx.get();
   g_ctx[device] = std::move(ctx);
   return FCCQP_OK;
@@ -120,7 +125,7 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream) {
   int rc = pick_kernel(ctx, p.n, p.m, p.nc, &fn, &threads, &smem);
   if (rc) return rc;
   p.lay = fccqp::Layout(p.n, p.m, p.nc);
-  static const int refine = getenv("FCCQP_PRESOLVE_REFINE") ? atoi(getenv("FCCQP_PRESOLVE_REFINE")) : 1;
+  static const int refine = getenv("FCCQP_PRESOLVE_REFINE") ? atoi(getenv("FCCQP_PRESOLVE_REFINE")) : 0;
   p.refine = refine < 0 ? 0 : refine;
   int ctas_per_sm = 0;
   {
@@ -573,6 +578,31 @@ int fccqp_batch_solve(const fccqp_batch_desc* desc) {
     return rc;
   CUDA_TRY(cudaStreamSynchronize(s0));
 
+  // where do the outputs go?  (page-locked destination: direct DMA; pageable: pinned bounce buffer)
+  void* outs[9] = {d.x, d.mu_x, d.mu_lambda_c, d.n_iter, d.status, d.res_bounds, d.res_fcone, d.bounds_viol, d.fcone_viol};
+  const size_t out_elem[9] = {n * sizeof(double), n * sizeof(double), nc * sizeof(double), sizeof(int), sizeof(int),
+                              sizeof(double), sizeof(double), sizeof(double), sizeof(double)};
+  bool out_pinned[9];
+  size_t out_off[9], hneed = 0;
+  for (int i = 0; i < 9; ++i) {
+    out_pinned[i] = true;
+    out_off[i] = 0;
+    if (!outs[i] || !out_elem[i]) continue;
+    cudaPointerAttributes at{};
+    const bool pinned = cudaPointerGetAttributes(&at, outs[i]) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    out_pinned[i] = pinned;
+    if (!pinned) { out_off[i] = hneed; hneed += align_up((size_t)B * out_elem[i], 256); }
+  }
+  if (hneed > ctx->hstage_bytes) {
+    if (ctx->hstage) CUDA_TRY(cudaFreeHost(ctx->hstage));
+    ctx->hstage = nullptr; ctx->hstage_bytes = 0;
+    CUDA_TRY(cudaMallocHost(&ctx->hstage, hneed));
+    ctx->hstage_bytes = hneed;
+  }
+  struct Pending { int chunk; void* dst; const void* src; size_t bytes; };
+  std::vector<Pending> pending;
+
   int nchunks = (B + 4095) / 4096;
   if (nchunks > 16) nchunks = 16;
   if (nchunks < 1) nchunks = 1;
@@ -610,24 +640,55 @@ int fccqp_batch_solve(const fccqp_batch_desc* desc) {
     p.res_b = res + lo; p.res_f = res + (size_t)B + lo; p.bviol = res + 2 * (size_t)B + lo; p.fviol = res + 3 * (size_t)B + lo;
     rc = launch_solve(*ctx, p, st);
     if (rc) return rc;
-    auto d2h = [&](void* dst, const void* src, size_t bytes) -> int {
-      if (dst && bytes) CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+    // D2H: straight into the caller's buffer when it is page-locked (a true asynchronous DMA);
+    // otherwise into the pinned bounce buffer, copied out below once the chunk's event has fired
+    // (a cudaMemcpyAsync into pageable memory would block the host and serialise the chunks).
+    auto d2h = [&](int slot, void* dst, const void* src, size_t elem_bytes) -> int {
+      if (!dst || !cnt) return FCCQP_OK;
+      const size_t bytes = cnt * elem_bytes;
+      void* to = (char*)dst + (size_t)lo * elem_bytes;
+      if (!out_pinned[slot]) {
+        to = ctx->hstage + out_off[slot] + (size_t)lo * elem_bytes;
+        pending.push_back({c, (char*)dst + (size_t)lo * elem_bytes, to, bytes});
+      }
+      CUDA_TRY(cudaMemcpyAsync(to, src, bytes, cudaMemcpyDeviceToHost, st));
       return FCCQP_OK;
     };
-    if ((rc = d2h(d.x + lo * n, p.x, cnt * n * sizeof(double))) ||
-        (rc = d2h(d.mu_x ? d.mu_x + lo * n : nullptr, p.mu_x, cnt * n * sizeof(double))) ||
-        (rc = d2h(d.mu_lambda_c ? d.mu_lambda_c + lo * nc : nullptr, p.mu_c, cnt * nc * sizeof(double))) ||
-        (rc = d2h(d.n_iter ? d.n_iter + lo : nullptr, p.n_iter, cnt * sizeof(int))) ||
-        (rc = d2h(d.status ? d.status + lo : nullptr, p.status, cnt * sizeof(int))) ||
-        (rc = d2h(d.res_bounds ? d.res_bounds + lo : nullptr, p.res_b, cnt * sizeof(double))) ||
-        (rc = d2h(d.res_fcone ? d.res_fcone + lo : nullptr, p.res_f, cnt * sizeof(double))) ||
-        (rc = d2h(d.bounds_viol ? d.bounds_viol + lo : nullptr, p.bviol, cnt * sizeof(double))) ||
-        (rc = d2h(d.fcone_viol ? d.fcone_viol + lo : nullptr, p.fviol, cnt * sizeof(double))))
+    if ((rc = d2h(0, d.x, p.x, n * sizeof(double))) ||
+        (rc = d2h(1, d.mu_x, p.mu_x, n * sizeof(double))) ||
+        (rc = d2h(2, d.mu_lambda_c, p.mu_c, nc * sizeof(double))) ||
+        (rc = d2h(3, d.n_iter, p.n_iter, sizeof(int))) ||
+        (rc = d2h(4, d.status, p.status, sizeof(int))) ||
+        (rc = d2h(5, d.res_bounds, p.res_b, sizeof(double))) ||
+        (rc = d2h(6, d.res_fcone, p.res_f, sizeof(double))) ||
+        (rc = d2h(7, d.bounds_viol, p.bviol, sizeof(double))) ||
+        (rc = d2h(8, d.fcone_viol, p.fviol, sizeof(double))))
       return rc;
+    CUDA_TRY(cudaEventRecord(ctx->chunk_ev[c], st));
+  }
+  // drain the bounce buffer chunk by chunk while later chunks are still in flight
+  {
+    int waited = -1;
+    for (const Pending& pe : pending) {
+      if (pe.chunk != waited) { CUDA_TRY(cudaEventSynchronize(ctx->chunk_ev[pe.chunk])); waited = pe.chunk; }
+      memcpy(pe.dst, pe.src, pe.bytes);
+    }
   }
   for (auto& s : ctx->streams) CUDA_TRY(cudaStreamSynchronize(s));
   if (d.device_seconds)
     *d.device_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return FCCQP_OK;
+}
+
+int fccqp_alloc_pinned(size_t bytes, void** out) {
+  if (!out) return fail(FCCQP_E_INVALID, "out is null");
+  *out = nullptr;
+  if (bytes == 0) return FCCQP_OK;
+  CUDA_TRY(cudaMallocHost(out, bytes));
+  return FCCQP_OK;
+}
+int fccqp_free_pinned(void* ptr) {
+  if (ptr) CUDA_TRY(cudaFreeHost(ptr));
   return FCCQP_OK;
 }
 
@@ -639,6 +700,7 @@ int fccqp_release_workspaces(void) {
     std::lock_guard<std::mutex> lk3(c.mu);
     cudaSetDevice(c.device);
     if (c.stage) { cudaFree(c.stage); c.stage = nullptr; c.stage_bytes = 0; }
+    if (c.hstage) { cudaFreeHost(c.hstage); c.hstage = nullptr; c.hstage_bytes = 0; }
   }
   return FCCQP_OK;
 }

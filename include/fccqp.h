@@ -163,6 +163,11 @@ typedef struct fccqp_batch_desc {
 } fccqp_batch_desc;
 
 int fccqp_batch_solve(const fccqp_batch_desc* desc);
+/* Page-locked host memory for FCCQP_MEM_HOST callers: inputs and outputs that live in
+ * memory from here (or from cudaHostAlloc / torch pin_memory) move by asynchronous DMA that
+ * overlaps the solve; pageable outputs go through an internal pinned bounce buffer. */
+int fccqp_alloc_pinned(size_t bytes, void** out);
+int fccqp_free_pinned(void* ptr);
 /* Frees the cached per-device staging buffers used by FCCQP_MEM_HOST calls. */
 int fccqp_release_workspaces(void);
 
