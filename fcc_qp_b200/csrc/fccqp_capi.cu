@@ -125,8 +125,9 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream) {
   int rc = pick_kernel(ctx, p.n, p.m, p.nc, &fn, &threads, &smem);
   if (rc) return rc;
   p.lay = fccqp::Layout(p.n, p.m, p.nc);
-  static const int refine = getenv("FCCQP_PRESOLVE_REFINE") ? atoi(getenv("FCCQP_PRESOLVE_REFINE")) : 0;
-  p.refine = refine < 0 ? 0 : refine;
+  // developer switch: FCCQP_FIRST_UPDATE_IDENTITY=0 solves the (mathematically redundant) first x-update of cold QPs
+  static const int fui = getenv("FCCQP_FIRST_UPDATE_IDENTITY") ? atoi(getenv("FCCQP_FIRST_UPDATE_IDENTITY")) : 1;
+  p.first_update_identity = fui != 0;
   int ctas_per_sm = 0;
   {
     std::lock_guard<std::mutex> lk(ctx.mu);
@@ -183,7 +184,7 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream) {
     CUDA_TRY(cudaStreamSynchronize(stream));
     CUDA_TRY(cudaFree(d_prof));
     static const char* names[14] = {"stage-in", "assemble", "sigma/rhs0", "ldlt-acc+diag", "ldlt-trsm",
-                                    "-", "xinv32", "kkt-solve", "presolve-refine", "admm-project",
+                                    "-", "xinv32", "kkt-solve", "presolve-tail", "admm-project",
                                     "epilogue", "B-work-w0w2", "B-work-w1w3", "B-barrier-w0"};
     double tot = 0;
     for (int i = 0; i < 14; ++i) tot += (double)h[i];

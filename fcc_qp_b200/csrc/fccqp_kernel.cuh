@@ -92,7 +92,7 @@ struct Layout {
 struct SolveParams {
   int B, n, m, nc, lcs;
   int max_iter, warm;
-  int refine;              // iterative-refinement steps of the cold pre-solve (default 1)
+  int first_update_identity;  // cold solves: take x-update 0 as the identity it is (see kernel), default 1
   double rho, eps_fcone, eps_bound;
   const double* Q;   long long q_bs, q_rs, q_cs;
   const double* b;   long long b_bs;
@@ -460,9 +460,34 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
     FCCQP_PROF(0);
     TR(2);
 
-    // pass 0: cold pre-solve on [[Q + sigma A'A, A'],[A,0]];  pass 1: ADMM on [[Q + rho I, A'],[A,0]]
+    // pass 0: cold pre-solve on [[Q + sigma A'A, A'],[A,0]];  pass 1: ADMM on [[Q + rho I, A'],[A,0]].
+    // A KKT matrix is assembled and factored lazily, right before the first solve that needs it.
+    // Cold solves never need pass 1's for their first x-update: ADMM starts from x_bar = x0 and
+    // zero duals (fcc_qp.cpp:74-75,136-139), so x-update 0 minimises
+    //   1/2 x'Qx + b'x + rho/2 |x - x0|^2   s.t.  A x = b_eq,
+    // whose minimiser is x0 itself (x0 minimises the first two terms on the same set).  The kernel
+    // takes that x-update as the identity: a QP whose pre-solve point already passes the exit test
+    // (98 % of the walking log) finishes without the second factorization; the others factor and
+    // carry on from iteration 1.  first_update_identity = 0 runs the solve instead.
     for (int pass = presolve ? 0 : 1; pass < 2; ++pass) {
       if (pass == 1 && eqc) break;
+      if (pass == 1) {
+        // ADMM initial slack (fcc_qp.cpp:74-75): x_bar = x, lambda_c_bar = x[lambda_c segment]
+        v_xbar = v_x;
+        if (t < nc) lcbar[t] = xs[lcs + t];
+        __syncthreads();
+        n_iter = p.max_iter;
+      }
+      const int iters = pass == 0 ? 1 : p.max_iter;
+      bool factored = false;
+      double rhs0 = 0.0;   // pass-0 right-hand side of row t
+
+#pragma unroll 1
+      for (int iter = 0; iter < iters; ++iter) {
+      double val = v_x;    // solution component of row t (t < N8)
+      if (!(pass == 1 && iter == 0 && presolve && p.first_update_identity)) {
+      if (!factored) {
+      factored = true;
       const long long t_f0 = clock64();
 
       // ---------------- assemble the lower tiles of the padded KKT matrix ----------------
@@ -521,7 +546,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
       FCCQP_PROF(1);
       TR(4);
 
-      double rhs0 = 0.0;   // pass-0 right-hand side of row t
       if (pass == 1) {
         if (is_x) M[mat_off(t, t)] += p.rho;
       } else {
@@ -705,23 +729,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
       FCCQP_PROF(6);
       TR(20);
 
-      if (pass == 1) {
-        // ADMM initial slack (fcc_qp.cpp:74-75): x_bar = x, lambda_c_bar = x[lambda_c segment]
-        v_xbar = v_x;
-        if (t < nc) lcbar[t] = xs[lcs + t];
-        __syncthreads();
-        n_iter = p.max_iter;
-      }
-      const int iters = pass == 0 ? 1 + p.refine : p.max_iter;
-      double sol = 0.0;   // pass 0: accumulated solution component of row t
-      double acc0 = rhs0; // pass 0: right-hand side of the next solve
+      }  // lazy factorization
 
-#pragma unroll 1
-      for (int iter = 0; iter < iters; ++iter) {
         // ---- K3 right-hand side
         double acc = 0.0;
         if (pass == 0) {
-          acc = acc0;
+          acc = rhs0;
         } else if (is_x) {
           // -(b + q_rho), q_rho = -rho (xbar - mu_x) with the cone segment overwritten (fcc_qp.cpp:81-83)
           const double w = in_cone ? (lcbar[t - lcs] - muc[t - lcs]) : (v_xbar - v_mux);
@@ -733,7 +746,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
         TR(30);
         // ---- forward: L y = rhs, 32 rows per step (warp J applies inv(L_JJ), later warps subtract).
         // Tiles of a tile row are contiguous; tiles beyond the diagonal are clamped and masked.
-        double val = 0.0;
         const double* lrow = M + tile_off(tbe, 0) + tr * 8;
 #pragma unroll 1
         for (int J = 0; J < NB32; ++J) {
@@ -786,62 +798,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
         TR(35);
         // val = solution component of row t (t < N8)
 
+        }  // x-update solve
+
         if (pass == 0) {
-          sol += val;
-          if (iter + 1 < iters) {
-            // ---- iterative refinement against the ORIGINAL system: r = [-b; b_eq] - [[Q,A'],[A,0]] s
-            if (is_row) sbuf[t] = sol;
-            __syncthreads();
-            double r = 0.0;
-            if (is_x) {
-              // 16 independent L2 loads in flight per thread; Q symmetric: column t == row t
-              double sacc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 1
-              for (int part = 0; part < 2; ++part) {
-                const double* gp = part == 0 ? Qg + t * q_fast : Ag + t * p.a_cs;
-                const long long gs = part == 0 ? q_slow : p.a_rs;
-                const double* sv = part == 0 ? sbuf : sbuf + n8;
-                const int cnt = part == 0 ? n : m;
-#pragma unroll 1
-                for (int j = 0; j < cnt; j += 16, sv += 16) {
-                  double v[16];
-#pragma unroll
-                  for (int u = 0; u < 16; ++u) { v[u] = j + u < cnt ? *gp : 0.0; gp += gs; }
-#pragma unroll
-                  for (int u = 0; u < 16; ++u) sacc[u & 3] += v[u] * (j + u < cnt ? sv[u] : 0.0);
-                }
-              }
-              r = -v_b - ((sacc[0] + sacc[1]) + (sacc[2] + sacc[3]));
-            }
-            // rows of A: four rows per warp at a time, lanes over columns
-#pragma unroll 1
-            for (int k = 4 * warp; k < m; k += 4 * kWarps) {
-              double sr[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 1
-              for (int jc = lane; jc < n; jc += 32) {
-                const double xj = sbuf[jc];
-                const double* gp = Ag + (long long)k * p.a_rs + jc * p.a_cs;
-#pragma unroll
-                for (int u = 0; u < 4; ++u, gp += p.a_rs)
-                  if (k + u < m) sr[u] += *gp * xj;
-              }
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) sr[u] += __shfl_xor_sync(0xffffffffu, sr[u], o);
-              }
-              if (lane < 4 && k + lane < m)
-                ybuf[n8 + k + lane] = lane == 0 ? sr[0] : lane == 1 ? sr[1] : lane == 2 ? sr[2] : sr[3];
-            }
-            __syncthreads();
-            if (is_c) r = v_b - ybuf[t];
-            acc0 = r;
-          } else {
-            v_x = sol;
-            if (t < n8) xs[t] = is_x ? sol : 0.0;
-            if (p.dbg_x0 && is_x) p.dbg_x0[(size_t)qp * n + t] = sol;
-            __syncthreads();
-          }
+          v_x = val;
+          if (t < n8) xs[t] = is_x ? val : 0.0;
+          if (p.dbg_x0 && is_x) p.dbg_x0[(size_t)qp * n + t] = val;
+          __syncthreads();
           FCCQP_PROF(8);
           TR(41);
           continue;
