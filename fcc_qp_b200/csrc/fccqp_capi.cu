@@ -101,6 +101,7 @@ int get_ctx(int device, DeviceCtx** out) {
 
 using KernelFn = void (*)(const fccqp::SolveParams);
 
+
 // Chooses the template instance (threads >= n + m; CTAs/SM hint from the packed-matrix footprint).
 int pick_kernel(const DeviceCtx& ctx, int n, int m, int nc, KernelFn* fn, int* threads, size_t* smem) {
   const int N = n + m;

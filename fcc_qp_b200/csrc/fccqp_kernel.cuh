@@ -297,24 +297,139 @@ __device__ __forceinline__ void bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
-// In-place left-looking update of ONE tile:  C(i,c) -= sum_{k<kend} L_ik D_k L_ck'.
+#ifdef FCCQP_DEV
+#define FCCQP_PROF(slot)                                                   \
+  do {                                                                     \
+    if (p.prof && tid == 0) {                                              \
+      const long long t_now = clock64();                                   \
+      s_prof[slot] += (unsigned long long)(t_now - t_prof);                \
+      t_prof = t_now;                                                      \
+    }                                                                      \
+  } while (0)
+#define TR(tag)                                                                                      \
+  do {                                                                                               \
+    if (trbuf && lane == 0 && trn < 4096) trbuf[trn++] = ((unsigned long long)clock64() << 8) | (unsigned)(tag); \
+  } while (0)
+#define FCCQP_TRACE_PARAMS , unsigned long long* trbuf, int& trn
+#define FCCQP_TRACE_ARGS , trbuf, trn
+#else
+#define FCCQP_PROF(slot) do { } while (0)
+#define TR(tag) do { } while (0)
+#define FCCQP_TRACE_PARAMS
+#define FCCQP_TRACE_ARGS
+#endif
+
+// One helper step of the left-looking LDL^T for up to T tile rows i_t = i0 + t*stride owned by
+// this warp (all >= j+2):
+//   (B) L_{i,j}    = C_{i,j} inv(L_jj)' inv(D_j)                      (stored; kept in registers)
+//   (A) C_{i,j+1} -= sum_{k<=j} L_{i,k} D_k L_{j+1,k}'                 (in place)
+//       C_{i,i}   -= sum_{k<=j} L_{i,k} D_k L_{i,k}'   for i == j+2   (the next-but-one diagonal tile)
+// All T tiles advance together: the scaled B operand D_k L_{j+1,k}' is loaded once per k and
+// shared, every tile has two independent DMMA chains, so a warp has 2T (+2) DMMAs in flight
+// instead of two, and the k = j term comes straight from the registers of step (B).
 // Tiles of one tile row are contiguous (64 doubles apart), so the operand pointers just advance.
-// The two DMMAs of a tile product go to different accumulators (no DMMA waits for the one
-// before it) and the loop is unrolled twice so that loads run ahead of the DMMAs.
-__device__ __forceinline__ void update_tile(double* __restrict__ M, const double* __restrict__ dneg, int i, int c,
-                                            int kend, int fragC, int fq) {
-  double* cp = M + tile_off(i, c) + fragC;
-  const double* ap = M + tile_off(i, 0) + fragC;
-  const double* bp = M + tile_off(c, 0) + fragC;
-  const double* dp = dneg + 2 * fq;
-  double2 ca = ld2(cp), cb = make_double2(0.0, 0.0);
-#pragma unroll 2
-  for (int k = 0; k < kend; ++k, ap += 64, bp += 64, dp += 8) {
-    const double2 a = ld2(ap), b = ld2(bp), d = ld2(dp);
-    dmma(ca.x, ca.y, a.x, b.x * d.x);
-    dmma(cb.x, cb.y, a.y, b.y * d.y);
+template <int T>
+__device__ __forceinline__ void helper_step(double* __restrict__ M, const double* __restrict__ dneg, int i0,
+                                            int stride, int j, const double2 li, const double2 di,
+                                            int fragC, int fq FCCQP_TRACE_PARAMS) {
+#ifdef FCCQP_DEV
+  const int lane = threadIdx.x & 31;
+#endif
+  int rowoff[T];
+  double2 l[T], ca[T], cb[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const int i = i0 + t * stride;
+    rowoff[t] = tile_off(i, 0) + fragC;
+    l[t] = ld2(M + rowoff[t] + 64 * j);
+    ca[t] = ld2(M + rowoff[t] + 64 * (j + 1));
+    cb[t] = make_double2(0.0, 0.0);
   }
-  st2(cp, make_double2(ca.x + cb.x, ca.y + cb.y));
+  const bool diag = i0 == j + 2;  // warp-uniform
+  double* const dgp = M + tile_off(i0, i0) + fragC;
+  double2 da = make_double2(0.0, 0.0), db = make_double2(0.0, 0.0);
+  if (diag) da = ld2(dgp);
+  // (B)
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    double2 wa = make_double2(0.0, 0.0), wb = make_double2(0.0, 0.0);
+    dmma(wa.x, wa.y, l[t].x, li.x);
+    dmma(wb.x, wb.y, l[t].y, li.y);
+    l[t] = make_double2((wa.x + wb.x) * di.x, (wa.y + wb.y) * di.y);
+    st2(M + rowoff[t] + 64 * j, l[t]);
+  }
+  TR(16);
+  // (A), terms k < j from shared memory
+  const double* bp = M + tile_off(j + 1, 0) + fragC;
+  const double* dp = dneg + 2 * fq;
+  int ko = 0;
+#pragma unroll 1
+  for (int k = 0; k < j; ++k, ko += 64, bp += 64, dp += 8) {
+    const double2 b = ld2(bp), d = ld2(dp);
+    const double bx = b.x * d.x, by = b.y * d.y;
+    double2 a[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) a[t] = ld2(M + rowoff[t] + ko);
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      dmma(ca[t].x, ca[t].y, a[t].x, bx);
+      dmma(cb[t].x, cb[t].y, a[t].y, by);
+    }
+    if (diag) {
+      dmma(da.x, da.y, a[0].x, a[0].x * d.x);
+      dmma(db.x, db.y, a[0].y, a[0].y * d.y);
+    }
+  }
+  TR(17);
+  // term k = j from registers
+  {
+    const double2 b = ld2(bp), d = ld2(dp);
+    const double bx = b.x * d.x, by = b.y * d.y;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      dmma(ca[t].x, ca[t].y, l[t].x, bx);
+      dmma(cb[t].x, cb[t].y, l[t].y, by);
+    }
+    if (diag) {
+      dmma(da.x, da.y, l[0].x, l[0].x * d.x);
+      dmma(db.x, db.y, l[0].y, l[0].y * d.y);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < T; ++t) st2(M + rowoff[t] + 64 * (j + 1), make_double2(ca[t].x + cb[t].x, ca[t].y + cb[t].y));
+  if (diag) st2(dgp, make_double2(da.x + db.x, da.y + db.y));
+}
+
+// sigma A'A for T consecutive tiles (I, J0..J0+T-1) of the variable block (cold pre-solve):
+//   C_IJ += sigma sum_kb A_{kb,I}' A_{kb,J},  kb over the constraint tile rows.
+// The A_{kb,I} operand is shared by the T tiles, each tile has two independent DMMA chains.
+template <int T>
+__device__ __forceinline__ void ata_chunk(double* __restrict__ M, int NBx, int NB, int I, int J0, double sigma,
+                                          int fragC, int fragT) {
+  double2 sa[T], sb[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) { sa[t] = make_double2(0.0, 0.0); sb[t] = make_double2(0.0, 0.0); }
+  const double* ai = M + tile_off(NBx, I) + fragT;
+  const double* aj = M + tile_off(NBx, J0) + fragT;
+#pragma unroll 1
+  for (int kb = NBx; kb < NB; ++kb) {
+    const double a0 = ai[0], a1 = ai[8];
+    double b0[T], b1[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) { b0[t] = aj[64 * t]; b1[t] = aj[64 * t + 8]; }
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      dmma(sa[t].x, sa[t].y, a0, b0[t]);
+      dmma(sb[t].x, sb[t].y, a1, b1[t]);
+    }
+    ai += 64 * (kb + 1); aj += 64 * (kb + 1);
+  }
+  double* cp = M + tile_off(I, J0) + fragC;
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const double2 c = ld2(cp + 64 * t);
+    st2(cp + 64 * t, make_double2(c.x + sigma * (sa[t].x + sb[t].x), c.y + sigma * (sa[t].y + sb[t].y)));
+  }
 }
 
 // Row-per-thread dot product over one tile: sum_c T[row][c] * v[c]   (trow = tile + row*8, tf = row/2)
@@ -340,23 +455,140 @@ __device__ __forceinline__ double col_dot8(const double* __restrict__ tcol, int 
   return s0 + s1;
 }
 
-#ifdef FCCQP_DEV
-#define FCCQP_PROF(slot)                                                   \
-  do {                                                                     \
-    if (p.prof && tid == 0) {                                              \
-      const long long t_now = clock64();                                   \
-      s_prof[slot] += (unsigned long long)(t_now - t_prof);                \
-      t_prof = t_now;                                                      \
-    }                                                                      \
-  } while (0)
-#define TR(tag)                                                                                      \
-  do {                                                                                               \
-    if (trbuf && lane == 0 && trn < 4096) trbuf[trn++] = ((unsigned long long)clock64() << 8) | (unsigned)(tag); \
-  } while (0)
-#else
-#define FCCQP_PROF(slot) do { } while (0)
-#define TR(tag) do { } while (0)
-#endif
+
+// ---------------------------------------------------------------------------
+// Factorization of the assembled tile matrix, in place: unpivoted blocked left-looking LDL^T,
+// then the explicit 32x32 diagonal-block inverses the triangular solves use.  Deliberately NOT
+// inlined: the call parks the caller's per-row state (bounds, duals, right-hand sides) in
+// local memory, so the DMMA loops get the whole register file and ptxas can keep the operand
+// loads of several tiles in flight instead of recycling two registers.
+// ---------------------------------------------------------------------------
+template <int kThreads>
+__device__ __noinline__ void factor_tiles(double* __restrict__ M, double* __restrict__ dinv, double* __restrict__ dneg,
+                                          const int NB, const int NB32 FCCQP_TRACE_PARAMS) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kThreads / 32;
+  constexpr int kHelpers = kWarps - 1;
+  const int fr = lane >> 2, fq = lane & 3;
+  const int fragC = (fr << 3) + (((fq ^ (fr >> 1)) & 3) << 1);
+  const int fragT = ((2 * fq) << 3) + ((((fr >> 1) ^ fq) & 3) << 1) + (fr & 1);
+  // ---------------- unpivoted blocked left-looking LDL^T on 8x8 tiles ----------------
+  // Warp 0 runs the critical path: factor the diagonal tile (one thread, registers), turn the
+  // tile below it into L, bring the next diagonal tile up to date, signal.  The helper warps
+  // stay one tile column behind: they finish the L tiles of column j, then accumulate column
+  // j+1 (and the part of the diagonal tile j+2 that does not need column j+1) in place.
+  if (warp == 0) {
+#pragma unroll 1
+    for (int j = 0; j < NB; ++j) {
+      double* dt = M + tile_off(j, j);
+      if (lane == 0) factor_diag_tile(dt, dinv + 8 * j, dneg + 8 * j);
+      __syncwarp();
+      TR(12);
+      if (j > 0) bar_sync(3 + ((j - 1) & 1), kThreads);   // helpers finished step j-1
+      if (j + 1 < NB) {
+        const double2 li = ld2(dt + fragC), di = ld2(dinv + 8 * j + 2 * fq);
+        double* lp = M + tile_off(j + 1, j) + fragC;
+        const double2 c = ld2(lp);
+        double2 t1 = ld2(lp + 64);                       // tile (j+1, j+1)
+        double2 wa = make_double2(0.0, 0.0), wb = make_double2(0.0, 0.0);
+        dmma(wa.x, wa.y, c.x, li.x);
+        dmma(wb.x, wb.y, c.y, li.y);
+        const double wx = wa.x + wb.x, wy = wa.y + wb.y;   // L D
+        const double2 l = make_double2(wx * di.x, wy * di.y);
+        st2(lp, l);
+        double2 t2 = make_double2(0.0, 0.0);
+        dmma(t1.x, t1.y, -wx, l.x);
+        dmma(t2.x, t2.y, -wy, l.y);
+        st2(lp + 64, make_double2(t1.x + t2.x, t1.y + t2.y));
+      }
+      bar_arrive(1 + (j & 1), kThreads);                  // column j: inv(L_jj), D_j, L_{j+1,j} ready
+      TR(13);
+    }
+    bar_sync(3 + ((NB - 1) & 1), kThreads);
+  } else {
+#pragma unroll 1
+    for (int j = 0; j < NB; ++j) {
+      bar_sync(1 + (j & 1), kThreads);
+      TR(10);
+      const double2 li = ld2(M + tile_off(j, j) + fragC), di = ld2(dinv + 8 * j + 2 * fq);
+      // own tile rows i >= j+2, i = warp-1 (mod kHelpers), four at a time
+      int i0 = j + 2;
+      i0 += (warp - 1 - i0 % kHelpers + kHelpers) % kHelpers;
+#pragma unroll 1
+      for (; i0 < NB; i0 += 4 * kHelpers) {
+        const int cnt = (NB - i0 + kHelpers - 1) / kHelpers;
+        if (cnt >= 4) helper_step<4>(M, dneg, i0, kHelpers, j, li, di, fragC, fq FCCQP_TRACE_ARGS);
+        else if (cnt == 3) helper_step<3>(M, dneg, i0, kHelpers, j, li, di, fragC, fq FCCQP_TRACE_ARGS);
+        else if (cnt == 2) helper_step<2>(M, dneg, i0, kHelpers, j, li, di, fragC, fq FCCQP_TRACE_ARGS);
+        else helper_step<1>(M, dneg, i0, kHelpers, j, li, di, fragC, fq FCCQP_TRACE_ARGS);
+      }
+      TR(11);
+      bar_arrive(3 + (j & 1), kThreads);
+    }
+  }
+  __syncthreads();
+  TR(15);
+  // ---------------- explicit inverses of the 32x32 diagonal blocks of L, in place ----------------
+  // level 1: 16x16 = [[X1,0],[-X2 L21 X1, X2]] from the 8x8 inverses left by the factorization
+#pragma unroll 1
+  for (int a = warp; 2 * a + 1 < NB; a += kWarps) {
+    const double* x1 = M + tile_off(2 * a, 2 * a) + fragT;
+    double* l21 = M + tile_off(2 * a + 1, 2 * a) + fragC;
+    const double2 x2 = ld2(M + tile_off(2 * a + 1, 2 * a + 1) + fragC);
+    double2 tt = make_double2(0.0, 0.0);                 // fragC((L21 X1)') = fragT(L21 X1)
+    mma8(tt, make_double2(x1[0], x1[8]), ld2(l21));      // X1' L21'
+    double2 r = make_double2(0.0, 0.0);
+    mma8(r, x2, tt);                                     // X2 (L21 X1)
+    st2(l21, make_double2(-r.x, -r.y));
+  }
+  __syncthreads();
+  // level 2: 32x32 = [[A,0],[-B L A, B]] with 16x16 A, B; one warp per (block, tile column).
+  // Both columns of a block read tiles the other one overwrites: all products first, one
+  // barrier, then the stores (the two columns of a block always share a round).
+#pragma unroll 1
+  for (int base = 0; base < 2 * NB32; base += kWarps) {
+    const int w = base + warp;
+    const int q4 = (w >> 1) * 4, col = w & 1;
+    const bool act = w < 2 * NB32 && q4 + 2 < NB;
+    const bool two = q4 + 3 < NB;  // second tile row of the lower-left 16x16 exists
+    double2 r0 = make_double2(0.0, 0.0), r1 = make_double2(0.0, 0.0);
+    if (act) {
+      // T(:,col) = L A(:,col), kept transposed in registers
+      double2 t0 = make_double2(0.0, 0.0), t1 = make_double2(0.0, 0.0);
+      const double2 l01 = ld2(M + tile_off(q4 + 2, q4 + 1) + fragC);
+      double2 l11 = make_double2(0.0, 0.0);
+      if (two) l11 = ld2(M + tile_off(q4 + 3, q4 + 1) + fragC);
+      if (col == 0) {
+        const double2 l00 = ld2(M + tile_off(q4 + 2, q4) + fragC);
+        const double* a00 = M + tile_off(q4, q4) + fragT;
+        const double* a10 = M + tile_off(q4 + 1, q4) + fragT;
+        const double2 f00 = make_double2(a00[0], a00[8]), f10 = make_double2(a10[0], a10[8]);
+        mma8(t0, f00, l00); mma8(t0, f10, l01);          // T00' = A00' L00' + A10' L01'
+        if (two) {
+          const double2 l10 = ld2(M + tile_off(q4 + 3, q4) + fragC);
+          mma8(t1, f00, l10); mma8(t1, f10, l11);        // T10'
+        }
+      } else {
+        const double* a11 = M + tile_off(q4 + 1, q4 + 1) + fragT;
+        const double2 f11 = make_double2(a11[0], a11[8]);
+        mma8(t0, f11, l01);                              // T01' = A11' L01'
+        if (two) mma8(t1, f11, l11);                     // T11'
+      }
+      // R(:,col) = B T(:,col)
+      mma8(r0, ld2(M + tile_off(q4 + 2, q4 + 2) + fragC), t0);
+      if (two) {
+        mma8(r1, ld2(M + tile_off(q4 + 3, q4 + 2) + fragC), t0);
+        mma8(r1, ld2(M + tile_off(q4 + 3, q4 + 3) + fragC), t1);
+      }
+    }
+    __syncthreads();
+    if (act) {
+      st2(M + tile_off(q4 + 2, q4 + col) + fragC, make_double2(-r0.x, -r0.y));
+      if (two) st2(M + tile_off(q4 + 3, q4 + col) + fragC, make_double2(-r1.x, -r1.y));
+    }
+  }
+  __syncthreads();
+}
 
 // ---------------------------------------------------------------------------
 // The fused solve kernel.  kThreads >= padded KKT size N8 (one thread per KKT row in the
@@ -390,8 +622,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
   long long t_prof = 0;
   if (p.prof && tid == 0) { for (int i = 0; i < 16; ++i) s_prof[i] = 0; t_prof = clock64(); }
   // developer tracing: lane 0 of every warp of CTA 0 logs (clock, tag) for the first QP it solves
-  unsigned long long* trbuf = (p.trace && blockIdx.x == 0) ? p.trace + warp * 4096 : nullptr;
-  int trn = 0;
+  // (the THIRD QP of CTA 0 when it gets that many: instruction caches warm, neighbours out of step)
+  unsigned long long* const trbase = (p.trace && blockIdx.x == 0) ? p.trace + warp * 4096 : nullptr;
+  unsigned long long* trbuf = nullptr;
+  int trn = 0, trcount = 0;
+  const int trsel = (p.B >= 3 * (int)gridDim.x) ? 2 : 0;
 #endif
 
   int parity = 0;
@@ -420,6 +655,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
     __syncthreads();
     const int qp = *s_work;
     if (qp >= p.B) break;
+#ifdef FCCQP_DEV
+    trbuf = (trcount++ == trsel) ? trbase : nullptr;
+#endif
     TR(1);
 
     const double* Qg = p.Q + (size_t)qp * p.q_bs;
@@ -551,16 +789,17 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
       } else {
         // sigma = trace(Q) / ||A||_F^2 balances the two terms of Q + sigma A'A
         double trq = is_x ? M[mat_off(t, t)] : 0.0, fro = 0.0;
+        if (t >= n8 && t < N8) tbuf[t] = is_c ? v_b : 0.0;
         if (is_c) {
-          tbuf[t] = v_b;
 #pragma unroll 1
           for (int jb = 0; jb < NBx; ++jb) {
             const double* row = M + tile_off(tb, jb) + tr * 8;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { const double2 v = ld2(row + 2 * c); fro += v.x * v.x + v.y * v.y; }
+            for (int c = 0; c < 4; ++c) { const double2 v = ld2(row + 2 * (c ^ tf)); fro += v.x * v.x + v.y * v.y; }
           }
         }
         block_reduce2<true>(trq, fro, red, parity);
+        TR(6);
         const double sigma = (trq > 0.0 && fro > 0.0 && isfinite(trq / fro)) ? trq / fro : 1.0;
         // rhs_x = -b + sigma A' b_eq (needs A before the factorization overwrites it)
         if (is_x) {
@@ -571,26 +810,22 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
         } else if (is_c) {
           rhs0 = v_b;
         }
-        // H += sigma A'A on the tiles of the variable block, in place, one tile per warp at a time
+        TR(7);
+        // H += sigma A'A on the tiles of the variable block, in place: chunks of up to four tiles of
+        // one tile row (shared A operand, 2 x cnt independent DMMA chains), round-robin over the warps
         {
-          int I = 0, J = warp;
-          while (J > I) { J -= I + 1; ++I; }
+          int ch = 0;
 #pragma unroll 1
-          for (; I < NBx;) {
-            double2 sa = make_double2(0.0, 0.0), sb = make_double2(0.0, 0.0);
-            const double* ai = M + tile_off(NBx, I) + fragT;
-            const double* aj = M + tile_off(NBx, J) + fragT;
-#pragma unroll 2
-            for (int kb = NBx; kb < NB; ++kb) {
-              dmma(sa.x, sa.y, ai[0], aj[0]);
-              dmma(sb.x, sb.y, ai[8], aj[8]);
-              ai += 64 * (kb + 1); aj += 64 * (kb + 1);
+          for (int I = 0; I < NBx; ++I) {
+#pragma unroll 1
+            for (int J0 = 0; J0 <= I; J0 += 4, ++ch) {
+              if (ch % kWarps != warp) continue;
+              const int cnt = I + 1 - J0;
+              if (cnt >= 4) ata_chunk<4>(M, NBx, NB, I, J0, sigma, fragC, fragT);
+              else if (cnt == 3) ata_chunk<3>(M, NBx, NB, I, J0, sigma, fragC, fragT);
+              else if (cnt == 2) ata_chunk<2>(M, NBx, NB, I, J0, sigma, fragC, fragT);
+              else ata_chunk<1>(M, NBx, NB, I, J0, sigma, fragC, fragT);
             }
-            double* cp = M + tile_off(I, J) + fragC;
-            const double2 c = ld2(cp);
-            st2(cp, make_double2(c.x + sigma * (sa.x + sb.x), c.y + sigma * (sa.y + sb.y)));
-            J += kWarps;
-            while (J > I) { J -= I + 1; ++I; }
           }
         }
       }
@@ -598,133 +833,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
       FCCQP_PROF(2);
       TR(5);
 
-      // ---------------- unpivoted blocked left-looking LDL^T on 8x8 tiles ----------------
-      // Warp 0 runs the critical path: factor the diagonal tile (one thread, registers), turn the
-      // tile below it into L, bring the next diagonal tile up to date, signal.  The helper warps
-      // stay one tile column behind: they finish the L tiles of column j, then accumulate column
-      // j+1 (and the part of the diagonal tile j+2 that does not need column j+1) in place.
-      if (warp == 0) {
-#pragma unroll 1
-        for (int j = 0; j < NB; ++j) {
-          double* dt = M + tile_off(j, j);
-          if (lane == 0) factor_diag_tile(dt, dinv + 8 * j, dneg + 8 * j);
-          __syncwarp();
-          TR(12);
-          if (j > 0) bar_sync(3 + ((j - 1) & 1), kThreads);   // helpers finished step j-1
-          if (j + 1 < NB) {
-            const double2 li = ld2(dt + fragC), di = ld2(dinv + 8 * j + 2 * fq);
-            double* lp = M + tile_off(j + 1, j) + fragC;
-            const double2 c = ld2(lp);
-            double2 t1 = ld2(lp + 64);                       // tile (j+1, j+1)
-            double2 wa = make_double2(0.0, 0.0), wb = make_double2(0.0, 0.0);
-            dmma(wa.x, wa.y, c.x, li.x);
-            dmma(wb.x, wb.y, c.y, li.y);
-            const double wx = wa.x + wb.x, wy = wa.y + wb.y;   // L D
-            const double2 l = make_double2(wx * di.x, wy * di.y);
-            st2(lp, l);
-            double2 t2 = make_double2(0.0, 0.0);
-            dmma(t1.x, t1.y, -wx, l.x);
-            dmma(t2.x, t2.y, -wy, l.y);
-            st2(lp + 64, make_double2(t1.x + t2.x, t1.y + t2.y));
-          }
-          bar_arrive(1 + (j & 1), kThreads);                  // column j: inv(L_jj), D_j, L_{j+1,j} ready
-          TR(13);
-        }
-        bar_sync(3 + ((NB - 1) & 1), kThreads);
-      } else {
-#pragma unroll 1
-        for (int j = 0; j < NB; ++j) {
-          bar_sync(1 + (j & 1), kThreads);
-          TR(10);
-          const double2 li = ld2(M + tile_off(j, j) + fragC), di = ld2(dinv + 8 * j + 2 * fq);
-          // own tile rows i >= j+2, i = warp-1 (mod kHelpers)
-          int i0 = j + 2;
-          i0 += (warp - 1 - i0 % kHelpers + kHelpers) % kHelpers;
-          // --- (B) L_ij = C_ij inv(L_jj)' inv(D_j)
-#pragma unroll 1
-          for (int i = i0; i < NB; i += kHelpers) {
-            double* cp = M + tile_off(i, j) + fragC;
-            const double2 c = ld2(cp);
-            double2 wa = make_double2(0.0, 0.0), wb = make_double2(0.0, 0.0);
-            dmma(wa.x, wa.y, c.x, li.x);
-            dmma(wb.x, wb.y, c.y, li.y);
-            st2(cp, make_double2((wa.x + wb.x) * di.x, (wa.y + wb.y) * di.y));
-          }
-          __syncwarp();
-          TR(14);
-          // --- (A) column j+1, terms k <= j; plus the diagonal tile j+2
-#pragma unroll 1
-          for (int i = i0; i < NB; i += kHelpers) {
-            update_tile(M, dneg, i, j + 1, j + 1, fragC, fq);
-            if (i == j + 2) update_tile(M, dneg, i, i, j + 1, fragC, fq);
-          }
-          TR(11);
-          bar_arrive(3 + (j & 1), kThreads);
-        }
-      }
-      __syncthreads();
+      factor_tiles<kThreads>(M, dinv, dneg, NB, NB32 FCCQP_TRACE_ARGS);
       FCCQP_PROF(3);
-      TR(15);
-      // ---------------- explicit inverses of the 32x32 diagonal blocks of L, in place ----------------
-      // level 1: 16x16 = [[X1,0],[-X2 L21 X1, X2]] from the 8x8 inverses left by the factorization
-#pragma unroll 1
-      for (int a = warp; 2 * a + 1 < NB; a += kWarps) {
-        const double* x1 = M + tile_off(2 * a, 2 * a) + fragT;
-        double* l21 = M + tile_off(2 * a + 1, 2 * a) + fragC;
-        const double2 x2 = ld2(M + tile_off(2 * a + 1, 2 * a + 1) + fragC);
-        double2 tt = make_double2(0.0, 0.0);                 // fragC((L21 X1)') = fragT(L21 X1)
-        mma8(tt, make_double2(x1[0], x1[8]), ld2(l21));      // X1' L21'
-        double2 r = make_double2(0.0, 0.0);
-        mma8(r, x2, tt);                                     // X2 (L21 X1)
-        st2(l21, make_double2(-r.x, -r.y));
-      }
-      __syncthreads();
-      // level 2: 32x32 = [[A,0],[-B L A, B]] with 16x16 A, B; one warp per (block, tile column).
-      // Both columns of a block read tiles the other one overwrites: all products first, one
-      // barrier, then the stores (the two columns of a block always share a round).
-#pragma unroll 1
-      for (int base = 0; base < 2 * NB32; base += kWarps) {
-        const int w = base + warp;
-        const int q4 = (w >> 1) * 4, col = w & 1;
-        const bool act = w < 2 * NB32 && q4 + 2 < NB;
-        const bool two = q4 + 3 < NB;  // second tile row of the lower-left 16x16 exists
-        double2 r0 = make_double2(0.0, 0.0), r1 = make_double2(0.0, 0.0);
-        if (act) {
-          // T(:,col) = L A(:,col), kept transposed in registers
-          double2 t0 = make_double2(0.0, 0.0), t1 = make_double2(0.0, 0.0);
-          const double2 l01 = ld2(M + tile_off(q4 + 2, q4 + 1) + fragC);
-          double2 l11 = make_double2(0.0, 0.0);
-          if (two) l11 = ld2(M + tile_off(q4 + 3, q4 + 1) + fragC);
-          if (col == 0) {
-            const double2 l00 = ld2(M + tile_off(q4 + 2, q4) + fragC);
-            const double* a00 = M + tile_off(q4, q4) + fragT;
-            const double* a10 = M + tile_off(q4 + 1, q4) + fragT;
-            const double2 f00 = make_double2(a00[0], a00[8]), f10 = make_double2(a10[0], a10[8]);
-            mma8(t0, f00, l00); mma8(t0, f10, l01);          // T00' = A00' L00' + A10' L01'
-            if (two) {
-              const double2 l10 = ld2(M + tile_off(q4 + 3, q4) + fragC);
-              mma8(t1, f00, l10); mma8(t1, f10, l11);        // T10'
-            }
-          } else {
-            const double* a11 = M + tile_off(q4 + 1, q4 + 1) + fragT;
-            const double2 f11 = make_double2(a11[0], a11[8]);
-            mma8(t0, f11, l01);                              // T01' = A11' L01'
-            if (two) mma8(t1, f11, l11);                     // T11'
-          }
-          // R(:,col) = B T(:,col)
-          mma8(r0, ld2(M + tile_off(q4 + 2, q4 + 2) + fragC), t0);
-          if (two) {
-            mma8(r1, ld2(M + tile_off(q4 + 3, q4 + 2) + fragC), t0);
-            mma8(r1, ld2(M + tile_off(q4 + 3, q4 + 3) + fragC), t1);
-          }
-        }
-        __syncthreads();
-        if (act) {
-          st2(M + tile_off(q4 + 2, q4 + col) + fragC, make_double2(-r0.x, -r0.y));
-          if (two) st2(M + tile_off(q4 + 3, q4 + col) + fragC, make_double2(-r1.x, -r1.y));
-        }
-      }
-      __syncthreads();
       fact_cycles += (unsigned long long)(clock64() - t_f0);
       FCCQP_PROF(6);
       TR(20);
@@ -887,7 +997,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
     TR(61);
 #ifdef FCCQP_DEV
     if (p.prof && tid == 0) s_prof[14] += 1;
-    trbuf = nullptr;
 #endif
   }
 #ifdef FCCQP_DEV
@@ -896,6 +1005,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
 #endif
 #undef FCCQP_PROF
 #undef TR
+#undef FCCQP_TRACE_PARAMS
+#undef FCCQP_TRACE_ARGS
 }
 
 }  // namespace fccqp

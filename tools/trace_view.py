@@ -5,7 +5,7 @@ ev = collections.defaultdict(list)
 for l in open(sys.argv[1]):
     w, c, t = l.split(); ev[int(w)].append((int(c), int(t)))
 t0 = min(e[0][0] for e in ev.values())
-names = {1:"qp", 2:"staged", 3:"asm-issued", 4:"asm-done", 5:"sigma", 10:"col", 11:"acc-done", 12:"P1-done", 13:"bar1", 14:"B-done", 15:"bar2",
+names = {1:"qp", 2:"staged", 3:"asm-issued", 4:"asm-done", 5:"sigma", 6:"sig-red", 7:"rhs0", 10:"col", 11:"acc-done", 12:"P1-done", 13:"bar1", 14:"B-done", 15:"bar2", 16:"hB", 17:"hK",
          20:"xinv", 30:"solve", 31:"f-arr", 32:"f-bar", 33:"b-arr", 34:"b-bar", 35:"solved", 41:"refined", 51:"projected", 60:"epi", 61:"end"}
 lo = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 60
