@@ -591,6 +591,76 @@ __device__ __noinline__ void factor_tiles(double* __restrict__ M, double* __rest
 }
 
 // ---------------------------------------------------------------------------
+// x = K^{-1} rhs with the factors left by factor_tiles: L y = rhs, D^{-1}, L' x = y, 32 rows per
+// step (one warp applies the explicit inverse of a 32x32 diagonal block, the others subtract the
+// 32-column slab).  Thread t owns row t: `acc` is its right-hand-side entry, the return value its
+// solution entry (rows >= N8 return 0).  Not inlined, for the same reason as factor_tiles.
+// ---------------------------------------------------------------------------
+__device__ __noinline__ double kkt_solve(const double* __restrict__ M, const double* __restrict__ dinv,
+                                         double* __restrict__ tbuf, double* __restrict__ ybuf, double acc,
+                                         const int NB, const int NB32, const int N8 FCCQP_TRACE_PARAMS) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const bool is_row = t < N8;
+  const int tb = t >> 3, tr = t & 7, tf = tr >> 1;
+  const int colo = tr & 1, colc = tr >> 1;
+  const int flip = tb & 1;
+  const int tbe = tb < NB ? tb : NB - 1;
+  double val = 0.0;
+  (void)lane;
+  // ---- forward: L y = rhs, 32 rows per step (warp J applies inv(L_JJ), later warps subtract).
+  // Tiles of a tile row are contiguous; tiles beyond the diagonal are clamped and masked.
+  const double* lrow = M + tile_off(tbe, 0) + tr * 8;
+#pragma unroll 1
+  for (int J = 0; J < NB32; ++J) {
+    const int Jb0 = J * 4;
+    if (warp == J) {
+      tbuf[t] = acc;
+      __syncwarp();
+      double s = 0.0;
+#pragma unroll 1
+      for (int jb = Jb0; jb <= tbe; ++jb) s += row_dot8(lrow + 64 * jb, tf, tbuf + jb * 8);
+      val = is_row ? s : 0.0;
+      ybuf[t] = val;
+    }
+    TR(31);
+    __syncthreads();
+    TR(32);
+    if (warp > J && is_row) {
+      double s = 0.0;
+#pragma unroll 2
+      for (int jb = Jb0; jb < Jb0 + 4; ++jb) s += row_dot8(lrow + 64 * jb, tf, ybuf + jb * 8);
+      acc -= s;
+    }
+  }
+  // ---- D^{-1}
+  acc = is_row ? val * dinv[t] : 0.0;
+  // ---- backward: L' x = y (column-per-thread reads; odd tile columns take row pairs swapped)
+#pragma unroll 1
+  for (int J = NB32 - 1; J >= 0; --J) {
+    const int Jb0 = J * 4, Jb1 = min(Jb0 + 4, NB);
+    if (warp == J) {
+      tbuf[t] = acc;
+      __syncwarp();
+      double s = 0.0;
+#pragma unroll 1
+      for (int ib = tbe; ib < Jb1; ++ib) s += col_dot8(M + tile_off(ib, tbe) + colo, colc, flip, tbuf + ib * 8);
+      val = is_row ? s : 0.0;
+      ybuf[t] = val;
+    }
+    TR(33);
+    __syncthreads();
+    TR(34);
+    if (warp < J) {
+      double s = 0.0;
+#pragma unroll 2
+      for (int ib = Jb0; ib < Jb1; ++ib) s += col_dot8(M + tile_off(ib, tb) + colo, colc, flip, ybuf + ib * 8);
+      acc -= s;
+    }
+  }
+  return val;
+}
+
+// ---------------------------------------------------------------------------
 // The fused solve kernel.  kThreads >= padded KKT size N8 (one thread per KKT row in the
 // triangular solves and all vector work).  Warp 0 is the factorization's critical-path warp,
 // warps 1.. are its helpers.
@@ -854,56 +924,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
           acc = v_b;
         }
         TR(30);
-        // ---- forward: L y = rhs, 32 rows per step (warp J applies inv(L_JJ), later warps subtract).
-        // Tiles of a tile row are contiguous; tiles beyond the diagonal are clamped and masked.
-        const double* lrow = M + tile_off(tbe, 0) + tr * 8;
-#pragma unroll 1
-        for (int J = 0; J < NB32; ++J) {
-          const int Jb0 = J * 4;
-          if (warp == J) {
-            tbuf[t] = acc;
-            __syncwarp();
-            double s = 0.0;
-#pragma unroll 1
-            for (int jb = Jb0; jb <= tbe; ++jb) s += row_dot8(lrow + 64 * jb, tf, tbuf + jb * 8);
-            val = is_row ? s : 0.0;
-            ybuf[t] = val;
-          }
-          TR(31);
-          __syncthreads();
-          TR(32);
-          if (warp > J && is_row) {
-            double s = 0.0;
-#pragma unroll 2
-            for (int jb = Jb0; jb < Jb0 + 4; ++jb) s += row_dot8(lrow + 64 * jb, tf, ybuf + jb * 8);
-            acc -= s;
-          }
-        }
-        // ---- D^{-1}
-        acc = is_row ? val * dinv[t] : 0.0;
-        // ---- backward: L' x = y (column-per-thread reads; odd tile columns take row pairs swapped)
-#pragma unroll 1
-        for (int J = NB32 - 1; J >= 0; --J) {
-          const int Jb0 = J * 4, Jb1 = min(Jb0 + 4, NB);
-          if (warp == J) {
-            tbuf[t] = acc;
-            __syncwarp();
-            double s = 0.0;
-#pragma unroll 1
-            for (int ib = tbe; ib < Jb1; ++ib) s += col_dot8(M + tile_off(ib, tbe) + colo, colc, flip, tbuf + ib * 8);
-            val = is_row ? s : 0.0;
-            ybuf[t] = val;
-          }
-          TR(33);
-          __syncthreads();
-          TR(34);
-          if (warp < J) {
-            double s = 0.0;
-#pragma unroll 2
-            for (int ib = Jb0; ib < Jb1; ++ib) s += col_dot8(M + tile_off(ib, tb) + colo, colc, flip, ybuf + ib * 8);
-            acc -= s;
-          }
-        }
+        val = kkt_solve(M, dinv, tbuf, ybuf, acc, NB, NB32, N8 FCCQP_TRACE_ARGS);
         FCCQP_PROF(7);
         TR(35);
         // val = solution component of row t (t < N8)
