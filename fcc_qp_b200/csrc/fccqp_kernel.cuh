@@ -124,15 +124,22 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // Block-wide reduction of two values (max or sum).  `red` holds 2 x 2 x 32 doubles;
-// `parity` alternates between the two halves so one barrier per call suffices.
+// `parity` alternates between the two halves so one barrier per call suffices.  Inlined and
+// by value: the two shuffle chains interleave and nothing goes through local memory.
 template <bool kSum>
-__device__ __noinline__ void block_reduce2(double& a, double& b, double* red, int& parity) {
+__device__ __forceinline__ void block_reduce2(double& a, double& b, double* red, int& parity) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  if (kSum) { a = warp_sum(a); b = warp_sum(b); } else { a = warp_max(a); b = warp_max(b); }
+  double va = a, vb = b;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double oa = __shfl_xor_sync(0xffffffffu, va, o), ob = __shfl_xor_sync(0xffffffffu, vb, o);
+    if (kSum) { va += oa; vb += ob; } else { va = fmax(va, oa); vb = fmax(vb, ob); }
+  }
   double* r = red + parity * 64;
-  if (lane == 0) { r[warp] = a; r[32 + warp] = b; }
+  if (lane == 0) { r[warp] = va; r[32 + warp] = vb; }
   __syncthreads();
   double ra = r[0], rb = r[32];
+#pragma unroll 1
   for (int w = 1; w < nw; ++w) {
     if (kSum) { ra += r[w]; rb += r[32 + w]; } else { ra = fmax(ra, r[w]); rb = fmax(rb, r[32 + w]); }
   }
@@ -861,12 +868,16 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
         double trq = is_x ? M[mat_off(t, t)] : 0.0, fro = 0.0;
         if (t >= n8 && t < N8) tbuf[t] = is_c ? v_b : 0.0;
         if (is_c) {
-#pragma unroll 1
+          double f1 = 0.0, f2 = 0.0, f3 = 0.0;
+#pragma unroll 2
           for (int jb = 0; jb < NBx; ++jb) {
             const double* row = M + tile_off(tb, jb) + tr * 8;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) { const double2 v = ld2(row + 2 * (c ^ tf)); fro += v.x * v.x + v.y * v.y; }
+            const double2 v0 = ld2(row + 2 * (0 ^ tf)), v1 = ld2(row + 2 * (1 ^ tf));
+            const double2 v2 = ld2(row + 2 * (2 ^ tf)), v3 = ld2(row + 2 * (3 ^ tf));
+            fro = fma(v0.x, v0.x, fma(v0.y, v0.y, fro)); f1 = fma(v1.x, v1.x, fma(v1.y, v1.y, f1));
+            f2 = fma(v2.x, v2.x, fma(v2.y, v2.y, f2)); f3 = fma(v3.x, v3.x, fma(v3.y, v3.y, f3));
           }
+          fro = (fro + f1) + (f2 + f3);
         }
         block_reduce2<true>(trq, fro, red, parity);
         TR(6);
