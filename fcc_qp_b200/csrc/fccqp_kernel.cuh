@@ -338,7 +338,7 @@ __device__ __forceinline__ void bar_sync(int id, int count) {
 template <int T>
 __device__ __forceinline__ void helper_step(double* __restrict__ M, const double* __restrict__ dneg, int i0,
                                             int stride, int j, const double2 li, const double2 di,
-                                            int fragC, int fq FCCQP_TRACE_PARAMS) {
+                                            int fragC, int fq, const int cnt FCCQP_TRACE_PARAMS) {
 #ifdef FCCQP_DEV
   const int lane = threadIdx.x & 31;
 #endif
@@ -346,7 +346,7 @@ __device__ __forceinline__ void helper_step(double* __restrict__ M, const double
   double2 l[T], ca[T], cb[T];
 #pragma unroll
   for (int t = 0; t < T; ++t) {
-    const int i = i0 + t * stride;
+    const int i = t < cnt ? i0 + t * stride : i0;     // unused slots alias the first tile row (never stored)
     rowoff[t] = tile_off(i, 0) + fragC;
     l[t] = ld2(M + rowoff[t] + 64 * j);
     ca[t] = ld2(M + rowoff[t] + 64 * (j + 1));
@@ -363,7 +363,7 @@ __device__ __forceinline__ void helper_step(double* __restrict__ M, const double
     dmma(wa.x, wa.y, l[t].x, li.x);
     dmma(wb.x, wb.y, l[t].y, li.y);
     l[t] = make_double2((wa.x + wb.x) * di.x, (wa.y + wb.y) * di.y);
-    st2(M + rowoff[t] + 64 * j, l[t]);
+    if (t < cnt) st2(M + rowoff[t] + 64 * j, l[t]);
   }
   TR(16);
   // (A), terms k < j from shared memory
@@ -403,7 +403,8 @@ __device__ __forceinline__ void helper_step(double* __restrict__ M, const double
     }
   }
 #pragma unroll
-  for (int t = 0; t < T; ++t) st2(M + rowoff[t] + 64 * (j + 1), make_double2(ca[t].x + cb[t].x, ca[t].y + cb[t].y));
+  for (int t = 0; t < T; ++t)
+    if (t < cnt) st2(M + rowoff[t] + 64 * (j + 1), make_double2(ca[t].x + cb[t].x, ca[t].y + cb[t].y));
   if (diag) st2(dgp, make_double2(da.x + db.x, da.y + db.y));
 }
 
@@ -524,10 +525,8 @@ __device__ __noinline__ void factor_tiles(double* __restrict__ M, double* __rest
 #pragma unroll 1
       for (; i0 < NB; i0 += 4 * kHelpers) {
         const int cnt = (NB - i0 + kHelpers - 1) / kHelpers;
-        if (cnt >= 4) helper_step<4>(M, dneg, i0, kHelpers, j, li, di, fragC, fq FCCQP_TRACE_ARGS);
-        else if (cnt == 3) helper_step<3>(M, dneg, i0, kHelpers, j, li, di, fragC, fq FCCQP_TRACE_ARGS);
-        else if (cnt == 2) helper_step<2>(M, dneg, i0, kHelpers, j, li, di, fragC, fq FCCQP_TRACE_ARGS);
-        else helper_step<1>(M, dneg, i0, kHelpers, j, li, di, fragC, fq FCCQP_TRACE_ARGS);
+        if (cnt > 2) helper_step<4>(M, dneg, i0, kHelpers, j, li, di, fragC, fq, cnt FCCQP_TRACE_ARGS);
+        else helper_step<2>(M, dneg, i0, kHelpers, j, li, di, fragC, fq, cnt FCCQP_TRACE_ARGS);
       }
       TR(11);
       bar_arrive(3 + (j & 1), kThreads);
