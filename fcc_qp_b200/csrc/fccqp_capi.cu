@@ -129,6 +129,9 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream) {
   // developer switch: FCCQP_FIRST_UPDATE_IDENTITY=0 solves the (mathematically redundant) first x-update of cold QPs
   static const int fui = getenv("FCCQP_FIRST_UPDATE_IDENTITY") ? atoi(getenv("FCCQP_FIRST_UPDATE_IDENTITY")) : 1;
   p.first_update_identity = fui != 0;
+  // developer switch: ADMM iteration at which long-running QPs complete inv(L) (huge value = never)
+  static const int fia = getenv("FCCQP_FULL_INVERSE_AT") ? atoi(getenv("FCCQP_FULL_INVERSE_AT")) : 6;
+  p.full_inverse_at = fia < 1 ? 1 : fia;
   int ctas_per_sm = 0;
   {
     std::lock_guard<std::mutex> lk(ctx.mu);
@@ -184,7 +187,7 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream) {
     CUDA_TRY(cudaMemcpyAsync(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     CUDA_TRY(cudaFree(d_prof));
-    static const char* names[14] = {"stage-in", "assemble", "sigma/rhs0", "ldlt-acc+diag", "ldlt-trsm",
+    static const char* names[14] = {"stage-in", "assemble", "sigma/rhs0", "ldlt-acc+diag", "full-inverse",
                                     "-", "xinv32", "kkt-solve", "presolve-tail", "admm-project",
                                     "epilogue", "B-work-w0w2", "B-work-w1w3", "B-barrier-w0"};
     double tot = 0;

@@ -92,6 +92,7 @@ struct Layout {
 struct SolveParams {
   int B, n, m, nc, lcs;
   int max_iter, warm;
+  int full_inverse_at;        // ADMM iteration from which x-updates use the completed inverse of L (default 6)
   int first_update_identity;  // cold solves: take x-update 0 as the identity it is (see kernel), default 1
   double rho, eps_fcone, eps_bound;
   const double* Q;   long long q_bs, q_rs, q_cs;
@@ -667,6 +668,146 @@ __device__ __noinline__ double kkt_solve(const double* __restrict__ M, const dou
 }
 
 // ---------------------------------------------------------------------------
+// Long-running QPs (the 1-2 % that iterate towards max_iter dominate both the mean and the tail of
+// a batch): after kFullInverseAt ADMM iterations the factor is completed to W = inv(L), in place,
+// and every later x-update is two triangular matrix-vector products (kkt_solve_full) instead of
+// 2 x N/32 dependent block steps.
+//
+// complete_inverse: recursive doubling from the 32x32 diagonal-block inverses factor_tiles left.
+// For block sizes s = 4, 8, 16 tiles, neighbouring diagonal blocks A (tiles [q, q+s)) and B (tiles
+// [q+s, q+2s), clipped) whose inverses are in place absorb the block C below A / left of B:
+//     inv([[A, 0], [C, B]]) = [[inv A, 0], [-inv(B) C inv(A), inv B]].
+// Phase 0: C <- C inv(A), phase 1: C <- -inv(B) C.  A task is one tile row (phase 0) or tile
+// column (phase 1) of C in chunks of up to four tiles sharing one operand.  In-place hazards
+// (a chunk overwrites tiles that chunks to its left / above still read) are covered by the task
+// order (phase 0: left chunks first, phase 1: bottom chunks first) and by "all products,
+// barrier, all stores, barrier" within a round.
+// ---------------------------------------------------------------------------
+template <int kThreads>
+__device__ __noinline__ void complete_inverse(double* __restrict__ M, const int NB) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kWarps = kThreads / 32;
+  const int fr = lane >> 2, fq = lane & 3;
+  const int fragC = (fr << 3) + (((fq ^ (fr >> 1)) & 3) << 1);
+  const int fragT = ((2 * fq) << 3) + ((((fr >> 1) ^ fq) & 3) << 1) + (fr & 1);
+#pragma unroll 1
+  for (int s = 4; s < NB; s <<= 1) {
+    const int nchunk = (s + 3) >> 2;
+    const int npair = (NB + 2 * s - 1) / (2 * s);
+    const int ntask = npair * s;               // (pair, line): line = row of C (phase 0) / column of C (phase 1)
+#pragma unroll 1
+    for (int phase = 0; phase < 2; ++phase) {
+#pragma unroll 1
+      for (int c = 0; c < nchunk; ++c) {
+#pragma unroll 1
+        for (int base = 0; base < ntask; base += kWarps) {
+          const int task = base + warp;
+          const int pr = task / s, ln = task - pr * s;
+          const int q = pr * 2 * s;            // A = [q, q+s), B = [q+s, qe)
+          const int qe = min(q + 2 * s, NB);
+          const int nb = qe - (q + s);         // tile rows of C (<= 0: no B block)
+          bool act = task < ntask && nb > 0;
+          double2 r[4], rb[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { r[u] = make_double2(0.0, 0.0); rb[u] = make_double2(0.0, 0.0); }
+          int cnt = 0, i = 0, j = 0;
+          if (phase == 0) {
+            // row i of C, columns j..j+cnt-1 of A:  T_ij = sum_{k=j}^{q+s-1} C_ik Ainv_kj
+            act = act && ln < nb;
+            i = q + s + ln; j = q + 4 * c; cnt = min(4, q + s - j);
+            if (act && cnt > 0) {
+#pragma unroll 1
+              for (int k = j; k < q + s; ++k) {
+                const double2 a = ld2(M + tile_off(i, k) + fragC);
+                const double* bp = M + tile_off(k, j) + fragT;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (u < cnt && j + u <= k) {
+                    dmma(r[u].x, r[u].y, a.x, bp[64 * u]);
+                    dmma(rb[u].x, rb[u].y, a.y, bp[64 * u + 8]);
+                  }
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) { r[u].x += rb[u].x; r[u].y += rb[u].y; }
+            }
+          } else {
+            // column j of C, rows i..i+cnt-1 of B, bottom chunk first:  R_ij = -sum_{k=q+s}^{i} Binv_ik T_kj
+            j = q + ln;
+            const int cc = ((nb + 3) >> 2) - 1 - c;
+            act = act && cc >= 0;
+            i = q + s + 4 * cc; cnt = min(4, qe - i);
+            if (act && cnt > 0) {
+#pragma unroll 1
+              for (int k = q + s; k < i + cnt; ++k) {
+                const double* bp = M + tile_off(k, j) + fragT;
+                const double b0 = bp[0], b1 = bp[8];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (u < cnt && i + u >= k) {
+                    const double2 a = ld2(M + tile_off(i + u, k) + fragC);
+                    dmma(r[u].x, r[u].y, a.x, b0);
+                    dmma(rb[u].x, rb[u].y, a.y, b1);
+                  }
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) { r[u].x = -(r[u].x + rb[u].x); r[u].y = -(r[u].y + rb[u].y); }
+            }
+          }
+          __syncthreads();
+          if (act && cnt > 0) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (u < cnt) {
+                if (phase == 0) st2(M + tile_off(i, j + u) + fragC, r[u]);
+                else st2(M + tile_off(i + u, j) + fragC, r[u]);
+              }
+          }
+          __syncthreads();
+        }
+      }
+    }
+  }
+}
+
+// x = W' D^{-1} W rhs with the full inverse W = inv(L) of complete_inverse.  Thread t owns row t of
+// the forward product (tiles (tb, 0..tb), contiguous) and column t of the backward one (tiles
+// (tb..NB-1, tb)): NB + 1 tile-vector products per thread whatever its row, two barriers per solve.
+__device__ __noinline__ double kkt_solve_full(const double* __restrict__ M, const double* __restrict__ dinv,
+                                              double* __restrict__ tbuf, double* __restrict__ ybuf, double acc,
+                                              const int NB, const int N8) {
+  const int t = threadIdx.x;
+  const bool is_row = t < N8;
+  const int tb = t >> 3, tr = t & 7, tf = tr >> 1;
+  const int colo = tr & 1, colc = tr >> 1;
+  const int flip = tb & 1;
+  const int tbe = tb < NB ? tb : NB - 1;
+  if (is_row) tbuf[t] = acc;
+  __syncthreads();
+  {
+    const double* lrow = M + tile_off(tbe, 0) + tr * 8;
+    double s0 = 0.0, s1 = 0.0;
+    int jb = 0;
+#pragma unroll 1
+    for (; jb + 1 <= tbe; jb += 2) {
+      s0 += row_dot8(lrow + 64 * jb, tf, tbuf + jb * 8);
+      s1 += row_dot8(lrow + 64 * jb + 64, tf, tbuf + jb * 8 + 8);
+    }
+    if (jb <= tbe) s0 += row_dot8(lrow + 64 * jb, tf, tbuf + jb * 8);
+    if (is_row) ybuf[t] = (s0 + s1) * dinv[t];
+  }
+  __syncthreads();
+  double s0 = 0.0, s1 = 0.0;
+  int ib = tbe;
+#pragma unroll 1
+  for (; ib + 1 < NB; ib += 2) {
+    s0 += col_dot8(M + tile_off(ib, tbe) + colo, colc, flip, ybuf + ib * 8);
+    s1 += col_dot8(M + tile_off(ib + 1, tbe) + colo, colc, flip, ybuf + ib * 8 + 8);
+  }
+  if (ib < NB) s0 += col_dot8(M + tile_off(ib, tbe) + colo, colc, flip, ybuf + ib * 8);
+  return is_row ? s0 + s1 : 0.0;
+}
+
+// ---------------------------------------------------------------------------
 // The fused solve kernel.  kThreads >= padded KKT size N8 (one thread per KKT row in the
 // triangular solves and all vector work).  Warp 0 is the factorization's critical-path warp,
 // warps 1.. are its helpers.
@@ -794,6 +935,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
       }
       const int iters = pass == 0 ? 1 : p.max_iter;
       bool factored = false;
+      bool full_inverse = false;   // W = inv(L) completed (long-running QPs)
       double rhs0 = 0.0;   // pass-0 right-hand side of row t
 
 #pragma unroll 1
@@ -934,7 +1076,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
           acc = v_b;
         }
         TR(30);
-        val = kkt_solve(M, dinv, tbuf, ybuf, acc, NB, NB32, N8 FCCQP_TRACE_ARGS);
+        if (!full_inverse && pass == 1 && iter >= p.full_inverse_at) {
+          __syncthreads();
+          complete_inverse<kThreads>(M, NB);
+          full_inverse = true;
+          FCCQP_PROF(4);
+        }
+        if (full_inverse) val = kkt_solve_full(M, dinv, tbuf, ybuf, acc, NB, N8);
+        else val = kkt_solve(M, dinv, tbuf, ybuf, acc, NB, NB32, N8 FCCQP_TRACE_ARGS);
         FCCQP_PROF(7);
         TR(35);
         // val = solution component of row t (t < N8)
