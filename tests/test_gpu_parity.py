@@ -179,3 +179,41 @@ def test_full_size_properties(walking_log):
     first = z[: walking_log.batch]
     for k in range(1, B // walking_log.batch):
         assert np.array_equal(z[k * walking_log.batch:(k + 1) * walking_log.batch], first)
+
+
+@pytest.mark.parametrize("switch_at", ["1", "1000000"])
+def test_long_running_path_switch_point(switch_at, tmp_path):
+    """Long-running QPs complete inv(L) after FCCQP_FULL_INVERSE_AT iterations (default 6).  Both
+    extremes -- every iterating QP on the full-inverse path from its first real x-update, and the
+    path never taken -- must meet the same parity bar on every shape (128- and 256-thread kernels,
+    NB = 11 ... 24 tile rows).  The switch is read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    code = r'''
+import os, sys, numpy as np
+sys.path.insert(0, os.path.join(sys.argv[1], "tests")); sys.path.insert(0, sys.argv[1])
+from fcc_qp_b200 import synthetic as syn
+from fcc_qp_b200.logdata import load_walking_log
+from fcc_qp_b200.batch import FCCQPBatch, FCCQPOptionsB
+G = os.path.join(sys.argv[1], "tests", "golden")
+opts = dict(max_iter=100, rho=5e-5, eps_fcone=1e-6, eps_bound=1e-6)
+log = load_walking_log()
+cases = [(log, "walking_cold")] + [(syn.make_batch(syn.SHAPES[n], B), f"synthetic_{n}_cold")
+                                   for n, B in (("humanoid", 192), ("quadruped", 192), ("multicontact", 96))]
+for qp, g in cases:
+    gold = np.load(os.path.join(G, g + ".npz"))
+    s = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start); s.set_options(FCCQPOptionsB(**opts))
+    s.Solve(qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)
+    sol = s.GetSolution()
+    err = (np.abs(sol.z - gold["z"]).max(1) / np.maximum(1.0, np.abs(gold["z"]).max(1))).max()
+    mism = float((sol.details.n_iter != gold["n_iter"]).mean())
+    print(g, err, mism, int((gold["n_iter"] > 6).sum()))
+    assert err <= 1e-6, (g, err)
+    assert mism <= (0.0 if g == "walking_cold" else 0.02), (g, mism)
+print("ok")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FCCQP_FULL_INVERSE_AT=switch_at)
+    r = subprocess.run([sys.executable, "-c", code, root], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.strip().endswith("ok")
