@@ -130,7 +130,7 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream) {
   static const int fui = getenv("FCCQP_FIRST_UPDATE_IDENTITY") ? atoi(getenv("FCCQP_FIRST_UPDATE_IDENTITY")) : 1;
   p.first_update_identity = fui != 0;
   // developer switch: ADMM iteration at which long-running QPs complete inv(L) (huge value = never)
-  static const int fia = getenv("FCCQP_FULL_INVERSE_AT") ? atoi(getenv("FCCQP_FULL_INVERSE_AT")) : 6;
+  static const int fia = getenv("FCCQP_FULL_INVERSE_AT") ? atoi(getenv("FCCQP_FULL_INVERSE_AT")) : 8;
   p.full_inverse_at = fia < 1 ? 1 : fia;
   int ctas_per_sm = 0;
   {

@@ -92,7 +92,7 @@ struct Layout {
 struct SolveParams {
   int B, n, m, nc, lcs;
   int max_iter, warm;
-  int full_inverse_at;        // ADMM iteration from which x-updates use the completed inverse of L (default 6)
+  int full_inverse_at;        // ADMM iteration from which x-updates use the completed inverse of L (default 8)
   int first_update_identity;  // cold solves: take x-update 0 as the identity it is (see kernel), default 1
   double rho, eps_fcone, eps_bound;
   const double* Q;   long long q_bs, q_rs, q_cs;
@@ -669,9 +669,11 @@ __device__ __noinline__ double kkt_solve(const double* __restrict__ M, const dou
 
 // ---------------------------------------------------------------------------
 // Long-running QPs (the 1-2 % that iterate towards max_iter dominate both the mean and the tail of
-// a batch): after kFullInverseAt ADMM iterations the factor is completed to W = inv(L), in place,
-// and every later x-update is two triangular matrix-vector products (kkt_solve_full) instead of
-// 2 x N/32 dependent block steps.
+// a batch): after SolveParams::full_inverse_at ADMM iterations the factor is completed to
+// W = inv(L), in place (complete_inverse), x_base = [K^{-1} (-b; b_eq)]_x is formed with two triangular
+// matrix-vector products (kkt_solve_full) and G = [K^{-1}]_xx replaces the top-left tiles of W
+// (form_g); every later x-update is x = x_base + rho G (x_bar - mu) (g_apply): one symmetric
+// n x n matrix-vector product and one barrier instead of 2 x N/32 dependent block steps.
 //
 // complete_inverse: recursive doubling from the 32x32 diagonal-block inverses factor_tiles left.
 // For block sizes s = 4, 8, 16 tiles, neighbouring diagonal blocks A (tiles [q, q+s)) and B (tiles
@@ -807,6 +809,91 @@ __device__ __noinline__ double kkt_solve_full(const double* __restrict__ M, cons
   return is_row ? s0 + s1 : 0.0;
 }
 
+// G = [K^{-1}]_xx = sum_K W_{K,:n8}' D_K^{-1} W_{K,:n8}, written over the top-left NBx x NBx tile triangle of
+// W (W is not needed afterwards): with x_base = [K^{-1} (-b; b_eq)]_x every later x-update is
+//     x = x_base + rho G (x_bar - mu)        (one symmetric matrix-vector product, one barrier).
+// One chunk of up to four tiles (I, J..J+3) per warp and round; chunks in ascending row order, so a
+// round only overwrites W rows that no later chunk reads (row I' > I needs W_{K,.} for K >= I' only;
+// the K = I term of a later chunk of the SAME row reads tile (I,I) and its own columns, which are
+// stored with that chunk).  All products of a round, barrier, all stores, barrier.
+template <int kThreads>
+__device__ __noinline__ void form_g(double* __restrict__ M, const double* __restrict__ dinv, const int NB, const int NBx) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kWarps = kThreads / 32;
+  const int fr = lane >> 2, fq = lane & 3;
+  const int fragC = (fr << 3) + (((fq ^ (fr >> 1)) & 3) << 1);
+  const int fragT = ((2 * fq) << 3) + ((((fr >> 1) ^ fq) & 3) << 1) + (fr & 1);
+  int I = 0, J = 0;               // chunk cursor: row I, first column J
+  bool more = NBx > 0;
+#pragma unroll 1
+  while (more) {
+    // this warp's chunk = cursor advanced by `warp` chunks; then the cursor moves kWarps chunks on
+    int ci = I, cj = J;
+    bool act = true;
+#pragma unroll 1
+    for (int k = 0; k < warp && act; ++k) { cj += 4; if (cj > ci) { ++ci; cj = 0; } act = ci < NBx; }
+    double2 r[4], rb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { r[u] = make_double2(0.0, 0.0); rb[u] = make_double2(0.0, 0.0); }
+    const int cnt = act ? min(4, ci + 1 - cj) : 0;
+    if (act) {
+#pragma unroll 1
+      for (int K = ci; K < NB; ++K) {
+        const double* ap = M + tile_off(K, ci) + fragT;
+        const double2 d = ld2(dinv + 8 * K + 2 * fq);
+        const double a0 = ap[0] * d.x, a1 = ap[8] * d.y;
+        const double* bp = M + tile_off(K, cj) + fragT;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (u < cnt) {
+            dmma(r[u].x, r[u].y, a0, bp[64 * u]);
+            dmma(rb[u].x, rb[u].y, a1, bp[64 * u + 8]);
+          }
+      }
+    }
+    __syncthreads();
+    if (act) {
+      double* cp = M + tile_off(ci, cj) + fragC;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (u < cnt) st2(cp + 64 * u, make_double2(r[u].x + rb[u].x, r[u].y + rb[u].y));
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int k = 0; k < kWarps && more; ++k) { J += 4; if (J > I) { ++I; J = 0; } more = I < NBx; }
+  }
+}
+
+// (G w)_t for the variable rows t < n8 (0 elsewhere): row part over tiles (tb, 0..tb), column part over
+// tiles (tb+1.., tb) of the lower-stored symmetric G.
+__device__ __noinline__ double g_apply(const double* __restrict__ M, double* __restrict__ tbuf, double w,
+                                       const int NBx, const int n8) {
+  const int t = threadIdx.x;
+  const int tb = t >> 3, tr = t & 7, tf = tr >> 1;
+  const int colo = tr & 1, colc = tr >> 1;
+  const int flip = tb & 1;
+  if (t < n8) tbuf[t] = w;
+  __syncthreads();
+  if (t >= n8) return 0.0;
+  const double* lrow = M + tile_off(tb, 0) + tr * 8;
+  double s0 = 0.0, s1 = 0.0;
+  int jb = 0;
+#pragma unroll 1
+  for (; jb + 1 <= tb; jb += 2) {
+    s0 += row_dot8(lrow + 64 * jb, tf, tbuf + jb * 8);
+    s1 += row_dot8(lrow + 64 * jb + 64, tf, tbuf + jb * 8 + 8);
+  }
+  if (jb <= tb) s0 += row_dot8(lrow + 64 * jb, tf, tbuf + jb * 8);
+  int ib = tb + 1;
+#pragma unroll 1
+  for (; ib + 1 < NBx; ib += 2) {
+    s0 += col_dot8(M + tile_off(ib, tb) + colo, colc, flip, tbuf + ib * 8);
+    s1 += col_dot8(M + tile_off(ib + 1, tb) + colo, colc, flip, tbuf + ib * 8 + 8);
+  }
+  if (ib < NBx) s0 += col_dot8(M + tile_off(ib, tb) + colo, colc, flip, tbuf + ib * 8);
+  return s0 + s1;
+}
+
 // ---------------------------------------------------------------------------
 // The fused solve kernel.  kThreads >= padded KKT size N8 (one thread per KKT row in the
 // triangular solves and all vector work).  Warp 0 is the factorization's critical-path warp,
@@ -935,7 +1022,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
       }
       const int iters = pass == 0 ? 1 : p.max_iter;
       bool factored = false;
-      bool full_inverse = false;   // W = inv(L) completed (long-running QPs)
+      bool full_inverse = false;   // long-running QP: x-updates through G = [K^{-1}]_xx
+      double v_xbase = 0.0;        // its x_base entry of row t
       double rhs0 = 0.0;   // pass-0 right-hand side of row t
 
 #pragma unroll 1
@@ -1077,13 +1165,23 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
         }
         TR(30);
         if (!full_inverse && pass == 1 && iter >= p.full_inverse_at) {
+          // long-running QP: W = inv(L), x_base = [K^{-1} (-b; b_eq)]_x, G = [K^{-1}]_xx (see form_g)
           __syncthreads();
           complete_inverse<kThreads>(M, NB);
+          v_xbase = kkt_solve_full(M, dinv, tbuf, ybuf, is_x ? -v_b : (is_c ? v_b : 0.0), NB, N8);
+          __syncthreads();
+          form_g<kThreads>(M, dinv, NB, NBx);
           full_inverse = true;
           FCCQP_PROF(4);
         }
-        if (full_inverse) val = kkt_solve_full(M, dinv, tbuf, ybuf, acc, NB, N8);
-        else val = kkt_solve(M, dinv, tbuf, ybuf, acc, NB, NB32, N8 FCCQP_TRACE_ARGS);
+        if (full_inverse) {
+          // rhs_x = -b + rho w, rhs_c = b_eq  =>  x = x_base + rho G w
+          const double w = is_x ? (in_cone ? (lcbar[t - lcs] - muc[t - lcs]) : (v_xbar - v_mux)) : 0.0;
+          const double gw = g_apply(M, tbuf, w, NBx, n8);
+          val = is_x ? fma(p.rho, gw, v_xbase) : 0.0;
+        } else {
+          val = kkt_solve(M, dinv, tbuf, ybuf, acc, NB, NB32, N8 FCCQP_TRACE_ARGS);
+        }
         FCCQP_PROF(7);
         TR(35);
         // val = solution component of row t (t < N8)
