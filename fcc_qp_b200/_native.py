@@ -64,6 +64,26 @@ class BatchDesc(C.Structure):
     ]
 
 
+class WbcDesc(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("batch", C.c_int32),
+        ("nv", C.c_int32), ("nu", C.c_int32), ("nh", C.c_int32), ("nc", C.c_int32), ("ny", C.c_int32),
+        ("device", C.c_int32),
+        ("w_vdot", C.c_double), ("w_u", C.c_double), ("w_lambda_c", C.c_double), ("w_eps", C.c_double),
+        ("M", C.c_void_p), ("M_batch_stride", C.c_int64),
+        ("Jh", C.c_void_p), ("Jh_batch_stride", C.c_int64),
+        ("Jc", C.c_void_p), ("Jc_batch_stride", C.c_int64),
+        ("Jy", C.c_void_p), ("Jy_batch_stride", C.c_int64),
+        ("W", C.c_void_p), ("W_batch_stride", C.c_int64),
+        ("ydd_cmd", C.c_void_p), ("ydd_batch_stride", C.c_int64),
+        ("bias", C.c_void_p), ("bias_batch_stride", C.c_int64),
+        ("gamma_h", C.c_void_p), ("gh_batch_stride", C.c_int64),
+        ("gamma_c", C.c_void_p), ("gc_batch_stride", C.c_int64),
+        ("Q", C.c_void_p), ("b", C.c_void_p), ("A_eq", C.c_void_p), ("b_eq", C.c_void_p),
+        ("stream", C.c_void_p),
+    ]
+
+
 # every symbol include/fccqp.h declares (tests check that the library exports them all)
 EXPORTS = [
     "fccqp_default_options", "fccqp_last_error", "fccqp_abi_version", "fccqp_device_count",
@@ -71,7 +91,7 @@ EXPORTS = [
     "fccqp_set_max_iter", "fccqp_set_warm_start", "fccqp_contact_vars_start", "fccqp_solve",
     "fccqp_get_solution", "fccqp_get_warm_state", "fccqp_set_warm_state", "fccqp_batch_solve",
     "fccqp_release_workspaces", "fccqp_kernel_launch_count", "fccqp_last_launch_info",
-    "fccqp_alloc_pinned", "fccqp_free_pinned",
+    "fccqp_alloc_pinned", "fccqp_free_pinned", "fccqp_wbc_assemble",
 ]
 
 _lib = None
@@ -107,6 +127,7 @@ def lib() -> C.CDLL:
     L.fccqp_last_launch_info.argtypes = [_ip, _ip, _ip, _ip]
     L.fccqp_alloc_pinned.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     L.fccqp_free_pinned.argtypes = [C.c_void_p]
+    L.fccqp_wbc_assemble.argtypes = [C.POINTER(WbcDesc)]
     _lib = L
     return L
 

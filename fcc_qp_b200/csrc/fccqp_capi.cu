@@ -685,6 +685,44 @@ int fccqp_batch_solve(const fccqp_batch_desc* desc) {
   return FCCQP_OK;
 }
 
+int fccqp_wbc_assemble(const fccqp_wbc_desc* d) {
+  if (!d) return fail(FCCQP_E_INVALID, "desc is null");
+  if (d->abi_version != FCCQP_ABI_VERSION) return fail(FCCQP_E_INVALID, "abi_version %d != %d", d->abi_version, FCCQP_ABI_VERSION);
+  if (d->batch < 0 || d->nv < 1 || d->nu < 0 || d->nu > d->nv || d->nh < 0 || d->nc < 0 || d->ny < 0)
+    return fail(FCCQP_E_INVALID, "bad WBC dimensions (need nv >= 1, 0 <= nu <= nv, nh, nc, ny >= 0)");
+  if (d->nc % 3 != 0) return fail(FCCQP_E_INVALID, "nc = %d must be a multiple of 3 (src/fcc_qp.cpp:32)", d->nc);
+  DeviceCtx* ctx = nullptr;
+  int rc = get_ctx(d->device, &ctx);
+  if (rc) return rc;
+  if (d->batch == 0) return FCCQP_OK;
+  if (!d->M || !d->bias || !d->Q || !d->b || !d->A_eq || !d->b_eq || (d->nh > 0 && (!d->Jh || !d->gamma_h)) ||
+      (d->nc > 0 && (!d->Jc || !d->gamma_c)) || (d->ny > 0 && (!d->Jy || !d->W || !d->ydd_cmd)))
+    return fail(FCCQP_E_INVALID, "null WBC input/output pointer");
+  CUDA_TRY(cudaSetDevice(d->device));
+  fccqp::WbcParams p{};
+  p.B = d->batch; p.nv = d->nv; p.nu = d->nu; p.nh = d->nh; p.nc = d->nc; p.ny = d->ny;
+  p.w_vdot = d->w_vdot; p.w_u = d->w_u; p.w_lc = d->w_lambda_c; p.w_eps = d->w_eps;
+  p.M = d->M; p.M_bs = d->M_batch_stride; p.Jh = d->Jh; p.Jh_bs = d->Jh_batch_stride;
+  p.Jc = d->Jc; p.Jc_bs = d->Jc_batch_stride; p.Jy = d->Jy; p.Jy_bs = d->Jy_batch_stride;
+  p.W = d->W; p.W_bs = d->W_batch_stride; p.ydd = d->ydd_cmd; p.ydd_bs = d->ydd_batch_stride;
+  p.bias = d->bias; p.bias_bs = d->bias_batch_stride; p.gh = d->gamma_h; p.gh_bs = d->gh_batch_stride;
+  p.gc = d->gamma_c; p.gc_bs = d->gc_batch_stride;
+  p.Q = d->Q; p.b = d->b; p.A = d->A_eq; p.beq = d->b_eq;
+  const size_t smem = sizeof(double) * ((size_t)d->ny * d->nv + d->ny + (size_t)d->nv * d->nv);
+  if (smem > (size_t)ctx->max_smem_optin) return fail(FCCQP_E_UNSUPPORTED, "WBC terms need %zu B of shared memory", smem);
+  static std::mutex attr_mu;
+  {
+    std::lock_guard<std::mutex> lk(attr_mu);
+    CUDA_TRY(cudaFuncSetAttribute(fccqp::wbc_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin));
+  }
+  int grid = ctx->num_sms * 8;
+  if (grid > d->batch) grid = d->batch;
+  fccqp::wbc_assemble_kernel<<<grid, 256, smem, (cudaStream_t)d->stream>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return FCCQP_OK;
+}
+
 int fccqp_alloc_pinned(size_t bytes, void** out) {
   if (!out) return fail(FCCQP_E_INVALID, "out is null");
   *out = nullptr;

@@ -1287,4 +1287,106 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
 #undef FCCQP_TRACE_ARGS
 }
 
+// ---------------------------------------------------------------------------
+// WBC assembly (include/fccqp.h, fccqp_wbc_assemble): one CTA per QP writes Q, b, A_eq, b_eq from
+// the robot quantities.  HBM-write bound (8 (n^2 + m n + n + m) bytes per QP, every output element
+// written exactly once, coalesced); the only arithmetic is the nv x nv task Hessian Jy' W Jy and
+// the gradient, formed from a shared-memory copy of Jy (lower triangle computed, mirrored, so Q is
+// exactly symmetric).
+// ---------------------------------------------------------------------------
+struct WbcParams {
+  int B, nv, nu, nh, nc, ny;
+  double w_vdot, w_u, w_lc, w_eps;
+  const double* M; long long M_bs;
+  const double* Jh; long long Jh_bs;
+  const double* Jc; long long Jc_bs;
+  const double* Jy; long long Jy_bs;
+  const double* W; long long W_bs;
+  const double* ydd; long long ydd_bs;
+  const double* bias; long long bias_bs;
+  const double* gh; long long gh_bs;
+  const double* gc; long long gc_bs;
+  double* Q; double* b; double* A; double* beq;
+};
+
+__global__ void __launch_bounds__(256) wbc_assemble_kernel(const WbcParams p) {
+  extern __shared__ __align__(16) double sm[];
+  const int nv = p.nv, nu = p.nu, nh = p.nh, nc = p.nc, ny = p.ny;
+  const int n = nv + nu + nh + 2 * nc, m = nv + nh + nc;
+  const int o_u = nv, o_h = nv + nu, o_c = nv + nu + nh, o_e = o_c + nc;
+  double* const sJ = sm;                 // [ny][nv]
+  double* const sW = sm + ny * nv;       // [ny]
+  double* const sH = sW + ny;            // [nv][nv] task Hessian
+  for (int qp = blockIdx.x; qp < p.B; qp += gridDim.x) {
+    const double* Jy = p.Jy + (size_t)qp * p.Jy_bs;
+    const double* W = p.W + (size_t)qp * p.W_bs;
+    const double* ydd = p.ydd + (size_t)qp * p.ydd_bs;
+    const double* Mq = p.M + (size_t)qp * p.M_bs;
+    const double* Jh = p.Jh + (size_t)qp * p.Jh_bs;
+    const double* Jc = p.Jc + (size_t)qp * p.Jc_bs;
+    double* Q = p.Q + (size_t)qp * n * n;
+    double* A = p.A + (size_t)qp * m * n;
+    double* b = p.b + (size_t)qp * n;
+    double* beq = p.beq + (size_t)qp * m;
+    __syncthreads();
+    for (int e = threadIdx.x; e < ny * nv; e += blockDim.x) sJ[e] = Jy[e];
+    for (int e = threadIdx.x; e < ny; e += blockDim.x) sW[e] = W[e];
+    __syncthreads();
+    // task Hessian, lower triangle (k ascending: the summation order of the numpy restatement)
+    for (int e = threadIdx.x; e < nv * nv; e += blockDim.x) {
+      const int i = e / nv, j = e - i * nv;
+      if (j <= i) {
+        double s = 0.0;
+        for (int k = 0; k < ny; ++k) s += sJ[k * nv + i] * sW[k] * sJ[k * nv + j];
+        sH[i * nv + j] = s;
+        sH[j * nv + i] = s;
+      }
+    }
+    // gradient and constraint right-hand side
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      double s = 0.0;
+      if (i < nv) {
+        for (int k = 0; k < ny; ++k) s += sJ[k * nv + i] * (sW[k] * ydd[k]);
+        s = -s;
+      }
+      b[i] = s;
+    }
+    for (int r = threadIdx.x; r < m; r += blockDim.x)
+      beq[r] = r < nv ? -p.bias[(size_t)qp * p.bias_bs + r]
+                      : (r < nv + nh ? -p.gh[(size_t)qp * p.gh_bs + (r - nv)] : -p.gc[(size_t)qp * p.gc_bs + (r - nv - nh)]);
+    __syncthreads();
+    // Q and A_eq: one warp per matrix row, lanes along the row (no index division, coalesced stores)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int i = wid; i < n; i += nw) {
+      const double dg = i < o_u ? p.w_vdot : (i < o_h ? p.w_u : (i < o_c ? 0.0 : (i < o_e ? p.w_lc : p.w_eps)));
+      double* qrow = Q + (size_t)i * n;
+      const double* hrow = sH + i * nv;
+      for (int j = lane; j < n; j += 32) {
+        double v = (i < nv && j < nv) ? hrow[j] : 0.0;
+        if (i == j) v += dg;
+        qrow[j] = v;
+      }
+    }
+    for (int r = wid; r < m; r += nw) {
+      double* arow = A + (size_t)r * n;
+      if (r < nv) {
+        const double* mrow = Mq + r * nv;
+        for (int c = lane; c < n; c += 32) {
+          double v = 0.0;
+          if (c < o_u) v = mrow[c];
+          else if (c < o_h) v = (r - (nv - nu) == c - o_u) ? -1.0 : 0.0;       // -S, S = [0; I_nu]
+          else if (c < o_c) v = -Jh[(c - o_h) * nv + r];                         // -Jh'
+          else if (c < o_e) v = -Jc[(c - o_c) * nv + r];                         // -Jc'
+          arow[c] = v;
+        }
+      } else {
+        const bool hol = r < nv + nh;
+        const double* jrow = hol ? Jh + (r - nv) * nv : Jc + (r - nv - nh) * nv;
+        const int one = hol ? -1 : o_e + (r - nv - nh);                          // identity on the slack columns
+        for (int c = lane; c < n; c += 32) arow[c] = c < o_u ? jrow[c] : (c == one ? 1.0 : 0.0);
+      }
+    }
+  }
+}
+
 }  // namespace fccqp

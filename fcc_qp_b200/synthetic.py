@@ -57,23 +57,46 @@ CASSIE_LIKE = Shape("cassie_like", nv=22, nu=10, nh=6, nc=12, seed=20240, joint_
 SHAPES = {s.name: s for s in (HUMANOID, QUADRUPED, MULTICONTACT, CASSIE_LIKE)}
 
 
-def make_batch(shape: Shape, batch: int, seed: int | None = None, u_max: float = 300.0,
+@dataclasses.dataclass
+class WBCTerms:
+    """Robot quantities one WBC QP is assembled from (``fccqp.pdf`` section 4; ``include/fccqp.h``,
+    ``fccqp_wbc_assemble``).  All arrays carry the batch as leading dimension, float64, C-contiguous."""
+    shape: Shape
+    M: np.ndarray          # [B,nv,nv] mass matrix
+    Jh: np.ndarray         # [B,nh,nv] holonomic Jacobian
+    Jc: np.ndarray         # [B,nc,nv] contact Jacobian (zero rows for feet off the ground)
+    Jy: np.ndarray         # [B,ny,nv] task Jacobian
+    W: np.ndarray          # [B,ny]    task weights
+    ydd_cmd: np.ndarray    # [B,ny]    commanded task accelerations
+    bias: np.ndarray       # [B,nv]    Coriolis + gravity
+    gamma_h: np.ndarray    # [B,nh]
+    gamma_c: np.ndarray    # [B,nc]
+    friction_coeffs: np.ndarray  # [B,nc/3]
+    u_max: float = 300.0
+    weights: tuple = (1e-5, 1e-4, 1e-6, 80.0)   # w_vdot, w_u, w_lambda_c, w_eps
+
+    @property
+    def batch(self) -> int:
+        return int(self.M.shape[0])
+
+    def nbytes(self) -> int:
+        return int(sum(a.nbytes for a in (self.M, self.Jh, self.Jc, self.Jy, self.W, self.ydd_cmd, self.bias,
+                                          self.gamma_h, self.gamma_c, self.friction_coeffs)))
+
+
+def make_terms(shape: Shape, batch: int, seed: int | None = None, u_max: float = 300.0,
                ydd_sigma: float = 1.0, bias_sigma: float = 1.0, joint_scale: float | None = None,
-               height: float = 0.75, weight: float = 300.0) -> QPBatch:
-    """B synthetic QPs of ``shape``.  Defaults are tuned (against the reference solver, rho=5e-5,
-    eps=1e-6, max_iter=100) so that most pre-solve points are feasible, 15-30 % of the QPs need
-    ADMM iterations and a few per cent run to max_iter -- the mix seen on the walking log."""
+               height: float = 0.75, weight: float = 300.0) -> WBCTerms:
+    """Robot quantities of B synthetic QPs of ``shape`` (see ``make_batch`` for the tuning)."""
     joint_scale = shape.joint_scale if joint_scale is None else joint_scale
     rng = np.random.default_rng(shape.seed if seed is None else seed)
     B, nv, nu, nh, nc, ne = batch, shape.nv, shape.nu, shape.nh, shape.nc, shape.ne
-    n, m, ncon = shape.n, shape.m, nc // 3
+    ncon = nc // 3
     ny = max(nv - 4, 1)
 
     G = rng.standard_normal((B, nv, nv))
     Mass = G @ G.transpose(0, 2, 1) / nv
     Mass[:, np.arange(nv), np.arange(nv)] += rng.uniform(0.05, 3.0, (B, nv))
-    Bsel = np.zeros((nv, nu))
-    Bsel[nv - nu:, :] = np.eye(nu)  # floating base (first nv - nu dofs) is unactuated
 
     # Point contacts around the floating base: J_c = [I3, -[p]x, J_joints].  With the gravity-like
     # bias below, the (almost cost-free) contact forces mostly come out inside their cones, like
@@ -110,37 +133,59 @@ def make_batch(shape: Shape, batch: int, seed: int | None = None, u_max: float =
     W = rng.uniform(0.1, 20.0, (B, ny))
     ydd = rng.standard_normal((B, ny)) * ydd_sigma
 
-    Q = np.zeros((B, n, n))
-    Q[:, :nv, :nv] = np.einsum("bki,bk,bkj->bij", Jy, W, Jy)
-    d = np.concatenate([np.full(nv, 1e-5), np.full(nu, 1e-4), np.zeros(nh), np.full(nc, 1e-6), np.full(ne, 80.0)])
-    Q[:, np.arange(n), np.arange(n)] += d
-    Q = 0.5 * (Q + Q.transpose(0, 2, 1))
-    b = np.zeros((B, n))
-    b[:, :nv] = -np.einsum("bki,bk->bi", Jy, W * ydd)
-
-    o_u, o_h, o_c, o_e = nv, nv + nu, nv + nu + nh, nv + nu + nh + nc
-    A = np.zeros((B, m, n))
-    A[:, :nv, :nv] = Mass
-    A[:, :nv, o_u:o_h] = -Bsel
-    if nh:
-        A[:, :nv, o_h:o_c] = -Jh.transpose(0, 2, 1)
-        A[:, nv:nv + nh, :nv] = Jh
-    A[:, :nv, o_c:o_e] = -Jc.transpose(0, 2, 1)
-    A[:, nv + nh:, :nv] = Jc
-    A[:, nv + nh:, o_e:] = np.eye(ne)
-
     Cg = rng.standard_normal((B, nv)) * bias_sigma
     Cg[:, :6] *= 0.25
     Cg[:, 2] += weight  # weight on the vertical floating-base coordinate
-    beq = np.concatenate([-Cg, -rng.standard_normal((B, nh)) * 0.1, -rng.standard_normal((B, ne)) * 0.1], axis=1)
+    gamma_h = rng.standard_normal((B, nh)) * 0.1
+    gamma_c = rng.standard_normal((B, ne)) * 0.1
+    mu = rng.uniform(0.4, 1.0, (B, ncon))
+    c = np.ascontiguousarray
+    return WBCTerms(shape, c(Mass), c(Jh), c(Jc), c(Jy), c(W), c(ydd), c(Cg), c(gamma_h), c(gamma_c), c(mu), u_max)
+
+
+def assemble_numpy(t: WBCTerms) -> QPBatch:
+    """CPU restatement of ``fccqp_wbc_assemble`` (the parity reference of the device kernel):
+    ``Q, b, A_eq, b_eq, lb, ub`` of the QPs described by ``t`` (formulas in the module docstring)."""
+    shape = t.shape
+    B, nv, nu, nh, nc, ne = t.batch, shape.nv, shape.nu, shape.nh, shape.nc, shape.ne
+    n, m = shape.n, shape.m
+    w_v, w_u, w_lc, w_eps = t.weights
+    Bsel = np.zeros((nv, nu))
+    Bsel[nv - nu:, :] = np.eye(nu)  # floating base (first nv - nu dofs) is unactuated
+
+    Q = np.zeros((B, n, n))
+    Q[:, :nv, :nv] = np.einsum("bki,bk,bkj->bij", t.Jy, t.W, t.Jy)
+    d = np.concatenate([np.full(nv, w_v), np.full(nu, w_u), np.zeros(nh), np.full(nc, w_lc), np.full(ne, w_eps)])
+    Q[:, np.arange(n), np.arange(n)] += d
+    Q = 0.5 * (Q + Q.transpose(0, 2, 1))
+    b = np.zeros((B, n))
+    b[:, :nv] = -np.einsum("bki,bk->bi", t.Jy, t.W * t.ydd_cmd)
+
+    o_u, o_h, o_c, o_e = nv, nv + nu, nv + nu + nh, nv + nu + nh + nc
+    A = np.zeros((B, m, n))
+    A[:, :nv, :nv] = t.M
+    A[:, :nv, o_u:o_h] = -Bsel
+    if nh:
+        A[:, :nv, o_h:o_c] = -t.Jh.transpose(0, 2, 1)
+        A[:, nv:nv + nh, :nv] = t.Jh
+    A[:, :nv, o_c:o_e] = -t.Jc.transpose(0, 2, 1)
+    A[:, nv + nh:, :nv] = t.Jc
+    A[:, nv + nh:, o_e:] = np.eye(ne)
+    beq = np.concatenate([-t.bias, -t.gamma_h, -t.gamma_c], axis=1)
 
     lb = np.full((B, n), -np.inf)
     ub = np.full((B, n), np.inf)
-    lb[:, o_u:o_h] = -u_max
-    ub[:, o_u:o_h] = u_max
-    mu = rng.uniform(0.4, 1.0, (B, ncon))
+    lb[:, o_u:o_h] = -t.u_max
+    ub[:, o_u:o_h] = t.u_max
     c = np.ascontiguousarray
-    return QPBatch(n, m, nc, shape.lambda_c_start, c(Q), c(b), c(A), c(beq), c(mu), c(lb), c(ub))
+    return QPBatch(n, m, nc, shape.lambda_c_start, c(Q), c(b), c(A), c(beq), c(t.friction_coeffs), c(lb), c(ub))
+
+
+def make_batch(shape: Shape, batch: int, seed: int | None = None, **kw) -> QPBatch:
+    """B synthetic QPs of ``shape``.  Defaults are tuned (against the reference solver, rho=5e-5,
+    eps=1e-6, max_iter=100) so that most pre-solve points are feasible, 15-30 % of the QPs need
+    ADMM iterations and a few per cent run to max_iter -- the mix seen on the walking log."""
+    return assemble_numpy(make_terms(shape, batch, seed, **kw))
 
 
 def random_walk(qp: QPBatch, rng: np.random.Generator, sigma: float = 0.02) -> QPBatch:

@@ -171,6 +171,43 @@ int fccqp_free_pinned(void* ptr);
 /* Frees the cached per-device staging buffers used by FCCQP_MEM_HOST calls. */
 int fccqp_release_workspaces(void);
 
+/* ------------------------------------------------------------------------- *
+ * On-device assembly of whole-body-control QPs from robot quantities (SURVEY.md 8f row 2:
+ * the step BEFORE Solve in an operational-space-control / sampling-MPC loop; fccqp.pdf
+ * section 4, eq. 10).  The reference has no such function -- its callers (fcc_qp_test.py's log,
+ * the DAIRLab OSC) hand FCCQP::Solve finished Q, b, A_eq, b_eq (src/fcc_qp.hpp:114-117) -- so a
+ * batch that is assembled on the GPU moves nv^2 + (nh+nc+ny) nv + ... doubles per QP over PCIe
+ * instead of n^2 + m n.  Decision vector x = [vdot(nv) u(nu) lambda_h(nh) lambda_c(nc) eps(nc)],
+ * n = nv+nu+nh+2nc, m = nv+nh+nc, lambda_c_start = nv+nu+nh:
+ *     Q    = blkdiag(Jy' diag(W) Jy + w_vdot I, w_u I, 0, w_lambda_c I, w_eps I)
+ *     b    = [-Jy' (W .* ydd_cmd); 0]
+ *     A_eq = [[M, -S, -Jh', -Jc', 0], [Jh, 0, 0, 0, 0], [Jc, 0, 0, 0, I]],  S = [0; I_nu]
+ *     b_eq = [-bias; -gamma_h; -gamma_c]
+ * All pointers are DEVICE pointers to dense row-major FP64 arrays with the batch as the leading
+ * dimension (inputs: a *_batch_stride of 0 shares one array across the batch); outputs are the
+ * dense [B,n,n], [B,n], [B,m,n], [B,m] arrays fccqp_batch_solve takes.  Asynchronous on `stream`.
+ * ------------------------------------------------------------------------- */
+typedef struct fccqp_wbc_desc {
+  int32_t abi_version;     /* FCCQP_ABI_VERSION */
+  int32_t batch;
+  int32_t nv, nu, nh, nc, ny;
+  int32_t device;
+  double w_vdot, w_u, w_lambda_c, w_eps;   /* diagonal cost weights (1e-5, 1e-4, 1e-6, 80 on the walking log) */
+  const double* M;        int64_t M_batch_stride;      /* [B,nv,nv] mass matrix              */
+  const double* Jh;       int64_t Jh_batch_stride;     /* [B,nh,nv] holonomic Jacobian       */
+  const double* Jc;       int64_t Jc_batch_stride;     /* [B,nc,nv] contact Jacobian         */
+  const double* Jy;       int64_t Jy_batch_stride;     /* [B,ny,nv] task Jacobian            */
+  const double* W;        int64_t W_batch_stride;      /* [B,ny]    task weights             */
+  const double* ydd_cmd;  int64_t ydd_batch_stride;    /* [B,ny]    commanded task accel.    */
+  const double* bias;     int64_t bias_batch_stride;   /* [B,nv]    Coriolis + gravity       */
+  const double* gamma_h;  int64_t gh_batch_stride;     /* [B,nh]    Jh_dot v                 */
+  const double* gamma_c;  int64_t gc_batch_stride;     /* [B,nc]    Jc_dot v                 */
+  double* Q; double* b; double* A_eq; double* b_eq;    /* outputs */
+  void* stream;
+} fccqp_wbc_desc;
+
+int fccqp_wbc_assemble(const fccqp_wbc_desc* desc);
+
 /* Introspection used by bench.py for the roofline line: kernel launches issued
  * by this library since load, and the launch geometry of the last batch call. */
 int64_t fccqp_kernel_launch_count(void);
