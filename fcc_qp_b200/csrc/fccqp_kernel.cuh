@@ -23,21 +23,26 @@
 //     form [[Q + sigma A'A, A'],[A,0]] with right-hand side [-b + sigma A' b_eq; b_eq]: on
 //     {Ax = b_eq} the added term is constant, so x is unchanged, while Q + sigma A'A is positive
 //     definite exactly when the KKT matrix is nonsingular.  That matrix is quasi-definite, so an
-//     unpivoted LDL^T exists; one step of iterative refinement against the ORIGINAL system
-//     removes the sigma-dependent rounding.
+//     unpivoted LDL^T exists.  x-update 0 of a cold solve is then the identity (x0 minimises the
+//     proximal problem anchored at itself), so the 98 % of QPs that pass the exit test at x0 never
+//     factor the rho-KKT matrix; the others factor it lazily at iteration 1.
 //   * K2 is the same unpivoted blocked LDL^T on [[Q + rho I, A'],[A,0]].
-//   * Blocked LEFT-looking LDL^T on 8x8 tiles, one tile column at a time.  Warp w owns the tile
-//     rows i = w (mod #warps).  (A) every warp accumulates its tiles of column j in registers,
-//     C_ij = A_ij - sum_{k<j} L_ik D_k L_jk' (two DMMAs per term, operands read straight from the
-//     tile storage; nothing is written back in between, which keeps the shared-memory traffic
-//     at about a third of a right-looking update); the owner of the diagonal tile then factors
-//     it with ONE thread in registers and inverts its unit-lower factor; (B) every sub-diagonal
-//     tile becomes L_ij = C_ij inv(L_jj)' inv(D_j) with two more DMMAs and is stored once.
-//     The sigma A'A term of K1 and the rho I term of K2 are folded into step (A).
-//   * K3.  The 8x8 inverses are composed (again with DMMAs) into explicit inverses of the 32x32
-//     diagonal blocks of L, stored in place.  A triangular solve is then ceil(N/32) steps of
-//     "one warp applies a 32x32 inverse, the others subtract a 32-column slab" instead of N
+//   * factor_tiles: blocked LEFT-looking LDL^T on 8x8 tiles, one tile column at a time.  One warp
+//     runs the critical path (ONE thread factors the diagonal tile in registers and inverts its
+//     unit-lower factor; the warp forms the tile below it and updates the next diagonal tile), the
+//     helper warps own the tile rows i = w (mod #helpers) and stay one column behind:
+//     (B) L_ij = C_ij inv(L_jj)' inv(D_j), (A) C_i,j+1 -= sum_{k<=j} L_ik D_k L_j+1,k' for up to four
+//     tiles at a time with one shared scaled operand, accumulators in registers, nothing written
+//     back in between.  sigma A'A (K1) is formed beforehand in tile-row chunks, rho I (K2) is a
+//     diagonal add.
+//   * K3, kkt_solve.  The 8x8 inverses are composed (again with DMMAs) into explicit inverses of
+//     the 32x32 diagonal blocks of L, stored in place.  A triangular solve is then ceil(N/32) steps
+//     of "one warp applies a 32x32 inverse, the others subtract a 32-column slab" instead of N
 //     dependent scalar steps.
+//   * K3 for long-running QPs (complete_inverse, kkt_solve_full, form_g, g_apply): after
+//     full_inverse_at ADMM iterations W = inv(L) is completed in place by recursive doubling and
+//     G = [K^-1]_xx replaces its top-left tiles; every later x-update is
+//     x = x_base + rho G (x_bar - mu), one symmetric matrix-vector product.
 //
 // Storage: the lower triangle of the padded KKT matrix as dense 8x8 tiles (512 B each),
 // tile (I,J) at index I(I+1)/2+J.  Variables are padded to a multiple of 8 (n8) before the
@@ -60,7 +65,7 @@ struct Layout {
   int NB, NBx;      // number of 8-tiles per side; tiles covering the variable rows
   int NB32, NT;     // 32-row solve blocks; padded vector length (NB32 * 32)
   int NBT;          // number of stored tiles
-  int off_M, off_dinv, off_dneg, off_tbuf, off_ybuf, off_sbuf, off_xs, off_lcbar, off_muc, off_mu;
+  int off_M, off_dinv, off_dneg, off_tbuf, off_ybuf, off_xs, off_lcbar, off_muc, off_mu;
   int off_red, off_int;
   int doubles_total;
   static inline int up2(int v) { return (v + 1) & ~1; }
@@ -77,7 +82,6 @@ struct Layout {
     off_dneg = o;  o += NT;
     off_tbuf = o;  o += NT;
     off_ybuf = o;  o += NT;
-    off_sbuf = o;  o += NT;
     off_xs = o;    o += n8 + 8;
     off_lcbar = o; o += up2(nc + 2);
     off_muc = o;   o += up2(nc + 2);
@@ -913,7 +917,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
   double* const dneg = smem + p.lay.off_dneg;
   double* const tbuf = smem + p.lay.off_tbuf;
   double* const ybuf = smem + p.lay.off_ybuf;
-  double* const sbuf = smem + p.lay.off_sbuf;
   double* const xs = smem + p.lay.off_xs;
   double* const lcbar = smem + p.lay.off_lcbar;
   double* const muc = smem + p.lay.off_muc;
