@@ -90,6 +90,16 @@ int get_ctx(int device, DeviceCtx** out) {
   CUDA_TRY(cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   CUDA_TRY(cudaDeviceGetAttribute(&ctx->clock_khz, cudaDevAttrClockRate, device));
   CUDA_TRY(cudaMalloc(&ctx->counters, kCounterRing * sizeof(unsigned int)));
+  {
+    // stream-ordered scratch (cudaMallocAsync in the shared-structure path) stays in the pool across
+    // synchronisation points instead of going back to the OS after every call
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   for (auto& s : ctx->streams) CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&ctx->ev0));
   CUDA_TRY(cudaEventCreate(&ctx->ev1));
@@ -103,7 +113,8 @@ using KernelFn = void (*)(const fccqp::SolveParams);
 
 
 // Chooses the template instance (threads >= n + m; CTAs/SM hint from the packed-matrix footprint).
-int pick_kernel(const DeviceCtx& ctx, int n, int m, int nc, KernelFn* fn, int* threads, size_t* smem) {
+int pick_kernel(const DeviceCtx& ctx, int n, int m, int nc, KernelFn* fn, int* threads, size_t* smem,
+                KernelFn* fn_shared = nullptr) {
   const int N = n + m;
   if (N < 1) return fail(FCCQP_E_INVALID, "n + m must be >= 1");
   fccqp::Layout l(n, m, nc);
@@ -113,8 +124,15 @@ int pick_kernel(const DeviceCtx& ctx, int n, int m, int nc, KernelFn* fn, int* t
                 "n + m = %d (padded %d) needs %zu B of shared memory per QP (limit %d B, 256 rows): too large "
                 "for the shared-memory-resident kernels", N, l.N8, *smem, ctx.max_smem_optin);
   // one thread per padded KKT row; 4 CTAs/SM for the <= 128-row shapes (Cassie, quadruped)
-  if (l.N8 <= 128) { *threads = 128; *fn = (KernelFn)fccqp::fccqp_solve_kernel<128, 4>; }
-  else { *threads = 256; *fn = (KernelFn)fccqp::fccqp_solve_kernel<256, 2>; }
+  if (l.N8 <= 128) {
+    *threads = 128;
+    *fn = (KernelFn)fccqp::fccqp_solve_kernel<128, 4, false>;
+    if (fn_shared) *fn_shared = (KernelFn)fccqp::fccqp_solve_kernel<128, 4, true>;
+  } else {
+    *threads = 256;
+    *fn = (KernelFn)fccqp::fccqp_solve_kernel<256, 2, false>;
+    if (fn_shared) *fn_shared = (KernelFn)fccqp::fccqp_solve_kernel<256, 2, true>;
+  }
   return FCCQP_OK;
 }
 
@@ -122,8 +140,8 @@ int pick_kernel(const DeviceCtx& ctx, int n, int m, int nc, KernelFn* fn, int* t
 // (work_counter / gscratch are filled in here).
 int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream) {
   if (p.B == 0) return FCCQP_OK;
-  KernelFn fn; int threads; size_t smem;
-  int rc = pick_kernel(ctx, p.n, p.m, p.nc, &fn, &threads, &smem);
+  KernelFn fn, fn_shared; int threads; size_t smem;
+  int rc = pick_kernel(ctx, p.n, p.m, p.nc, &fn, &threads, &smem, &fn_shared);
   if (rc) return rc;
   p.lay = fccqp::Layout(p.n, p.m, p.nc);
   // developer switch: FCCQP_FIRST_UPDATE_IDENTITY=0 solves the (mathematically redundant) first x-update of cold QPs
@@ -133,6 +151,7 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream) {
   static const int fia = getenv("FCCQP_FULL_INVERSE_AT") ? atoi(getenv("FCCQP_FULL_INVERSE_AT")) : 8;
   p.full_inverse_at = fia < 1 ? 1 : fia;
   int ctas_per_sm = 0;
+  unsigned int* counter2 = nullptr;
   {
     std::lock_guard<std::mutex> lk(ctx.mu);
     const auto key = std::make_pair((const void*)fn, smem);
@@ -140,6 +159,7 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream) {
     if (it == ctx.occupancy.end()) {
       // the attribute is per kernel, the smem size per (n, m, nc): raise it to the device maximum once
       CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx.max_smem_optin));
+      CUDA_TRY(cudaFuncSetAttribute(fn_shared, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx.max_smem_optin));
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, fn, threads, smem));
       if (ctas_per_sm < 1) return fail(FCCQP_E_UNSUPPORTED, "kernel does not fit on an SM (smem %zu B)", smem);
       ctx.occupancy[key] = ctas_per_sm;
@@ -148,12 +168,59 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream) {
     }
     p.work_counter = ctx.counters + ctx.next_counter;
     ctx.next_counter = (ctx.next_counter + 1) % kCounterRing;
+    counter2 = ctx.counters + ctx.next_counter;   // second launch of the shared-structure path
+    ctx.next_counter = (ctx.next_counter + 1) % kCounterRing;
   }
   static const int cta_cap = getenv("FCCQP_CTAS_PER_SM") ? atoi(getenv("FCCQP_CTAS_PER_SM")) : 0;  // developer aid
   if (cta_cap > 0 && cta_cap < ctas_per_sm) ctas_per_sm = cta_cap;
   int grid = ctas_per_sm * ctx.num_sms;
   if (grid > p.B) grid = p.B;
   CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned int), stream));
+  // Shared-structure batches (one Q and one A_eq for the whole batch, cold): two launches, each with
+  // its KKT factorization cached per CTA (SolveParams::shared_mode).  Worth it once every CTA sees
+  // several QPs; FCCQP_NO_SHARED=1 forces the general path (tests compare the two).
+  static const bool no_shared = getenv("FCCQP_NO_SHARED") != nullptr;
+  if (!no_shared && !p.warm && p.q_bs == 0 && (p.m == 0 || p.a_bs == 0) && p.B >= 4 * ctas_per_sm * ctx.num_sms) {
+    unsigned int* scratch = nullptr;   // [0] = pending count, [1..B] = pending QP indices
+    CUDA_TRY(cudaMallocAsync(&scratch, ((size_t)p.B + 1) * sizeof(unsigned int), stream));
+    CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(unsigned int), stream));
+    CUDA_TRY(cudaMemsetAsync(counter2, 0, sizeof(unsigned int), stream));
+    fccqp::SolveParams a = p;
+    a.shared_mode = 1;
+    a.pending_count = scratch;
+    a.pending_list = reinterpret_cast<int*>(scratch + 1);
+    static const bool timing = getenv("FCCQP_SHARED_TIMING") != nullptr;   // developer aid: per-launch times
+    cudaEvent_t te[3] = {nullptr, nullptr, nullptr};
+    if (timing) { for (auto& e : te) CUDA_TRY(cudaEventCreate(&e)); CUDA_TRY(cudaEventRecord(te[0], stream)); }
+    fn_shared<<<grid, threads, smem, stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    if (timing) CUDA_TRY(cudaEventRecord(te[1], stream));
+    fccqp::SolveParams b = p;
+    b.shared_mode = 2;
+    b.count_dev = scratch;
+    b.index_list = reinterpret_cast<const int*>(scratch + 1);
+    b.work_counter = counter2;
+    fn_shared<<<grid, threads, smem, stream>>>(b);
+    CUDA_TRY(cudaGetLastError());
+    if (timing) {
+      unsigned int pending = 0;
+      CUDA_TRY(cudaEventRecord(te[2], stream));
+      CUDA_TRY(cudaMemcpyAsync(&pending, scratch, sizeof(pending), cudaMemcpyDeviceToHost, stream));
+      CUDA_TRY(cudaEventSynchronize(te[2]));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      float m1 = 0.f, m2 = 0.f;
+      cudaEventElapsedTime(&m1, te[0], te[1]); cudaEventElapsedTime(&m2, te[1], te[2]);
+      fprintf(stderr, "[fccqp shared] B=%d pre-solve launch %.3f ms, ADMM launch %.3f ms over %u QPs\n", p.B, m1, m2, pending);
+      for (auto& e : te) cudaEventDestroy(e);
+    }
+    CUDA_TRY(cudaFreeAsync(scratch, stream));
+    g_launches.fetch_add(2);
+    {
+      std::lock_guard<std::mutex> lk(g_info_mu);
+      g_last_launch = {grid, threads, (int)smem, ctas_per_sm};
+    }
+    return FCCQP_OK;
+  }
   static const bool profile = getenv("FCCQP_PROFILE") != nullptr;  // developer aid: phase cycle counters
   unsigned long long* d_prof = nullptr;
   if (profile) {

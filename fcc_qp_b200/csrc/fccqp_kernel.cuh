@@ -96,6 +96,16 @@ struct Layout {
 struct SolveParams {
   int B, n, m, nc, lcs;
   int max_iter, warm;
+  // Shared-structure batches (Q and A_eq common to all QPs, only the vectors vary -- sampling-based MPC;
+  // SURVEY 8f row 3): 0 = off; 1 = pre-solve launch (every CTA factors the pre-solve KKT matrix ONCE,
+  // completes inv(L) and streams QPs through it; QPs that need ADMM iterations park x0 and their
+  // index in pending_list); 2 = ADMM launch over index_list / count_dev with the rho-KKT factors cached
+  // the same way.
+  int shared_mode;
+  const int* index_list;          // mode 2: QP indices to process
+  const unsigned int* count_dev;  // mode 2: how many (device memory, written by the mode-1 launch)
+  int* pending_list;              // mode 1: output list
+  unsigned int* pending_count;    // mode 1: its length
   int full_inverse_at;        // ADMM iteration from which x-updates use the completed inverse of L (default 8)
   int first_update_identity;  // cold solves: take x-update 0 as the identity it is (see kernel), default 1
   double rho, eps_fcone, eps_bound;
@@ -821,25 +831,28 @@ __device__ __noinline__ double kkt_solve_full(const double* __restrict__ M, cons
 // the K = I term of a later chunk of the SAME row reads tile (I,I) and its own columns, which are
 // stored with that chunk).  All products of a round, barrier, all stores, barrier.
 template <int kThreads>
-__device__ __noinline__ void form_g(double* __restrict__ M, const double* __restrict__ dinv, const int NB, const int NBx) {
+__device__ __noinline__ void form_g(double* __restrict__ M, const double* __restrict__ dinv, const int NB, const int NBx,
+                                    const int NBr) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int kWarps = kThreads / 32;
   const int fr = lane >> 2, fq = lane & 3;
   const int fragC = (fr << 3) + (((fq ^ (fr >> 1)) & 3) << 1);
   const int fragT = ((2 * fq) << 3) + ((((fr >> 1) ^ fq) & 3) << 1) + (fr & 1);
+  // NBr = NBx: G itself.  NBr = NB: the rows [K^{-1}]_cx below it as well (tiles (I >= NBx, J < NBx)), so that
+  // [K^{-1}]_{x,:} rhs is one product over the lower-stored block column (shared-structure batches).
   int I = 0, J = 0;               // chunk cursor: row I, first column J
-  bool more = NBx > 0;
+  bool more = NBr > 0;
 #pragma unroll 1
   while (more) {
     // this warp's chunk = cursor advanced by `warp` chunks; then the cursor moves kWarps chunks on
     int ci = I, cj = J;
     bool act = true;
 #pragma unroll 1
-    for (int k = 0; k < warp && act; ++k) { cj += 4; if (cj > ci) { ++ci; cj = 0; } act = ci < NBx; }
+    for (int k = 0; k < warp && act; ++k) { cj += 4; if (cj > min(ci, NBx - 1)) { ++ci; cj = 0; } act = ci < NBr; }
     double2 r[4], rb[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) { r[u] = make_double2(0.0, 0.0); rb[u] = make_double2(0.0, 0.0); }
-    const int cnt = act ? min(4, ci + 1 - cj) : 0;
+    const int cnt = act ? min(4, min(ci, NBx - 1) + 1 - cj) : 0;
     if (act) {
 #pragma unroll 1
       for (int K = ci; K < NB; ++K) {
@@ -864,19 +877,19 @@ __device__ __noinline__ void form_g(double* __restrict__ M, const double* __rest
     }
     __syncthreads();
 #pragma unroll 1
-    for (int k = 0; k < kWarps && more; ++k) { J += 4; if (J > I) { ++I; J = 0; } more = I < NBx; }
+    for (int k = 0; k < kWarps && more; ++k) { J += 4; if (J > min(I, NBx - 1)) { ++I; J = 0; } more = I < NBr; }
   }
 }
 
 // (G w)_t for the variable rows t < n8 (0 elsewhere): row part over tiles (tb, 0..tb), column part over
 // tiles (tb+1.., tb) of the lower-stored symmetric G.
 __device__ __noinline__ double g_apply(const double* __restrict__ M, double* __restrict__ tbuf, double w,
-                                       const int NBx, const int n8) {
+                                       const int NBr, const int n8) {
   const int t = threadIdx.x;
   const int tb = t >> 3, tr = t & 7, tf = tr >> 1;
   const int colo = tr & 1, colc = tr >> 1;
   const int flip = tb & 1;
-  if (t < n8) tbuf[t] = w;
+  if (t < 8 * NBr) tbuf[t] = w;      // NBr tile rows of the operand take part (NBx: w; NB: a full KKT right-hand side)
   __syncthreads();
   if (t >= n8) return 0.0;
   const double* lrow = M + tile_off(tb, 0) + tr * 8;
@@ -890,11 +903,11 @@ __device__ __noinline__ double g_apply(const double* __restrict__ M, double* __r
   if (jb <= tb) s0 += row_dot8(lrow + 64 * jb, tf, tbuf + jb * 8);
   int ib = tb + 1;
 #pragma unroll 1
-  for (; ib + 1 < NBx; ib += 2) {
+  for (; ib + 1 < NBr; ib += 2) {
     s0 += col_dot8(M + tile_off(ib, tb) + colo, colc, flip, tbuf + ib * 8);
     s1 += col_dot8(M + tile_off(ib + 1, tb) + colo, colc, flip, tbuf + ib * 8 + 8);
   }
-  if (ib < NBx) s0 += col_dot8(M + tile_off(ib, tb) + colo, colc, flip, tbuf + ib * 8);
+  if (ib < NBr) s0 += col_dot8(M + tile_off(ib, tb) + colo, colc, flip, tbuf + ib * 8);
   return s0 + s1;
 }
 
@@ -903,8 +916,10 @@ __device__ __noinline__ double g_apply(const double* __restrict__ M, double* __r
 // triangular solves and all vector work).  Warp 0 is the factorization's critical-path warp,
 // warps 1.. are its helpers.
 // ---------------------------------------------------------------------------
-template <int kThreads, int kMinBlocks>
+template <int kThreads, int kMinBlocks, bool kShared>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const SolveParams p) {
+  // kShared = false compiles the shared-structure logic out of the general kernel
+  const int shared_mode = kShared ? p.shared_mode : 0;
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kWarps = kThreads / 32;
@@ -956,12 +971,17 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
   const long long q_slow = p.q_cs <= p.q_rs ? p.q_rs : p.q_cs;
   const long long q_fast = p.q_cs <= p.q_rs ? p.q_cs : p.q_rs;
 
+  const int Btot = (kShared && p.count_dev) ? (int)*p.count_dev : p.B;
+  const bool resume = shared_mode == 2;   // x0 of the pre-solve launch is in p.x, pass 0 is done
+  int cached_pass = -1;                     // shared-structure modes: which KKT factorization sits in M
+  double sigma_cached = 1.0;
   for (;;) {
     __syncthreads();  // previous QP fully retired (smem reuse) before taking new work
     if (tid == 0) *s_work = (int)atomicAdd(p.work_counter, 1u);
     __syncthreads();
-    const int qp = *s_work;
-    if (qp >= p.B) break;
+    const int qslot = *s_work;
+    if (qslot >= Btot) break;
+    const int qp = (kShared && p.index_list) ? p.index_list[qslot] : qslot;
 #ifdef FCCQP_DEV
     trbuf = (trcount++ == trsel) ? trbase : nullptr;
 #endif
@@ -984,10 +1004,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
       v_lb = p.lb[(size_t)qp * p.lb_bs + t];
       v_ub = p.ub[(size_t)qp * p.ub_bs + t];
       if (!isinf(v_lb) || !isinf(v_ub)) finite_bounds = 1;
-      if (p.warm) {
-        v_x = p.x[(size_t)qp * n + t];
-        v_mux = p.mu_x[(size_t)qp * n + t];
-      }
+      if (p.warm || resume) v_x = p.x[(size_t)qp * n + t];
+      if (p.warm) v_mux = p.mu_x[(size_t)qp * n + t];
     } else if (is_c) {
       v_b = p.beq[(size_t)qp * p.beq_bs + (t - n8)];
     }
@@ -1014,7 +1032,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
     // takes that x-update as the identity: a QP whose pre-solve point already passes the exit test
     // (98 % of the walking log) finishes without the second factorization; the others factor and
     // carry on from iteration 1.  first_update_identity = 0 runs the solve instead.
-    for (int pass = presolve ? 0 : 1; pass < 2; ++pass) {
+    bool defer = false;   // shared_mode 1: this QP needs ADMM iterations, hand it to the second launch
+    for (int pass = (presolve && !resume) ? 0 : 1; pass < 2 && !defer; ++pass) {
       if (pass == 1 && eqc) break;
       if (pass == 1) {
         // ADMM initial slack (fcc_qp.cpp:74-75): x_bar = x, lambda_c_bar = x[lambda_c segment]
@@ -1036,6 +1055,23 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
       if (!factored) {
       factored = true;
       const long long t_f0 = clock64();
+      if (shared_mode != 0 && cached_pass == pass) {
+        // shared structure: the factors (and inv(L)) of an earlier QP of this CTA are still in M; only the
+        // pre-solve right-hand side -b + sigma A' b_eq is new (A from global memory: shared, L2-resident)
+        if (pass == 0) {
+          if (t >= n8 && t < N8) tbuf[t] = is_c ? v_b : 0.0;
+          __syncthreads();
+          if (is_x) {
+            double s0 = 0.0;
+            const double* acol = Ag + (long long)t * p.a_cs;
+#pragma unroll 4
+            for (int k = 0; k < m; ++k) s0 = fma(acol[(long long)k * p.a_rs], tbuf[n8 + k], s0);
+            rhs0 = fma(sigma_cached, s0, -v_b);
+          } else if (is_c) {
+            rhs0 = v_b;
+          }
+        }
+      } else {
 
       // ---------------- assemble the lower tiles of the padded KKT matrix ----------------
       // one warp per tile, lane = (row fr, column pair 2fq): 8 x 64-byte row segments from HBM/L2.
@@ -1114,6 +1150,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
         block_reduce2<true>(trq, fro, red, parity);
         TR(6);
         const double sigma = (trq > 0.0 && fro > 0.0 && isfinite(trq / fro)) ? trq / fro : 1.0;
+        sigma_cached = sigma;
         // rhs_x = -b + sigma A' b_eq (needs A before the factorization overwrites it)
         if (is_x) {
           double s = 0.0;
@@ -1149,9 +1186,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
       factor_tiles<kThreads>(M, dinv, dneg, NB, NB32 FCCQP_TRACE_ARGS);
       FCCQP_PROF(3);
       fact_cycles += (unsigned long long)(clock64() - t_f0);
+      if (shared_mode != 0) {
+        // shared structure: [K^{-1}]_{x,:} as an explicit operator, kept for every later QP of this CTA
+        complete_inverse<kThreads>(M, NB);
+        form_g<kThreads>(M, dinv, NB, NBx, NB);
+        cached_pass = pass;
+      }
       FCCQP_PROF(6);
       TR(20);
-
+      }
       }  // lazy factorization
 
         // ---- K3 right-hand side
@@ -1167,13 +1210,17 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
           acc = v_b;
         }
         TR(30);
+        if (shared_mode != 0) {
+          const double gx = g_apply(M, tbuf, is_row ? acc : 0.0, NB, n8);   // x = [K^{-1}]_{x,:} rhs, cached operator
+          val = is_x ? gx : 0.0;
+        } else {
         if (!full_inverse && pass == 1 && iter >= p.full_inverse_at) {
           // long-running QP: W = inv(L), x_base = [K^{-1} (-b; b_eq)]_x, G = [K^{-1}]_xx (see form_g)
           __syncthreads();
           complete_inverse<kThreads>(M, NB);
           v_xbase = kkt_solve_full(M, dinv, tbuf, ybuf, is_x ? -v_b : (is_c ? v_b : 0.0), NB, N8);
           __syncthreads();
-          form_g<kThreads>(M, dinv, NB, NBx);
+          form_g<kThreads>(M, dinv, NB, NBx, NBx);
           full_inverse = true;
           FCCQP_PROF(4);
         }
@@ -1184,6 +1231,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
           val = is_x ? fma(p.rho, gw, v_xbase) : 0.0;
         } else {
           val = kkt_solve(M, dinv, tbuf, ybuf, acc, NB, NB32, N8 FCCQP_TRACE_ARGS);
+        }
         }
         FCCQP_PROF(7);
         TR(35);
@@ -1236,10 +1284,19 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
           block_reduce2<false>(rx, rc, red, parity);
           res_x = rx; res_c = rc;
           if (conv) { n_iter = iter; break; }
+        } else if (shared_mode == 1) {
+          defer = true;   // iteration 0 (the identity x-update) did not pass the exit test
+          break;
         }
       }
     }
 
+    if (defer) {
+      // park x0 and the index; the ADMM launch redoes iteration 0 from x0 (same arithmetic) and carries on
+      if (is_x) p.x[(size_t)qp * n + t] = xs[t];
+      if (tid == 0) p.pending_list[atomicAdd(p.pending_count, 1u)] = qp;
+      continue;
+    }
     // ---------------- K6: epilogue ----------------
     TR(60);
     __syncthreads();

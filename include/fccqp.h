@@ -134,7 +134,9 @@ typedef struct fccqp_batch_desc {
                               1: warm: x/mu_x/mu_lambda_c are read as the carried state      */
   fccqp_options options;
 
-  /* inputs; *_batch_stride in elements between consecutive QPs (0 = shared by all) */
+  /* inputs; *_batch_stride in elements between consecutive QPs (0 = shared by all).  A cold batch
+   * whose Q and A_eq are BOTH shared (stride 0) is solved with the KKT factorizations cached per
+   * thread block (two launches) -- same results as B separate FCCQP::Solve calls. */
   const double* Q;        int64_t q_batch_stride, q_row_stride, q_col_stride;
   const double* b;        int64_t b_batch_stride;
   const double* A_eq;     int64_t a_batch_stride, a_row_stride, a_col_stride;

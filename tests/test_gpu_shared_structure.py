@@ -1,0 +1,55 @@
+"""Shared-structure batches (the sampling-based-MPC case): one Q and one A_eq for the
+whole batch (batch stride 0), only b, b_eq, friction coefficients vary.  The library then runs two
+launches with the KKT factorizations cached per CTA; results must match the general path (same
+inputs materialised per QP) and the CPU oracle."""
+import numpy as np
+import pytest
+
+from fcc_qp_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+OPTS = dict(max_iter=100, rho=5e-5, eps_fcone=1e-6, eps_bound=1e-6)
+
+
+def shared_batch(shape, B, seed=7):
+    """B QPs that share the structure terms of draw 0 (M, Jacobians, weights) and differ in commands / bias."""
+    t = syn.make_terms(shape, B, seed=shape.seed + seed)
+    rep = lambda a: np.ascontiguousarray(np.broadcast_to(a[:1], a.shape))
+    t.M, t.Jh, t.Jc, t.Jy, t.W = rep(t.M), rep(t.Jh), rep(t.Jc), rep(t.Jy), rep(t.W)
+    return syn.assemble_numpy(t)
+
+
+@pytest.mark.parametrize("name,B", [("quadruped", 3072), ("cassie_like", 3072), ("humanoid", 1536)])
+def test_shared_structure_matches_general_path_and_oracle(name, B):
+    import torch
+    import oracle
+    from fcc_qp_b200.batch import FCCQPBatch, FCCQPOptionsB
+    from fcc_qp_b200 import _native as nat
+    shp = syn.SHAPES[name]
+    qp = shared_batch(shp, B)
+    assert np.array_equal(qp.Q[0], qp.Q[-1]) and np.array_equal(qp.A_eq[0], qp.A_eq[-1])
+    dev = torch.device("cuda:0")
+    vec = [torch.as_tensor(a, device=dev) for a in (qp.b, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)]
+    Q1, A1 = torch.as_tensor(qp.Q[:1], device=dev), torch.as_tensor(qp.A_eq[:1], device=dev)
+
+    def run(Q, A):
+        s = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start)
+        s.set_options(FCCQPOptionsB(**OPTS))
+        n0 = nat.lib().fccqp_kernel_launch_count()
+        s.Solve(Q, vec[0], A, vec[1], vec[2], vec[3], vec[4])
+        sol = s.GetSolution()
+        torch.cuda.synchronize()
+        return (sol.z.cpu().numpy(), sol.details.n_iter.cpu().numpy(), sol.details.solve_status.cpu().numpy(),
+                nat.lib().fccqp_kernel_launch_count() - n0)
+
+    zs, its, sts, launches_shared = run(Q1.expand(B, qp.n, qp.n), A1.expand(B, qp.m, qp.n))       # batch stride 0
+    zg, itg, stg, launches_general = run(torch.as_tensor(qp.Q, device=dev), torch.as_tensor(qp.A_eq, device=dev))
+    assert launches_shared == 2 and launches_general == 1           # the shared path really ran
+    rel = lambda z, ref: (np.abs(z - ref).max(1) / np.maximum(1.0, np.abs(ref).max(1))).max()
+    assert rel(zs, zg) <= 1e-7
+    assert (its != itg).mean() <= 0.01
+    sub = np.arange(0, B, 8)
+    ref = oracle.Oracle("port").solve_batch(qp.take(sub), warm_mode=0, nthreads=8, **OPTS)
+    assert rel(zs[sub], ref["z"]) <= 1e-6
+    assert (its[sub] != ref["n_iter"]).mean() <= 0.02
+    assert np.array_equal(sts[sub][its[sub] == ref["n_iter"]], ref["status"][its[sub] == ref["n_iter"]])

@@ -30,3 +30,23 @@ def run(name, qp, B):
 run("cassie_walking_log", load_walking_log(), B)
 for nm, gen in (("humanoid", 2048), ("quadruped", 2048), ("multicontact", 1024)):
     run(nm, syn.make_batch(syn.SHAPES[nm], gen), B if nm != "multicontact" else B // 4)
+# shared-structure batches (one Q / A_eq for the whole batch): the two-launch cached-factor path
+for nm in ("quadruped", "cassie_like"):
+    shp = syn.SHAPES[nm]
+    t = syn.make_terms(shp, 4096, seed=shp.seed + 7)
+    rep = lambda a: np.ascontiguousarray(np.broadcast_to(a[:1], a.shape))
+    t.M, t.Jh, t.Jc, t.Jy, t.W = rep(t.M), rep(t.Jh), rep(t.Jc), rep(t.Jy), rep(t.W)
+    q = syn.assemble_numpy(t).tile(B)
+    vec = [torch.as_tensor(a, device=dev) for a in (q.b, q.b_eq, q.friction_coeffs, q.lb, q.ub)]
+    Q1, A1 = torch.as_tensor(q.Q[:1], device=dev), torch.as_tensor(q.A_eq[:1], device=dev)
+    s = FCCQPBatch(q.n, q.m, q.nc, q.lambda_c_start); s.set_options(FCCQPOptionsB(100, 5e-5, 1e-6, 1e-6))
+    res = {"shape": nm + "_shared_structure", "n": q.n, "m": q.m, "batch": B}
+    for label, Qx, Ax in (("shared", Q1.expand(B, q.n, q.n), A1.expand(B, q.m, q.n)),
+                          ("general", torch.as_tensor(q.Q, device=dev), torch.as_tensor(q.A_eq, device=dev))):
+        best = 1e9
+        for _ in range(3):
+            s.Solve(Qx, vec[0], Ax, vec[1], vec[2], vec[3], vec[4]); torch.cuda.synchronize()
+            best = min(best, s.GetSolution().details.device_time)
+        it = s.GetSolution().details.n_iter.cpu().numpy()
+        res[label] = {"ms": 1e3 * best, "M_qps_per_s": B / best / 1e6, "iterating_fraction": float((it > 0).mean())}
+    print(json.dumps(res), flush=True)
