@@ -110,6 +110,9 @@ class FCCQPBatch:
 
         Q ``[B,n,n]``, b ``[B,n]``, A_eq ``[B,m,n]``, b_eq ``[B,m]``; friction_coeffs
         ``[B,nc/3]`` or ``[nc/3]``; lb/ub ``[B,n]`` or ``[n]`` (shared by all QPs).
+        Q ``[n,n]`` together with A_eq ``[m,n]`` declares a shared-structure batch (one cost
+        matrix and one constraint matrix for all B right-hand sides): the KKT factorizations
+        are then cached on the device instead of redone per QP.
         """
         if _is_torch(Q):
             self._solve_torch(Q, b, A_eq, b_eq, friction_coeffs, lb, ub)
@@ -134,6 +137,8 @@ class FCCQPBatch:
     def _check_shapes(self, shp, B):
         n, m, nc = self.n, self.m, self.nc
         Q, b, A, beq, mu, lb, ub = shp
+        if tuple(Q) == (n, n) and tuple(A) == (m, n):
+            Q, A = (B, n, n), (B, m, n)       # shared structure
         if tuple(Q) != (B, n, n) or tuple(b) != (B, n) or tuple(A) != (B, m, n) or tuple(beq) != (B, m):
             raise ValueError(f"expected Q[{B},{n},{n}], b[{B},{n}], A_eq[{B},{m},{n}], b_eq[{B},{m}]; got "
                              f"{tuple(Q)}, {tuple(b)}, {tuple(A)}, {tuple(beq)}")
@@ -150,10 +155,12 @@ class FCCQPBatch:
         import time
         f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
         Q, b, A_eq, b_eq, mu, lb, ub = map(f, (Q, b, A_eq, b_eq, mu, lb, ub))
-        if Q.ndim != 3:
-            raise ValueError("Q must be [B,n,n]")
-        B = Q.shape[0]
-        A_eq = A_eq.reshape(B, self.m, self.n) if A_eq.size == B * self.m * self.n else A_eq
+        if Q.ndim not in (2, 3):
+            raise ValueError("Q must be [B,n,n] (or [n,n] with A_eq [m,n] for a shared-structure batch)")
+        shared = Q.ndim == 2
+        B = b.shape[0] if shared else Q.shape[0]
+        if not shared:
+            A_eq = A_eq.reshape(B, self.m, self.n) if A_eq.size == B * self.m * self.n else A_eq
         self._check_shapes([a.shape for a in (Q, b, A_eq, b_eq, mu, lb, ub)], B)
         n, m, nc = self.n, self.m, self.nc
         warm = self.warm_start
@@ -179,9 +186,9 @@ class FCCQPBatch:
         d = self._desc(B, nat.MEM_HOST)
         d.warm_start = int(warm)
         p = lambda a: a.ctypes.data
-        d.Q, d.q_batch_stride, d.q_row_stride, d.q_col_stride = p(Q), n * n, n, 1
+        d.Q, d.q_batch_stride, d.q_row_stride, d.q_col_stride = p(Q), (0 if shared else n * n), n, 1
         d.b, d.b_batch_stride = p(b), n
-        d.A_eq, d.a_batch_stride, d.a_row_stride, d.a_col_stride = p(A_eq), m * n, n, 1
+        d.A_eq, d.a_batch_stride, d.a_row_stride, d.a_col_stride = p(A_eq), (0 if shared else m * n), n, 1
         d.b_eq, d.beq_batch_stride = p(b_eq), m
         d.friction_coeffs, d.mu_batch_stride = p(mu), (nc // 3 if mu.ndim == 2 else 0)
         d.lb, d.lb_batch_stride = p(lb), (n if lb.ndim == 2 else 0)
@@ -211,6 +218,9 @@ class FCCQPBatch:
         t = lambda a: a if (_is_torch(a) and a.dtype == torch.float64 and a.device == dev) else \
             torch.as_tensor(a, dtype=torch.float64, device=dev)
         Q, b, A_eq, b_eq, mu, lb, ub = map(t, (Q, b, A_eq, b_eq, mu, lb, ub))
+        if Q.dim() == 2 and A_eq.dim() == 2:      # shared structure: one Q / A_eq, batch stride 0
+            Q = Q.unsqueeze(0).expand(b.shape[0], *Q.shape)
+            A_eq = A_eq.unsqueeze(0).expand(b.shape[0], *A_eq.shape)
         B = Q.shape[0]
         self._check_shapes([a.shape for a in (Q, b, A_eq, b_eq, mu, lb, ub)], B)
         n, m, nc = self.n, self.m, self.nc

@@ -1059,13 +1059,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
         // shared structure: the factors (and inv(L)) of an earlier QP of this CTA are still in M; only the
         // pre-solve right-hand side -b + sigma A' b_eq is new (A from global memory: shared, L2-resident)
         if (pass == 0) {
-          if (t >= n8 && t < N8) tbuf[t] = is_c ? v_b : 0.0;
+          // (b_eq staged in ybuf: the operator product below refills tbuf while slower threads still read)
+          if (t >= n8 && t < N8) ybuf[t] = is_c ? v_b : 0.0;
           __syncthreads();
           if (is_x) {
             double s0 = 0.0;
             const double* acol = Ag + (long long)t * p.a_cs;
 #pragma unroll 4
-            for (int k = 0; k < m; ++k) s0 = fma(acol[(long long)k * p.a_rs], tbuf[n8 + k], s0);
+            for (int k = 0; k < m; ++k) s0 = fma(acol[(long long)k * p.a_rs], ybuf[n8 + k], s0);
             rhs0 = fma(sigma_cached, s0, -v_b);
           } else if (is_c) {
             rhs0 = v_b;

@@ -53,3 +53,22 @@ def test_shared_structure_matches_general_path_and_oracle(name, B):
     assert rel(zs[sub], ref["z"]) <= 1e-6
     assert (its[sub] != ref["n_iter"]).mean() <= 0.02
     assert np.array_equal(sts[sub][its[sub] == ref["n_iter"]], ref["status"][its[sub] == ref["n_iter"]])
+
+
+def test_shared_structure_host_path_and_2d_arguments():
+    """Q [n,n] + A_eq [m,n] (numpy, host memory): staged once, stride 0 through the C ABI, chunked launches."""
+    from fcc_qp_b200.batch import FCCQPBatch, FCCQPOptionsB
+    shp = syn.QUADRUPED
+    B = 8192
+    qp = shared_batch(shp, B)
+    s = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start); s.set_options(FCCQPOptionsB(**OPTS))
+    s.Solve(qp.Q[0], qp.b, qp.A_eq[0], qp.b_eq, qp.friction_coeffs, qp.lb[0], qp.ub[0])
+    a = s.GetSolution()
+    g = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start); g.set_options(FCCQPOptionsB(**OPTS))
+    g.Solve(qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)
+    r = g.GetSolution()
+    err = (np.abs(a.z - r.z).max(1) / np.maximum(1.0, np.abs(r.z).max(1))).max()
+    assert err <= 1e-7
+    assert (a.details.n_iter != r.details.n_iter).mean() <= 0.01
+    assert np.array_equal(a.details.solve_status[a.details.n_iter == r.details.n_iter],
+                          r.details.solve_status[a.details.n_iter == r.details.n_iter])

@@ -14,3 +14,13 @@ it = s.GetSolution().details.n_iter
 s.set_warm_start(True)
 s.Solve(qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)
 print(shape, "QPs", qp.batch, "cold iterations", np.unique(it, return_counts=True), "warm", np.unique(s.GetSolution().details.n_iter, return_counts=True))
+# shared-structure batch (two-launch path with cached factorizations)
+if shape != "walking":
+    shp = syn.SHAPES[shape]
+    t = syn.make_terms(shp, 1300 if shp.n + shp.m > 128 else 2500, seed=shp.seed + 7)
+    rep = lambda a: np.ascontiguousarray(np.broadcast_to(a[:1], a.shape))
+    t.M, t.Jh, t.Jc, t.Jy, t.W = rep(t.M), rep(t.Jh), rep(t.Jc), rep(t.Jy), rep(t.W)
+    q = syn.assemble_numpy(t)
+    s2 = FCCQPBatch(q.n, q.m, q.nc, q.lambda_c_start); s2.set_options(FCCQPOptionsB(100, 5e-5, 1e-6, 1e-6))
+    s2.Solve(q.Q[0], q.b, q.A_eq[0], q.b_eq, q.friction_coeffs, q.lb[0], q.ub[0])
+    print("shared-structure", shape, "QPs", q.batch, np.unique(s2.GetSolution().details.n_iter, return_counts=True)[1][:3])
