@@ -66,9 +66,25 @@ def build_pybind(force=False, verbose=False):
     return tgt
 
 
+def build_cpp_dropin(force=False, verbose=False, eigen="/root/reference/eigen"):
+    """tests/cpp/dropin_main: a caller written against the reference's Eigen-typed C++ surface, compiled
+    against include/fcc_qp.hpp.  Needs Eigen headers (the reference's vendored copy; not on the GPU box,
+    where the prebuilt binary is used).  Returns the binary path or None."""
+    src = os.path.join(ROOT, "tests", "cpp", "dropin_main.cpp")
+    tgt = os.path.join(ROOT, "tests", "cpp", "dropin_main")
+    if not os.path.isdir(eigen) or not os.path.exists(src):
+        return tgt if os.path.exists(tgt) else None
+    if force or _stale(tgt, [src, os.path.join(ROOT, "include", "fcc_qp.hpp"), os.path.join(ROOT, "include", "fccqp.h"), LIB]):
+        cxx = os.environ.get("CXX", "g++")
+        _run([cxx, "-std=c++17", "-O1", "-w", "-I", eigen, "-I", os.path.join(ROOT, "include"), src,
+              "-L", HERE, "-lfccqp_b200", "-Wl,-rpath,$ORIGIN/../../fcc_qp_b200", "-o", tgt], verbose)
+    return tgt
+
+
 def build_all(force=False, verbose=False):
     build_cuda(force, verbose)
     build_pybind(force, verbose)
+    build_cpp_dropin(force, verbose)
 
 
 if __name__ == "__main__":

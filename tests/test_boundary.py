@@ -150,3 +150,15 @@ def test_roofline_arithmetic():
     # Cassie 48,816 B in + 520 B out
     assert bench.algorithmic_bytes_per_qp(60, 38, 12) == 48816 + 520
     assert abs(bench.algorithmic_flops_per_qp(60, 38, 1, cold=False) - (98 ** 3 / 3 + 2 * 98 ** 2)) < 1e-6
+
+
+def test_cpp_dropin_compiles_against_eigen_surface():
+    """A C++ caller of the reference's Eigen-typed FCCQP surface (src/fcc_qp.hpp:73-121) compiles and
+    links against include/fcc_qp.hpp + libfccqp_b200.so unchanged (tests/cpp/dropin_main.cpp).
+    Needs Eigen headers: the reference's vendored copy, present in the build container only."""
+    import os
+    from fcc_qp_b200 import build
+    if not os.path.isdir("/root/reference/eigen"):
+        pytest.skip("no Eigen headers here")
+    tgt = build.build_cpp_dropin(force=True)
+    assert tgt and os.path.exists(tgt)

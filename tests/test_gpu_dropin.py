@@ -79,3 +79,16 @@ def test_warm_state_roundtrip(walking_log):
         s.set_warm_start(True)
         s.Solve(q['Q'], q['b'], q['A_eq'], q['b_eq'], q['friction_coeffs'], q['lb'], q['ub'])
     assert np.array_equal(a.GetSolution().z, b.GetSolution().z)
+
+
+def test_cpp_eigen_caller():
+    """tests/cpp/dropin_main (built where Eigen headers exist, shipped with the repo snapshot): equality-only
+    closed form, cone-projection KAT, warm restart, Eigen::Ref blocks with an outer stride -- through
+    include/fcc_qp.hpp and the C ABI."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(__file__), "cpp", "dropin_main")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/dropin_main not built (needs Eigen headers at build time)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "dropin_main: ok" in r.stdout
