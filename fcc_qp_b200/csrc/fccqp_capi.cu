@@ -313,6 +313,7 @@ struct fccqp_solver {
   double* h_out = nullptr;   // [n + 4] z + scalars
   int* h_iout = nullptr;
   unsigned long long* h_cycles = nullptr;
+  unsigned long long prev_fact_cycles = 0;   // the device counter accumulates across solves
   size_t in_doubles = 0;
   fccqp_details details{};
 };
@@ -364,21 +365,22 @@ int fccqp_create(int n, int m, int nc, int lcs, int device, fccqp_handle* out) {
   cudaError_t e;
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking))) return cleanup_fail(e, "cudaStreamCreate");
   if ((e = cudaMalloc(&h->d_in, (h->in_doubles + 2) * sizeof(double)))) return cleanup_fail(e, "cudaMalloc");
-  if ((e = cudaMalloc(&h->d_x, (size_t)(n + 1) * sizeof(double)))) return cleanup_fail(e, "cudaMalloc");
+  // outputs packed in one device buffer so that ONE D2H copy brings everything back:
+  //   [x (n doubles) | res_b res_f bviol fviol | cycles (2 x u64) | n_iter status (2 x i32)]
+  if ((e = cudaMalloc(&h->d_x, (size_t)(n + 8) * sizeof(double)))) return cleanup_fail(e, "cudaMalloc");
+  h->d_out = h->d_x + n;
+  h->d_cycles = reinterpret_cast<unsigned long long*>(h->d_x + n + 4);
+  h->d_iout = reinterpret_cast<int*>(h->d_x + n + 6);
   if ((e = cudaMalloc(&h->d_mux, (size_t)(n + 1) * sizeof(double)))) return cleanup_fail(e, "cudaMalloc");
   if ((e = cudaMalloc(&h->d_muc, (size_t)(nc + 1) * sizeof(double)))) return cleanup_fail(e, "cudaMalloc");
-  if ((e = cudaMalloc(&h->d_out, 4 * sizeof(double)))) return cleanup_fail(e, "cudaMalloc");
-  if ((e = cudaMalloc(&h->d_iout, 2 * sizeof(int)))) return cleanup_fail(e, "cudaMalloc");
-  if ((e = cudaMalloc(&h->d_cycles, 2 * sizeof(unsigned long long)))) return cleanup_fail(e, "cudaMalloc");
   if ((e = cudaMallocHost(&h->h_in, (h->in_doubles + 2) * sizeof(double)))) return cleanup_fail(e, "cudaMallocHost");
-  if ((e = cudaMallocHost(&h->h_out, (size_t)(n + 4) * sizeof(double)))) return cleanup_fail(e, "cudaMallocHost");
-  if ((e = cudaMallocHost(&h->h_iout, 2 * sizeof(int)))) return cleanup_fail(e, "cudaMallocHost");
-  if ((e = cudaMallocHost(&h->h_cycles, 2 * sizeof(unsigned long long)))) return cleanup_fail(e, "cudaMallocHost");
-  if ((e = cudaMemset(h->d_x, 0, (size_t)(n + 1) * sizeof(double)))) return cleanup_fail(e, "cudaMemset");
+  if ((e = cudaMallocHost(&h->h_out, (size_t)(n + 8) * sizeof(double)))) return cleanup_fail(e, "cudaMallocHost");
+  h->h_cycles = reinterpret_cast<unsigned long long*>(h->h_out + n + 4);
+  h->h_iout = reinterpret_cast<int*>(h->h_out + n + 6);
+  if ((e = cudaMemset(h->d_x, 0, (size_t)(n + 8) * sizeof(double)))) return cleanup_fail(e, "cudaMemset");
   if ((e = cudaMemset(h->d_mux, 0, (size_t)(n + 1) * sizeof(double)))) return cleanup_fail(e, "cudaMemset");
   if ((e = cudaMemset(h->d_muc, 0, (size_t)(nc + 1) * sizeof(double)))) return cleanup_fail(e, "cudaMemset");
-  memset(h->h_out, 0, (size_t)(n + 4) * sizeof(double));
-  h->h_iout[0] = h->h_iout[1] = 0;
+  memset(h->h_out, 0, (size_t)(n + 8) * sizeof(double));
   *out = h;
   return FCCQP_OK;
 }
@@ -388,8 +390,7 @@ int fccqp_destroy(fccqp_handle h) {
   cudaSetDevice(h->device);
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   cudaFree(h->d_in); cudaFree(h->d_x); cudaFree(h->d_mux); cudaFree(h->d_muc);
-  cudaFree(h->d_out); cudaFree(h->d_iout); cudaFree(h->d_cycles);
-  cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_iout); cudaFreeHost(h->h_cycles);
+  cudaFreeHost(h->h_in); cudaFreeHost(h->h_out);
   delete h;
   return FCCQP_OK;
 }
@@ -464,7 +465,6 @@ int fccqp_solve(fccqp_handle h, const double* Q, ptrdiff_t q_rs, ptrdiff_t q_cs,
   memcpy(slb, lb, sizeof(double) * n);
   memcpy(sub, ub, sizeof(double) * n);
   CUDA_TRY(cudaMemcpyAsync(h->d_in, h->h_in, h->in_doubles * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(cudaMemsetAsync(h->d_cycles, 0, 2 * sizeof(unsigned long long), h->stream));
 
   fccqp::SolveParams p{};
   p.B = 1; p.n = n; p.m = m; p.nc = nc; p.lcs = h->lcs;
@@ -484,10 +484,7 @@ int fccqp_solve(fccqp_handle h, const double* Q, ptrdiff_t q_rs, ptrdiff_t q_cs,
   p.cycles = h->d_cycles;
   int rc = launch_solve(*h->ctx, p, h->stream);
   if (rc) return rc;
-  CUDA_TRY(cudaMemcpyAsync(h->h_out, h->d_x, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaMemcpyAsync(h->h_out + n, h->d_out, sizeof(double) * 4, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaMemcpyAsync(h->h_iout, h->d_iout, sizeof(int) * 2, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaMemcpyAsync(h->h_cycles, h->d_cycles, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->h_out, h->d_x, sizeof(double) * (n + 8), cudaMemcpyDeviceToHost, h->stream));   // packed outputs
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   h->has_state = true;
   h->details.n_iter = h->h_iout[0];
@@ -496,7 +493,9 @@ int fccqp_solve(fccqp_handle h, const double* Q, ptrdiff_t q_rs, ptrdiff_t q_cs,
   h->details.admm_residual_friction_cone = h->h_out[n + 1];
   h->details.bounds_viol = h->h_out[n + 2];
   h->details.friction_cone_viol = h->h_out[n + 3];
-  h->details.factorization_time = h->ctx->clock_khz > 0 ? (double)h->h_cycles[0] / (1e3 * h->ctx->clock_khz) : 0.0;
+  h->details.factorization_time =
+      h->ctx->clock_khz > 0 ? (double)(h->h_cycles[0] - h->prev_fact_cycles) / (1e3 * h->ctx->clock_khz) : 0.0;
+  h->prev_fact_cycles = h->h_cycles[0];
   h->details.solve_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return FCCQP_OK;
 }
