@@ -180,7 +180,22 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream) {
   // its KKT factorization cached per CTA (SolveParams::shared_mode).  Worth it once every CTA sees
   // several QPs; FCCQP_NO_SHARED=1 forces the general path (tests compare the two).
   static const bool no_shared = getenv("FCCQP_NO_SHARED") != nullptr;
-  if (!no_shared && !p.warm && p.q_bs == 0 && (p.m == 0 || p.a_bs == 0) && p.B >= 4 * ctas_per_sm * ctx.num_sms) {
+  const bool shared_structure = !no_shared && p.q_bs == 0 && (p.m == 0 || p.a_bs == 0) && p.B >= 4 * ctas_per_sm * ctx.num_sms;
+  if (shared_structure && p.warm) {
+    // warm shared-structure batch (an MPC loop re-solving around one linearisation with carried duals):
+    // no pre-solve, so ONE launch of the ADMM mode over all QPs with the rho-KKT operator cached per CTA
+    fccqp::SolveParams b = p;
+    b.shared_mode = 2;
+    fn_shared<<<grid, threads, smem, stream>>>(b);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    {
+      std::lock_guard<std::mutex> lk(g_info_mu);
+      g_last_launch = {grid, threads, (int)smem, ctas_per_sm};
+    }
+    return FCCQP_OK;
+  }
+  if (shared_structure) {
     unsigned int* scratch = nullptr;   // [0] = pending count, [1..B] = pending QP indices
     CUDA_TRY(cudaMallocAsync(&scratch, ((size_t)p.B + 1) * sizeof(unsigned int), stream));
     CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(unsigned int), stream));

@@ -72,3 +72,33 @@ def test_shared_structure_host_path_and_2d_arguments():
     assert (a.details.n_iter != r.details.n_iter).mean() <= 0.01
     assert np.array_equal(a.details.solve_status[a.details.n_iter == r.details.n_iter],
                           r.details.solve_status[a.details.n_iter == r.details.n_iter])
+
+
+def test_shared_structure_warm_sequence():
+    """Warm-started re-solves of a shared-structure batch (carried x, mu_x, mu_lambda_c; b and b_eq take a
+    random-walk step per tick): the cached-operator single launch against the general warm path."""
+    import torch
+    from fcc_qp_b200.batch import FCCQPBatch, FCCQPOptionsB
+    shp = syn.QUADRUPED
+    B, T = 3072, 3
+    qp = shared_batch(shp, B)
+    rng = np.random.default_rng(5)
+    dev = torch.device("cuda:0")
+    mk = lambda: FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start)
+    a, g = mk(), mk()
+    for s in (a, g):
+        s.set_options(FCCQPOptionsB(**OPTS))
+    Q1, A1 = torch.as_tensor(qp.Q[0], device=dev), torch.as_tensor(qp.A_eq[0], device=dev)
+    Qf, Af = torch.as_tensor(qp.Q, device=dev), torch.as_tensor(qp.A_eq, device=dev)
+    for t in range(T):
+        vec = [torch.as_tensor(x, device=dev) for x in (qp.b, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)]
+        for s, Q, A in ((a, Q1, A1), (g, Qf, Af)):
+            s.set_warm_start(t > 0)
+            s.Solve(Q, vec[0], A, vec[1], vec[2], vec[3], vec[4])
+        za, zg = a.GetSolution().z.cpu().numpy(), g.GetSolution().z.cpu().numpy()
+        ia, ig = a.GetSolution().details.n_iter.cpu().numpy(), g.GetSolution().details.n_iter.cpu().numpy()
+        err = (np.abs(za - zg).max(1) / np.maximum(1.0, np.abs(zg).max(1)))
+        same = ia == ig
+        assert (~same).mean() <= 0.02, t
+        assert err[same].max() <= 1e-6, t      # lanes whose iteration counts agree took the same path
+        qp = syn.random_walk(qp, rng)
