@@ -432,14 +432,19 @@ __device__ __forceinline__ void ata_chunk(double* __restrict__ M, int NBx, int N
   double2 sa[T], sb[T];
 #pragma unroll
   for (int t = 0; t < T; ++t) { sa[t] = make_double2(0.0, 0.0); sb[t] = make_double2(0.0, 0.0); }
+  // X'Y products take both operands as "fragT" (element (2q+s, l/4), s = 0/1: two 8-byte loads).  Lanes
+  // with odd q take s = 1 first: the two loads of a warp then cover all shared-memory banks instead
+  // of half of them (2 wavefronts instead of 4), and each DMMA still contracts every k exactly once
+  // (k = 2q+s with the same s rule for both operands).
+  const int s0 = (fragT >> 4 & 1) << 3, s1 = 8 - s0;   // fragT = (2q) * 8 + ...: bit 4 is q & 1
   const double* ai = M + tile_off(NBx, I) + fragT;
   const double* aj = M + tile_off(NBx, J0) + fragT;
 #pragma unroll 1
   for (int kb = NBx; kb < NB; ++kb) {
-    const double a0 = ai[0], a1 = ai[8];
+    const double a0 = ai[s0], a1 = ai[s1];
     double b0[T], b1[T];
 #pragma unroll
-    for (int t = 0; t < T; ++t) { b0[t] = aj[64 * t]; b1[t] = aj[64 * t + 8]; }
+    for (int t = 0; t < T; ++t) { b0[t] = aj[64 * t + s0]; b1[t] = aj[64 * t + s1]; }
 #pragma unroll
     for (int t = 0; t < T; ++t) {
       dmma(sa[t].x, sa[t].y, a0, b0[t]);
