@@ -58,13 +58,19 @@ def _is_torch(a) -> bool:
 
 class FCCQPBatch:
     def __init__(self, num_vars: int, num_equality_constraints: int, nc: int, lambda_c_start: int,
-                 device: int = 0):
+                 device: int = 0, precision: str = "fp64"):
         if nc % 3 != 0:
             raise ValueError("nc must be a multiple of 3 (src/fcc_qp.cpp:32)")
         if lambda_c_start < 0 or lambda_c_start + nc > num_vars:
             raise ValueError("lambda_c_start + nc must be <= num_vars (src/fcc_qp.cpp:33)")
         self.n, self.m, self.nc, self.lcs = int(num_vars), int(num_equality_constraints), int(nc), int(lambda_c_start)
         self.device = int(device)
+        # "fp64": the reference's arithmetic and data.  "fp32_data": Q, b, A_eq, b_eq, friction_coeffs, lb, ub
+        # travel and are stored as float32 (half the PCIe / HBM bytes), arithmetic, state and outputs stay
+        # FP64 (FCCQP_PRECISION_FP32_DATA in include/fccqp.h; stated bound 2e-3 relative on z).
+        if precision not in ("fp64", "fp32_data"):
+            raise ValueError("precision must be 'fp64' or 'fp32_data'")
+        self.precision = precision
         self.options = FCCQPOptionsB()
         self.warm_start = False
         self.time_kernel = True
@@ -129,7 +135,7 @@ class FCCQPBatch:
         d = nat.BatchDesc()
         d.abi_version = nat.ABI_VERSION
         d.batch, d.n, d.m, d.nc, d.lambda_c_start = B, self.n, self.m, self.nc, self.lcs
-        d.device, d.memory_space, d.precision = self.device, mem, 0
+        d.device, d.memory_space, d.precision = self.device, mem, (1 if self.precision == "fp32_data" else 0)
         o = self.options
         d.options = nat.Options(int(o.max_iter), 0, float(o.rho), float(o.eps_fcone), float(o.eps_bound))
         return d
@@ -153,7 +159,8 @@ class FCCQPBatch:
 
     def _solve_numpy(self, Q, b, A_eq, b_eq, mu, lb, ub):
         import time
-        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        in_dtype = np.float32 if self.precision == "fp32_data" else np.float64
+        f = lambda a: np.ascontiguousarray(a, dtype=in_dtype)
         Q, b, A_eq, b_eq, mu, lb, ub = map(f, (Q, b, A_eq, b_eq, mu, lb, ub))
         if Q.ndim not in (2, 3):
             raise ValueError("Q must be [B,n,n] (or [n,n] with A_eq [m,n] for a shared-structure batch)")
@@ -215,8 +222,9 @@ class FCCQPBatch:
         if dev.type != "cuda":
             raise ValueError("torch inputs must be CUDA tensors (no CPU solve path); pass numpy arrays for host data")
         self.device = dev.index if dev.index is not None else torch.cuda.current_device()
-        t = lambda a: a if (_is_torch(a) and a.dtype == torch.float64 and a.device == dev) else \
-            torch.as_tensor(a, dtype=torch.float64, device=dev)
+        in_dtype = torch.float32 if self.precision == "fp32_data" else torch.float64
+        t = lambda a: a if (_is_torch(a) and a.dtype == in_dtype and a.device == dev) else \
+            torch.as_tensor(a, dtype=in_dtype, device=dev)
         Q, b, A_eq, b_eq, mu, lb, ub = map(t, (Q, b, A_eq, b_eq, mu, lb, ub))
         if Q.dim() == 2 and A_eq.dim() == 2:      # shared structure: one Q / A_eq, batch stride 0
             Q = Q.unsqueeze(0).expand(b.shape[0], *Q.shape)

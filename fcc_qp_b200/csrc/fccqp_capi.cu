@@ -114,7 +114,7 @@ using KernelFn = void (*)(const fccqp::SolveParams);
 
 // Chooses the template instance (threads >= n + m; CTAs/SM hint from the packed-matrix footprint).
 int pick_kernel(const DeviceCtx& ctx, int n, int m, int nc, KernelFn* fn, int* threads, size_t* smem,
-                KernelFn* fn_shared = nullptr) {
+                KernelFn* fn_shared = nullptr, KernelFn* fn_f32 = nullptr) {
   const int N = n + m;
   if (N < 1) return fail(FCCQP_E_INVALID, "n + m must be >= 1");
   fccqp::Layout l(n, m, nc);
@@ -126,23 +126,27 @@ int pick_kernel(const DeviceCtx& ctx, int n, int m, int nc, KernelFn* fn, int* t
   // one thread per padded KKT row; 4 CTAs/SM for the <= 128-row shapes (Cassie, quadruped)
   if (l.N8 <= 128) {
     *threads = 128;
-    *fn = (KernelFn)fccqp::fccqp_solve_kernel<128, 4, false>;
-    if (fn_shared) *fn_shared = (KernelFn)fccqp::fccqp_solve_kernel<128, 4, true>;
+    *fn = (KernelFn)fccqp::fccqp_solve_kernel<128, 4, false, false>;
+    if (fn_shared) *fn_shared = (KernelFn)fccqp::fccqp_solve_kernel<128, 4, true, false>;
+    if (fn_f32) *fn_f32 = (KernelFn)fccqp::fccqp_solve_kernel<128, 4, false, true>;
   } else {
     *threads = 256;
-    *fn = (KernelFn)fccqp::fccqp_solve_kernel<256, 2, false>;
-    if (fn_shared) *fn_shared = (KernelFn)fccqp::fccqp_solve_kernel<256, 2, true>;
+    *fn = (KernelFn)fccqp::fccqp_solve_kernel<256, 2, false, false>;
+    if (fn_shared) *fn_shared = (KernelFn)fccqp::fccqp_solve_kernel<256, 2, true, false>;
+    if (fn_f32) *fn_f32 = (KernelFn)fccqp::fccqp_solve_kernel<256, 2, false, true>;
   }
   return FCCQP_OK;
 }
 
 // Launches the fused solve on `stream` for device-resident data described by p
 // (work_counter / gscratch are filled in here).
-int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream) {
+int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool in_f32 = false) {
   if (p.B == 0) return FCCQP_OK;
-  KernelFn fn, fn_shared; int threads; size_t smem;
-  int rc = pick_kernel(ctx, p.n, p.m, p.nc, &fn, &threads, &smem, &fn_shared);
+  KernelFn fn, fn_shared, fn_f32; int threads; size_t smem;
+  int rc = pick_kernel(ctx, p.n, p.m, p.nc, &fn, &threads, &smem, &fn_shared, &fn_f32);
   if (rc) return rc;
+  const bool f32 = in_f32;
+  if (f32) fn = fn_f32;   // float32 problem data: same launch geometry, widening stage-in
   p.lay = fccqp::Layout(p.n, p.m, p.nc);
   // developer switch: FCCQP_FIRST_UPDATE_IDENTITY=0 solves the (mathematically redundant) first x-update of cold QPs
   static const int fui = getenv("FCCQP_FIRST_UPDATE_IDENTITY") ? atoi(getenv("FCCQP_FIRST_UPDATE_IDENTITY")) : 1;
@@ -159,7 +163,7 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream) {
     if (it == ctx.occupancy.end()) {
       // the attribute is per kernel, the smem size per (n, m, nc): raise it to the device maximum once
       CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx.max_smem_optin));
-      CUDA_TRY(cudaFuncSetAttribute(fn_shared, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx.max_smem_optin));
+      if (!f32) CUDA_TRY(cudaFuncSetAttribute(fn_shared, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx.max_smem_optin));
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, fn, threads, smem));
       if (ctas_per_sm < 1) return fail(FCCQP_E_UNSUPPORTED, "kernel does not fit on an SM (smem %zu B)", smem);
       ctx.occupancy[key] = ctas_per_sm;
@@ -180,7 +184,7 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream) {
   // its KKT factorization cached per CTA (SolveParams::shared_mode).  Worth it once every CTA sees
   // several QPs; FCCQP_NO_SHARED=1 forces the general path (tests compare the two).
   static const bool no_shared = getenv("FCCQP_NO_SHARED") != nullptr;
-  const bool shared_structure = !no_shared && p.q_bs == 0 && (p.m == 0 || p.a_bs == 0) && p.B >= 4 * ctas_per_sm * ctx.num_sms;
+  const bool shared_structure = !no_shared && !f32 && p.q_bs == 0 && (p.m == 0 || p.a_bs == 0) && p.B >= 4 * ctas_per_sm * ctx.num_sms;
   if (shared_structure && p.warm) {
     // warm shared-structure batch (an MPC loop re-solving around one linearisation with carried duals):
     // no pre-solve, so ONE launch of the ADMM mode over all QPs with the rho-KKT operator cached per CTA
@@ -560,7 +564,8 @@ static int validate_desc(const fccqp_batch_desc* d) {
   if (rc) return rc;
   rc = check_options(d->options);
   if (rc) return rc;
-  if (d->precision != FCCQP_PRECISION_FP64) return fail(FCCQP_E_UNSUPPORTED, "only FCCQP_PRECISION_FP64 is implemented");
+  if (d->precision != FCCQP_PRECISION_FP64 && d->precision != FCCQP_PRECISION_FP32_DATA)
+    return fail(FCCQP_E_UNSUPPORTED, "precision must be FCCQP_PRECISION_FP64 or FCCQP_PRECISION_FP32_DATA");
   if (d->memory_space != FCCQP_MEM_HOST && d->memory_space != FCCQP_MEM_DEVICE)
     return fail(FCCQP_E_INVALID, "bad memory_space");
   if (d->batch == 0) return FCCQP_OK;
@@ -598,7 +603,7 @@ int fccqp_batch_solve(const fccqp_batch_desc* desc) {
     p.res_b = d.res_bounds; p.res_f = d.res_fcone; p.bviol = d.bounds_viol; p.fviol = d.fcone_viol;
     cudaStream_t st = (cudaStream_t)d.stream;
     if (d.device_seconds) CUDA_TRY(cudaEventRecord(ctx->ev0, st));
-    rc = launch_solve(*ctx, p, st);
+    rc = launch_solve(*ctx, p, st, d.precision == FCCQP_PRECISION_FP32_DATA);
     if (rc) return rc;
     if (d.device_seconds) {
       CUDA_TRY(cudaEventRecord(ctx->ev1, st));
@@ -653,9 +658,12 @@ int fccqp_batch_solve(const fccqp_batch_desc* desc) {
   const auto t0 = std::chrono::steady_clock::now();
   // shared inputs once
   cudaStream_t s0 = ctx->streams[0];
+  // problem data are float32 in FCCQP_PRECISION_FP32_DATA (es = 4): half the bytes over PCIe; the staging
+  // segments keep their FP64 size, state and outputs are always FP64
+  const size_t es = d.precision == FCCQP_PRECISION_FP32_DATA ? sizeof(float) : sizeof(double);
   auto h2d_shared = [&](const Seg& s, const double* src) -> int {
     if (s.shared && s.per_qp && src)
-      CUDA_TRY(cudaMemcpyAsync(dp(s), src, s.per_qp * sizeof(double), cudaMemcpyHostToDevice, s0));
+      CUDA_TRY(cudaMemcpyAsync(dp(s), src, s.per_qp * es, cudaMemcpyHostToDevice, s0));
     return FCCQP_OK;
   };
   if ((rc = h2d_shared(sQ, d.Q)) || (rc = h2d_shared(sA, d.A_eq)) || (rc = h2d_shared(sb, d.b)) ||
@@ -697,34 +705,38 @@ int fccqp_batch_solve(const fccqp_batch_desc* desc) {
     const size_t cnt = (size_t)(hi - lo);
     if (!cnt) continue;
     cudaStream_t st = ctx->streams[c % 3];
-    auto h2d = [&](const Seg& s, const double* src) -> int {
+    auto h2d = [&](const Seg& s, const void* src, size_t esz) -> int {
       if (!s.shared && s.per_qp && src)
-        CUDA_TRY(cudaMemcpyAsync(dp(s) + lo * s.per_qp, src + lo * s.per_qp, cnt * s.per_qp * sizeof(double),
+        CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(dp(s)) + (size_t)lo * s.per_qp * esz,
+                                 static_cast<const char*>(src) + (size_t)lo * s.per_qp * esz, cnt * s.per_qp * esz,
                                  cudaMemcpyHostToDevice, st));
       return FCCQP_OK;
     };
-    if ((rc = h2d(sQ, d.Q)) || (rc = h2d(sA, d.A_eq)) || (rc = h2d(sb, d.b)) || (rc = h2d(sbeq, d.b_eq)) ||
-        (rc = h2d(smu, d.friction_coeffs)) || (rc = h2d(slb, d.lb)) || (rc = h2d(sub, d.ub)))
+    if ((rc = h2d(sQ, d.Q, es)) || (rc = h2d(sA, d.A_eq, es)) || (rc = h2d(sb, d.b, es)) || (rc = h2d(sbeq, d.b_eq, es)) ||
+        (rc = h2d(smu, d.friction_coeffs, es)) || (rc = h2d(slb, d.lb, es)) || (rc = h2d(sub, d.ub, es)))
       return rc;
     if (d.warm_start) {
-      if ((rc = h2d(sx, d.x)) || (rc = h2d(smx, d.mu_x)) || (rc = h2d(smc, d.mu_lambda_c))) return rc;
+      if ((rc = h2d(sx, d.x, 8)) || (rc = h2d(smx, d.mu_x, 8)) || (rc = h2d(smc, d.mu_lambda_c, 8))) return rc;
     }
     fccqp::SolveParams p{};
     fill_params(d, p);
     p.B = (int)cnt;
     auto off = [&](const Seg& s) { return s.shared ? dp(s) : dp(s) + lo * s.per_qp; };
-    p.Q = off(sQ); p.q_bs = q_shared ? 0 : (long long)n * n; p.q_rs = d.q_row_stride; p.q_cs = d.q_col_stride;
-    p.A = off(sA); p.a_bs = a_shared ? 0 : (long long)m * n; p.a_rs = d.a_row_stride; p.a_cs = d.a_col_stride;
-    p.b = off(sb); p.b_bs = b_shared ? 0 : n;
-    p.beq = off(sbeq); p.beq_bs = beq_shared ? 0 : m;
-    p.mu = off(smu); p.mu_bs = mu_shared ? 0 : nc / 3;
-    p.lb = off(slb); p.lb_bs = lb_shared ? 0 : n;
-    p.ub = off(sub); p.ub_bs = ub_shared ? 0 : n;
+    auto offi = [&](const Seg& s) {   // problem data: element size es
+      return s.shared ? dp(s) : reinterpret_cast<double*>(reinterpret_cast<char*>(dp(s)) + (size_t)lo * s.per_qp * es);
+    };
+    p.Q = offi(sQ); p.q_bs = q_shared ? 0 : (long long)n * n; p.q_rs = d.q_row_stride; p.q_cs = d.q_col_stride;
+    p.A = offi(sA); p.a_bs = a_shared ? 0 : (long long)m * n; p.a_rs = d.a_row_stride; p.a_cs = d.a_col_stride;
+    p.b = offi(sb); p.b_bs = b_shared ? 0 : n;
+    p.beq = offi(sbeq); p.beq_bs = beq_shared ? 0 : m;
+    p.mu = offi(smu); p.mu_bs = mu_shared ? 0 : nc / 3;
+    p.lb = offi(slb); p.lb_bs = lb_shared ? 0 : n;
+    p.ub = offi(sub); p.ub_bs = ub_shared ? 0 : n;
     p.x = off(sx); p.mu_x = off(smx); p.mu_c = off(smc);
     p.n_iter = d_niter + lo; p.status = d_status + lo;
     double* res = dp(sres);
     p.res_b = res + lo; p.res_f = res + (size_t)B + lo; p.bviol = res + 2 * (size_t)B + lo; p.fviol = res + 3 * (size_t)B + lo;
-    rc = launch_solve(*ctx, p, st);
+    rc = launch_solve(*ctx, p, st, es == sizeof(float));
     if (rc) return rc;
     // D2H: straight into the caller's buffer when it is page-locked (a true asynchronous DMA);
     // otherwise into the pinned bounce buffer, copied out below once the chunk's event has fired

@@ -174,6 +174,10 @@ __device__ __forceinline__ double fast_rcp(double d) {
   return fma(x, t, x);
 }
 
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
@@ -921,8 +925,10 @@ __device__ __noinline__ double g_apply(const double* __restrict__ M, double* __r
 // triangular solves and all vector work).  Warp 0 is the factorization's critical-path warp,
 // warps 1.. are its helpers.
 // ---------------------------------------------------------------------------
-template <int kThreads, int kMinBlocks, bool kShared>
+template <int kThreads, int kMinBlocks, bool kShared, bool kF32>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const SolveParams p) {
+  // kF32: the problem data (Q, b, A_eq, b_eq, friction_coeffs, lb, ub) are float32 arrays (same element
+  // strides); they are widened on the way into shared memory / registers, everything else is FP64.
   // kShared = false compiles the shared-structure logic out of the general kernel
   const int shared_mode = kShared ? p.shared_mode : 0;
   extern __shared__ __align__(16) double smem[];
@@ -973,6 +979,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
   const int fragT = ((2 * fq) << 3) + ((((fr >> 1) ^ fq) & 3) << 1) + (fr & 1);      // (2fq, fr); +8 for (2fq+1, fr)
 
   // Q is symmetric: walk it along whichever stride is contiguous.
+  auto ldin = [](const double* base, size_t idx) -> double {
+    return kF32 ? (double)reinterpret_cast<const float*>(base)[idx] : base[idx];
+  };
   const long long q_slow = p.q_cs <= p.q_rs ? p.q_rs : p.q_cs;
   const long long q_fast = p.q_cs <= p.q_rs ? p.q_cs : p.q_rs;
 
@@ -1005,17 +1014,17 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
     double v_lb = 0.0, v_ub = 0.0, v_mux = 0.0, v_xbar = 0.0, v_x = 0.0;
     int finite_bounds = 0;
     if (is_x) {
-      v_b = p.b[(size_t)qp * p.b_bs + t];
-      v_lb = p.lb[(size_t)qp * p.lb_bs + t];
-      v_ub = p.ub[(size_t)qp * p.ub_bs + t];
+      v_b = ldin(p.b, (size_t)qp * p.b_bs + t);
+      v_lb = ldin(p.lb, (size_t)qp * p.lb_bs + t);
+      v_ub = ldin(p.ub, (size_t)qp * p.ub_bs + t);
       if (!isinf(v_lb) || !isinf(v_ub)) finite_bounds = 1;
       if (p.warm || resume) v_x = p.x[(size_t)qp * n + t];
       if (p.warm) v_mux = p.mu_x[(size_t)qp * n + t];
     } else if (is_c) {
-      v_b = p.beq[(size_t)qp * p.beq_bs + (t - n8)];
+      v_b = ldin(p.beq, (size_t)qp * p.beq_bs + (t - n8));
     }
     if (t < n8) xs[t] = v_x;
-    if (t < nc / 3) vmu[t] = p.mu[(size_t)qp * p.mu_bs + t];
+    if (t < nc / 3) vmu[t] = ldin(p.mu, (size_t)qp * p.mu_bs + t);
     if (t < nc) muc[t] = p.warm ? p.mu_c[(size_t)qp * nc + t] : 0.0;
     const bool eqc = (__syncthreads_or(finite_bounds) == 0) && (nc == 0);  // fcc_qp.cpp:132-133
     const bool presolve = eqc || !p.warm;                                  // fcc_qp.cpp:159
@@ -1082,7 +1091,77 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
       // ---------------- assemble the lower tiles of the padded KKT matrix ----------------
       // one warp per tile, lane = (row fr, column pair 2fq): 8 x 64-byte row segments from HBM/L2.
       // Tile rows outer, warps strided over the tile columns.
-      {
+      if constexpr (kF32) {
+        // float32 problem data: stage 0 copies each tile's 8 x 8 floats asynchronously into the first
+        // 256 bytes of its own 512-byte slot, stage 1 widens them in place (all lanes of the owning
+        // warp read their pair, __syncwarp, write the FP64 pair / the pad value at its final place)
+        const float* Qf = reinterpret_cast<const float*>(p.Q) + (size_t)qp * p.q_bs;
+        const float* Af = reinterpret_cast<const float*>(p.A) + (size_t)qp * p.a_bs;
+        const bool q_v2 = q_fast == 1 && (n & 1) == 0 && ((reinterpret_cast<uintptr_t>(Qf) | (uintptr_t)(q_slow * 4)) & 7) == 0;
+        const bool a_v2 = p.a_cs == 1 && (n & 1) == 0 && ((reinterpret_cast<uintptr_t>(Af) | (uintptr_t)(p.a_rs * 4)) & 7) == 0;
+        const int gc0 = 2 * fq;
+        const int stg = fr * 4 + fq;   // staging slot of this lane inside a tile (in doubles = float pairs)
+#pragma unroll 1
+        for (int stage = 0; stage < 2; ++stage) {
+          const float* qrow = Qf + fr * q_slow + gc0 * q_fast;
+#pragma unroll 1
+          for (int I = 0; I < NBx; ++I, qrow += 8 * q_slow) {
+            const int gi = 8 * I + fr;
+#pragma unroll 1
+            for (int J = warp; J <= I; J += kWarps) {
+              const int gc = 8 * J + gc0;
+              double* tile = M + tile_off(I, J);
+              const float* src = qrow + (8 * J) * q_fast;
+              const bool d0 = gi < n && gc < n, d1 = gi < n && gc + 1 < n;
+              if (stage == 0) {
+                if (q_v2) { if (d0) cp_async8(tile + stg, reinterpret_cast<const double*>(src)); }
+                else {
+                  if (d0) cp_async4(reinterpret_cast<float*>(tile + stg), src);
+                  if (d1) cp_async4(reinterpret_cast<float*>(tile + stg) + 1, src + q_fast);
+                }
+              } else {
+                const float2 v = *reinterpret_cast<const float2*>(tile + stg);
+                __syncwarp();
+                st2(tile + fragC, make_double2(d0 ? (double)v.x : (gi == gc ? 1.0 : 0.0),
+                                               d1 ? (double)v.y : (gi == gc + 1 ? 1.0 : 0.0)));
+              }
+            }
+          }
+          const float* arow = Af + (long long)fr * p.a_rs + gc0 * p.a_cs;
+#pragma unroll 1
+          for (int I = NBx; I < NB; ++I, arow += 8 * p.a_rs) {
+            const int k = 8 * (I - NBx) + fr;
+#pragma unroll 1
+            for (int J = warp; J < NBx; J += kWarps) {
+              const int gc = 8 * J + gc0;
+              double* tile = M + tile_off(I, J);
+              const float* src = arow + (8 * J) * p.a_cs;
+              const bool d0 = k < m && gc < n, d1 = k < m && gc + 1 < n;
+              if (stage == 0) {
+                if (a_v2) { if (d0) cp_async8(tile + stg, reinterpret_cast<const double*>(src)); }
+                else {
+                  if (d0) cp_async4(reinterpret_cast<float*>(tile + stg), src);
+                  if (d1) cp_async4(reinterpret_cast<float*>(tile + stg) + 1, src + p.a_cs);
+                }
+              } else {
+                const float2 v = *reinterpret_cast<const float2*>(tile + stg);
+                __syncwarp();
+                st2(tile + fragC, make_double2(d0 ? (double)v.x : 0.0, d1 ? (double)v.y : 0.0));
+              }
+            }
+            if (stage == 0) {
+              // (2,2) block: zero; decoupled unit pivots on the constraint pads
+              double* dst = M + tile_off(I, NBx + warp) + fragC;
+#pragma unroll 1
+              for (int J = NBx + warp; J <= I; J += kWarps, dst += 64 * kWarps) {
+                const bool dg = J == I && k >= m;
+                st2(dst, make_double2((dg && fr == gc0) ? 1.0 : 0.0, (dg && fr == gc0 + 1) ? 1.0 : 0.0));
+              }
+            }
+          }
+          if (stage == 0) { cp_async_wait_all(); __syncthreads(); }
+        }
+      } else {
         const int gc0 = 2 * fq;
         // Q (symmetric; row read along the contiguous direction), unit pivots on the pads
         const double* qrow = Qg + fr * q_slow + gc0 * q_fast;

@@ -217,3 +217,49 @@ print("ok")
     r = subprocess.run([sys.executable, "-c", code, root], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.strip().endswith("ok")
+
+
+@pytest.mark.parametrize("path", ["host", "device"])
+def test_fp32_data_mode_walking_log(walking_log, path):
+    """FCCQP_PRECISION_FP32_DATA: float32 problem data, FP64 arithmetic.  Stated bound (include/fccqp.h):
+    2e-3 relative on z, 1e-5 on the objective; measured on the log with the CPU oracle fed float32-rounded
+    inputs: p50 1e-7, max 7.7e-4 on z, 1e-8 on the objective, iteration counts unchanged."""
+    import torch
+    from fcc_qp_b200.batch import FCCQPBatch, FCCQPOptionsB
+    gold = np.load(os.path.join(G, "walking_cold.npz"))
+    qp = walking_log
+    s = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start, precision="fp32_data")
+    s.set_options(FCCQPOptionsB(**LOG_OPTS))
+    args = (qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)
+    if path == "device":
+        args = [torch.as_tensor(a, dtype=torch.float32, device="cuda:0") for a in args]
+    s.Solve(*args)
+    sol = s.GetSolution()
+    z = sol.z.cpu().numpy() if path == "device" else sol.z
+    it = sol.details.n_iter.cpu().numpy() if path == "device" else sol.details.n_iter
+    err = rel_err(z, gold["z"])
+    assert err.max() <= 2e-3 and np.median(err) <= 1e-6
+    o, oref = qp.objective(z), qp.objective(gold["z"])
+    assert (np.abs(o - oref) / np.maximum(1.0, np.abs(oref))).max() <= 1e-5
+    assert (it != gold["n_iter"]).mean() <= 0.005
+    # and it is exactly the FP64 solver on float32-rounded data
+    r = lambda a: a.astype(np.float32).astype(np.float64)
+    s64 = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start)
+    s64.set_options(FCCQPOptionsB(**LOG_OPTS))
+    s64.Solve(*[r(a) for a in (qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)])
+    z64 = s64.GetSolution().z
+    assert np.abs(z - z64).max() <= 1e-9 * max(1.0, np.abs(z64).max())
+
+
+@pytest.mark.parametrize("name,B", [("humanoid", 192), ("multicontact", 96)])
+def test_fp32_data_mode_synthetic(name, B):
+    from fcc_qp_b200 import synthetic as syn
+    from fcc_qp_b200.batch import FCCQPBatch, FCCQPOptionsB
+    gold = np.load(os.path.join(G, f"synthetic_{name}_cold.npz"))
+    qp = syn.make_batch(syn.SHAPES[name], B)
+    s = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start, precision="fp32_data")
+    s.set_options(FCCQPOptionsB(**LOG_OPTS))
+    s.Solve(qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)
+    sol = s.GetSolution()
+    assert rel_err(sol.z, gold["z"]).max() <= 2e-3
+    assert (sol.details.n_iter != gold["n_iter"]).mean() <= 0.05
