@@ -24,3 +24,7 @@ if shape != "walking":
     s2 = FCCQPBatch(q.n, q.m, q.nc, q.lambda_c_start); s2.set_options(FCCQPOptionsB(100, 5e-5, 1e-6, 1e-6))
     s2.Solve(q.Q[0], q.b, q.A_eq[0], q.b_eq, q.friction_coeffs, q.lb[0], q.ub[0])
     print("shared-structure", shape, "QPs", q.batch, np.unique(s2.GetSolution().details.n_iter, return_counts=True)[1][:3])
+# float32 problem data (widening stage-in)
+s3 = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start, precision="fp32_data"); s3.set_options(FCCQPOptionsB(100, 5e-5, 1e-6, 1e-6))
+s3.Solve(qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)
+print("fp32_data", shape, "QPs", qp.batch, np.unique(s3.GetSolution().details.n_iter, return_counts=True)[1][:3])
