@@ -174,4 +174,88 @@ class FCCQP {
   const int n_vars_, n_eq_, nc_, lambda_c_start_;
 };
 
+// ---------------------------------------------------------------------------
+// Batched solver (extension; the reference solves one QP per call): B QPs of identical dimensions per
+// Solve through fccqp_batch_solve.  Same option / warm-start semantics as FCCQP, applied lane-wise;
+// the carried state (x, mu_x, mu_lambda_c) of every lane lives in this object.
+// ---------------------------------------------------------------------------
+struct FCCQPBatchProblem {
+  // dense row-major stacks: Q [B,n,n], b [B,n], A_eq [B,m,n], b_eq [B,m], friction_coeffs [B,nc/3], lb/ub [B,n]
+  const double* Q = nullptr;
+  const double* b = nullptr;
+  const double* A_eq = nullptr;
+  const double* b_eq = nullptr;
+  const double* friction_coeffs = nullptr;
+  const double* lb = nullptr;
+  const double* ub = nullptr;
+  bool shared_structure = false;   // Q is [n,n] and A_eq is [m,n]: one pair for the whole batch
+  bool shared_bounds = false;      // lb / ub are [n]
+  bool shared_friction = false;    // friction_coeffs is [nc/3]
+};
+
+struct FCCQPBatchSolution {
+  int batch = 0;
+  std::vector<double> z;                       // [B,n]
+  std::vector<int> n_iter, solve_status;       // [B]
+  std::vector<double> admm_residual_bounds, admm_residual_friction_cone, bounds_viol, friction_cone_viol;  // [B]
+  double solve_time = 0.0;                     // wall seconds of the whole call
+};
+
+class FCCQPBatch {
+ public:
+  FCCQPBatch(int num_vars, int num_equality_constraints, int nc, int lambda_c_start, int device = 0)
+      : n_(num_vars), m_(num_equality_constraints), nc_(nc), lcs_(lambda_c_start), device_(device) {
+    if (nc % 3 != 0) throw std::invalid_argument("nc must be a multiple of 3 (src/fcc_qp.cpp:32)");
+    if (lambda_c_start < 0 || lambda_c_start + nc > num_vars)
+      throw std::invalid_argument("lambda_c_start + nc must be <= num_vars (src/fcc_qp.cpp:33)");
+    fccqp_default_options(&opt_);
+  }
+  void set_rho(double rho) { if (!(rho > 0)) throw std::invalid_argument("rho must be > 0"); opt_.rho = rho; }
+  void set_max_iter(int n) { if (n <= 0) throw std::invalid_argument("max_iter must be > 0"); opt_.max_iter = n; }
+  void set_options(FCCQPOptions o) {
+    opt_.max_iter = o.max_iter; opt_.rho = o.rho; opt_.eps_fcone = o.eps_fcone; opt_.eps_bound = o.eps_bound;
+  }
+  void set_warm_start(bool warm_start) { warm_ = warm_start; }
+
+  // Host pointers; blocks until the results are back.
+  void Solve(int batch, const FCCQPBatchProblem& p) {
+    const size_t B = (size_t)batch, n = (size_t)n_, m = (size_t)m_, nc = (size_t)nc_;
+    const bool carry = warm_ && sol_.batch == batch;    // like a never-solved FCCQP, a fresh lane starts from zero
+    if (!carry) { sol_.z.assign(B * n, 0.0); mu_x_.assign(B * n, 0.0); mu_c_.assign(B * nc, 0.0); }
+    sol_.batch = batch;
+    sol_.n_iter.resize(B); sol_.solve_status.resize(B);
+    sol_.admm_residual_bounds.resize(B); sol_.admm_residual_friction_cone.resize(B);
+    sol_.bounds_viol.resize(B); sol_.friction_cone_viol.resize(B);
+    fccqp_batch_desc d{};
+    d.abi_version = FCCQP_ABI_VERSION; d.batch = batch; d.n = n_; d.m = m_; d.nc = nc_; d.lambda_c_start = lcs_;
+    d.device = device_; d.memory_space = FCCQP_MEM_HOST; d.precision = FCCQP_PRECISION_FP64; d.warm_start = warm_ ? 1 : 0;
+    d.options = opt_;
+    d.Q = p.Q; d.q_batch_stride = p.shared_structure ? 0 : (int64_t)(n * n); d.q_row_stride = n_; d.q_col_stride = 1;
+    d.b = p.b; d.b_batch_stride = n_;
+    d.A_eq = p.A_eq; d.a_batch_stride = p.shared_structure ? 0 : (int64_t)(m * n); d.a_row_stride = n_; d.a_col_stride = 1;
+    d.b_eq = p.b_eq; d.beq_batch_stride = m_;
+    d.friction_coeffs = p.friction_coeffs; d.mu_batch_stride = p.shared_friction ? 0 : nc_ / 3;
+    d.lb = p.lb; d.lb_batch_stride = p.shared_bounds ? 0 : n_;
+    d.ub = p.ub; d.ub_batch_stride = p.shared_bounds ? 0 : n_;
+    d.x = sol_.z.data(); d.mu_x = mu_x_.data(); d.mu_lambda_c = mu_c_.data();
+    d.n_iter = sol_.n_iter.data(); d.status = sol_.solve_status.data();
+    d.res_bounds = sol_.admm_residual_bounds.data(); d.res_fcone = sol_.admm_residual_friction_cone.data();
+    d.bounds_viol = sol_.bounds_viol.data(); d.fcone_viol = sol_.friction_cone_viol.data();
+    double secs = 0.0;
+    d.device_seconds = &secs;
+    const int rc = fccqp_batch_solve(&d);
+    if (rc == FCCQP_E_INVALID) throw std::invalid_argument(fccqp_last_error());
+    if (rc != FCCQP_OK) throw std::runtime_error(fccqp_last_error());
+    sol_.solve_time = secs;
+  }
+  const FCCQPBatchSolution& GetSolution() const { return sol_; }
+
+ private:
+  const int n_, m_, nc_, lcs_, device_;
+  fccqp_options opt_{};
+  bool warm_ = false;
+  FCCQPBatchSolution sol_;
+  std::vector<double> mu_x_, mu_c_;
+};
+
 }  // namespace fcc_qp

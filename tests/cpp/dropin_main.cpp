@@ -68,6 +68,36 @@ int main() {
     solver.Solve(big.topLeftCorner(3, 3), b, A, b_eq, std::vector<double>{0.5}, lb, ub);
     CHECK(std::abs(solver.GetSolution().z(2) - 2.8) < 1e-4);
   }
+  {  // batched C++ entry point: B cone projections with different targets, against single solves
+    const int B = 16;
+    std::vector<double> Q(B * 9, 0.0), b(B * 3), mu(B), lbv(3, -inf), ubv(3, inf);
+    for (int k = 0; k < B; ++k) {
+      for (int i = 0; i < 3; ++i) Q[k * 9 + i * 3 + i] = 1.0;
+      b[k * 3 + 0] = -(1.0 + 0.25 * k); b[k * 3 + 1] = -(2.0 - 0.1 * k); b[k * 3 + 2] = -(0.5 + 0.05 * k);
+      mu[k] = 0.4 + 0.02 * k;
+    }
+    fcc_qp::FCCQPBatch batch(3, 0, 3, 0);
+    options.rho = 1.0; options.max_iter = 500;
+    batch.set_options(options);
+    fcc_qp::FCCQPBatchProblem p;
+    p.Q = Q.data(); p.b = b.data(); p.friction_coeffs = mu.data(); p.lb = lbv.data(); p.ub = ubv.data();
+    p.shared_bounds = true;
+    batch.Solve(B, p);
+    const fcc_qp::FCCQPBatchSolution& bs = batch.GetSolution();
+    FCCQP single(3, 0, 3, 0);
+    single.set_options(options);
+    for (int k = 0; k < B; ++k) {
+      MatrixXd Qk = MatrixXd::Identity(3, 3);
+      VectorXd bk(3); bk << b[k * 3], b[k * 3 + 1], b[k * 3 + 2];
+      MatrixXd A(0, 3); VectorXd beq(0);
+      VectorXd lb = VectorXd::Constant(3, -inf), ub = VectorXd::Constant(3, inf);
+      single.Solve(Qk, bk, A, beq, std::vector<double>{mu[k]}, lb, ub);
+      FCCQPSolution s1 = single.GetSolution();
+      for (int i = 0; i < 3; ++i) CHECK(std::abs(bs.z[k * 3 + i] - s1.z(i)) < 1e-12);
+      CHECK(bs.n_iter[k] == s1.details.n_iter);
+      CHECK(bs.solve_status[k] == (int)s1.details.solve_status);
+    }
+  }
   std::printf(fails ? "dropin_main: %d failure(s)\n" : "dropin_main: ok\n", fails);
   return fails ? 1 : 0;
 }
