@@ -1026,7 +1026,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
     if (t < n8) xs[t] = v_x;
     if (t < nc / 3) vmu[t] = ldin(p.mu, (size_t)qp * p.mu_bs + t);
     if (t < nc) muc[t] = p.warm ? p.mu_c[(size_t)qp * nc + t] : 0.0;
-    const bool eqc = (__syncthreads_or(finite_bounds) == 0) && (nc == 0);  // fcc_qp.cpp:132-133
+    // equality-constrained (fcc_qp.cpp:132-133) needs nc == 0 AND no finite bound: with contacts the block-wide
+    // vote -- and the stall on the bound loads it implies -- is skipped (nothing below reads another thread's
+    // K0 shared-memory writes before the next barrier)
+    const bool eqc = (nc == 0) && (__syncthreads_or(finite_bounds) == 0);
     const bool presolve = eqc || !p.warm;                                  // fcc_qp.cpp:159
 
     const long long t_start = clock64();
@@ -1052,7 +1055,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
       if (pass == 1) {
         // ADMM initial slack (fcc_qp.cpp:74-75): x_bar = x, lambda_c_bar = x[lambda_c segment]
         v_xbar = v_x;
-        if (t < nc) lcbar[t] = xs[lcs + t];
+        if (in_cone) lcbar[t - lcs] = v_x;
         __syncthreads();
         n_iter = p.max_iter;
       }
