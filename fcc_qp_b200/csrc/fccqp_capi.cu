@@ -199,9 +199,12 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool
     }
     return FCCQP_OK;
   }
-  if (shared_structure) {
-    unsigned int* scratch = nullptr;   // [0] = pending count, [1..B] = pending QP indices
-    CUDA_TRY(cudaMallocAsync(&scratch, ((size_t)p.B + 1) * sizeof(unsigned int), stream));
+  unsigned int* scratch = nullptr;   // [0] = pending count, [1..B] = pending QP indices
+  if (shared_structure && cudaMallocAsync(&scratch, ((size_t)p.B + 1) * sizeof(unsigned int), stream) != cudaSuccess) {
+    cudaGetLastError();                // no stream-ordered allocator here: the general path below still applies
+    scratch = nullptr;
+  }
+  if (shared_structure && scratch) {
     CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(unsigned int), stream));
     CUDA_TRY(cudaMemsetAsync(counter2, 0, sizeof(unsigned int), stream));
     fccqp::SolveParams a = p;
