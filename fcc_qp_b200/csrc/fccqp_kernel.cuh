@@ -934,7 +934,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kWarps = kThreads / 32;
-  constexpr int kHelpers = kWarps - 1;
   const int n = p.n, m = p.m, nc = p.nc, lcs = p.lcs;
   const int n8 = p.lay.n8, N8 = p.lay.N8, NB = p.lay.NB, NBx = p.lay.NBx, NB32 = p.lay.NB32;
 
@@ -972,7 +971,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
   const int tb = t >> 3, tr = t & 7, tf = tr >> 1;  // tile row, row in tile, row swizzle
   const int colo = tr & 1, colc = tr >> 1;          // column-per-thread access: element (r, tr) of a tile
   const int flip = tb & 1;                          // odd tile columns walk row pairs swapped (bank spread)
-  const int tbe = tb < NB ? tb : NB - 1;            // clamped tile row (threads beyond N8 read valid data, masked)
   // tensor-core fragment coordinates of this lane
   const int fr = lane >> 2, fq = lane & 3;
   const int fragC = (fr << 3) + (((fq ^ (fr >> 1)) & 3) << 1);                       // (fr, 2fq..2fq+1)
