@@ -7,7 +7,12 @@ from fcc_qp_b200.logdata import load_walking_log
 from fcc_qp_b200 import synthetic as syn
 from fcc_qp_b200.batch import FCCQPBatch, FCCQPOptionsB
 shape = sys.argv[1] if len(sys.argv) > 1 else "walking"
-qp = load_walking_log().take(np.arange(0, 2019, 48)) if shape == "walking" else syn.make_batch(syn.SHAPES[shape], 24)
+if shape == "odd":   # odd n, no 16-byte row alignment: the 8-byte / 4-byte staging paths
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_gpu_random_shapes import random_qps
+    qp = random_qps(np.random.default_rng(3), 24, 13, 6, 6, 5)
+else:
+    qp = load_walking_log().take(np.arange(0, 2019, 48)) if shape == "walking" else syn.make_batch(syn.SHAPES[shape], 24)
 s = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start); s.set_options(FCCQPOptionsB(100, 5e-5, 1e-6, 1e-6))
 s.Solve(qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)
 it = s.GetSolution().details.n_iter
@@ -15,7 +20,7 @@ s.set_warm_start(True)
 s.Solve(qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)
 print(shape, "QPs", qp.batch, "cold iterations", np.unique(it, return_counts=True), "warm", np.unique(s.GetSolution().details.n_iter, return_counts=True))
 # shared-structure batch (two-launch path with cached factorizations)
-if shape != "walking":
+if shape not in ("walking", "odd"):
     shp = syn.SHAPES[shape]
     t = syn.make_terms(shp, 1300 if shp.n + shp.m > 128 else 2500, seed=shp.seed + 7)
     rep = lambda a: np.ascontiguousarray(np.broadcast_to(a[:1], a.shape))
