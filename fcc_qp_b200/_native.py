@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # FCCQP_LIB: developer override (e.g. an instrumented -DFCCQP_DEV build of the same sources)
 LIB_PATH = os.environ.get("FCCQP_LIB") or os.path.join(_HERE, "libfccqp_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MEM_HOST, MEM_DEVICE = 0, 1
 STATUS_SUCCESS, STATUS_MAX_ITERATIONS, STATUS_NUMERICAL_ISSUE = 0, 1, 2
 E_INVALID, E_CUDA, E_UNSUPPORTED = -1, -2, -3
@@ -31,7 +31,7 @@ class FCCQPError(RuntimeError):
 
 class Options(C.Structure):
     _fields_ = [("max_iter", C.c_int32), ("reserved", C.c_int32), ("rho", C.c_double),
-                ("eps_fcone", C.c_double), ("eps_bound", C.c_double)]
+                ("eps_fcone", C.c_double), ("eps_bound", C.c_double), ("relaxation", C.c_double)]
 
 
 class Details(C.Structure):

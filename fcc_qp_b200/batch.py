@@ -30,6 +30,7 @@ class FCCQPOptionsB:
     rho: float = 1e-6
     eps_fcone: float = 1e-3
     eps_bound: float = 1e-6
+    relaxation: float = 1.0   # extension (not in the reference): ADMM over-relaxation alpha in (0, 2); 1.0 = reference
 
 
 @dataclasses.dataclass
@@ -92,7 +93,8 @@ class FCCQPBatch:
         self.options.max_iter = int(n)
 
     def set_options(self, opt):
-        self.options = FCCQPOptionsB(int(opt.max_iter), float(opt.rho), float(opt.eps_fcone), float(opt.eps_bound))
+        self.options = FCCQPOptionsB(int(opt.max_iter), float(opt.rho), float(opt.eps_fcone), float(opt.eps_bound),
+                                     float(getattr(opt, "relaxation", 1.0)))
 
     def set_warm_start(self, warm_start: bool):
         self.warm_start = bool(warm_start)
@@ -137,7 +139,7 @@ class FCCQPBatch:
         d.batch, d.n, d.m, d.nc, d.lambda_c_start = B, self.n, self.m, self.nc, self.lcs
         d.device, d.memory_space, d.precision = self.device, mem, (1 if self.precision == "fp32_data" else 0)
         o = self.options
-        d.options = nat.Options(int(o.max_iter), 0, float(o.rho), float(o.eps_fcone), float(o.eps_bound))
+        d.options = nat.Options(int(o.max_iter), 0, float(o.rho), float(o.eps_fcone), float(o.eps_bound), float(o.relaxation))
         return d
 
     def _check_shapes(self, shp, B):

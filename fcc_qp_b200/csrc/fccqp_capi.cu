@@ -307,6 +307,8 @@ int check_dims(int n, int m, int nc, int lcs) {
 int check_options(const fccqp_options& o) {
   if (o.max_iter < 0) return fail(FCCQP_E_INVALID, "max_iter must be >= 0");
   if (!(o.rho > 0.0)) return fail(FCCQP_E_INVALID, "rho must be > 0 (src/fcc_qp.hpp:76)");
+  if (o.relaxation != 0.0 && !(o.relaxation > 0.0 && o.relaxation < 2.0))
+    return fail(FCCQP_E_INVALID, "relaxation must be in (0, 2) (0 = unset = 1)");
   return FCCQP_OK;
 }
 
@@ -345,6 +347,7 @@ extern "C" {
 void fccqp_default_options(fccqp_options* opt) {
   if (!opt) return;
   opt->max_iter = 1000; opt->reserved = 0; opt->rho = 1e-6; opt->eps_fcone = 1e-3; opt->eps_bound = 1e-6;
+  opt->relaxation = 1.0;
 }
 const char* fccqp_last_error(void) { return g_err.c_str(); }
 int fccqp_abi_version(void) { return FCCQP_ABI_VERSION; }
@@ -491,6 +494,7 @@ int fccqp_solve(fccqp_handle h, const double* Q, ptrdiff_t q_rs, ptrdiff_t q_cs,
   fccqp::SolveParams p{};
   p.B = 1; p.n = n; p.m = m; p.nc = nc; p.lcs = h->lcs;
   p.max_iter = h->opt.max_iter; p.rho = h->opt.rho; p.eps_fcone = h->opt.eps_fcone; p.eps_bound = h->opt.eps_bound;
+  p.alpha = h->opt.relaxation > 0.0 ? h->opt.relaxation : 1.0;
   p.warm = h->warm;  // warm with no earlier Solve starts from the zero state, like the reference object
   double* d = h->d_in;
   p.Q = d; p.q_bs = 0; p.q_rs = n; p.q_cs = 1; d += (size_t)n * n;
@@ -554,6 +558,7 @@ static int fill_params(const fccqp_batch_desc& d, fccqp::SolveParams& p) {
   p.B = d.batch; p.n = d.n; p.m = d.m; p.nc = d.nc; p.lcs = d.lambda_c_start;
   p.max_iter = d.options.max_iter; p.rho = d.options.rho;
   p.eps_fcone = d.options.eps_fcone; p.eps_bound = d.options.eps_bound;
+  p.alpha = d.options.relaxation > 0.0 ? d.options.relaxation : 1.0;
   p.warm = d.warm_start != 0;
   return FCCQP_OK;
 }

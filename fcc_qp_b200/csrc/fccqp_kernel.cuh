@@ -109,6 +109,7 @@ struct SolveParams {
   int full_inverse_at;        // ADMM iteration from which x-updates use the completed inverse of L (default 8)
   int first_update_identity;  // cold solves: take x-update 0 as the identity it is (see kernel), default 1
   double rho, eps_fcone, eps_bound;
+  double alpha;               // over-relaxation (fccqp_options::relaxation); 1.0 = the reference's iteration
   const double* Q;   long long q_bs, q_rs, q_cs;
   const double* b;   long long b_bs;
   const double* A;   long long a_bs, a_rs, a_cs;
@@ -1339,16 +1340,23 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
         if (is_x) { xs[t] = val; v_x = val; }
         __syncthreads();
         double rx = 0.0, rc = 0.0;
+        const bool relax = p.alpha != 1.0;   // extension: x_hat = alpha x + (1 - alpha) x_bar_prev in place of x below
         if (is_x) {
-          const double xb = clampd(val + v_mux, v_lb, v_ub);
+          const double xh = relax ? fma(p.alpha, val, (1.0 - p.alpha) * v_xbar) : val;
+          const double xb = clampd(xh + v_mux, v_lb, v_ub);
           v_xbar = xb;
-          const double r = val - xb;
+          const double r = xh - xb;
           v_mux += r;
           rx = fabs(r);
         }
         if (t < nc / 3) {  // lane per contact
           const int o = lcs + 3 * t;
-          const double x0 = xs[o], x1 = xs[o + 1], x2 = xs[o + 2];
+          double x0 = xs[o], x1 = xs[o + 1], x2 = xs[o + 2];
+          if (relax) {
+            x0 = fma(p.alpha, x0, (1.0 - p.alpha) * lcbar[3 * t]);
+            x1 = fma(p.alpha, x1, (1.0 - p.alpha) * lcbar[3 * t + 1]);
+            x2 = fma(p.alpha, x2, (1.0 - p.alpha) * lcbar[3 * t + 2]);
+          }
           double o0, o1, o2;
           project_cone3(x0 + muc[3 * t], x1 + muc[3 * t + 1], x2 + muc[3 * t + 2], vmu[t], o0, o1, o2);
           lcbar[3 * t] = o0; lcbar[3 * t + 1] = o1; lcbar[3 * t + 2] = o2;

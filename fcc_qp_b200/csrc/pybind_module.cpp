@@ -58,7 +58,8 @@ PYBIND11_MODULE(fcc_qp_solver, m) {
       .def_readwrite("max_iter", &FCCQPOptions::max_iter)
       .def_readwrite("rho", &FCCQPOptions::rho)
       .def_readwrite("eps_fcone", &FCCQPOptions::eps_fcone)
-      .def_readwrite("eps_bound", &FCCQPOptions::eps_bound);
+      .def_readwrite("eps_bound", &FCCQPOptions::eps_bound)
+      .def_readwrite("relaxation", &FCCQPOptions::relaxation);   // extension, default 1.0 = the reference
 
   py::class_<FCCQPSolution>(m, "FCCQPSolution")
       .def_readwrite("details", &FCCQPSolution::details)

@@ -48,6 +48,7 @@ struct FCCQPOptions {
   double rho = 1e-6;
   double eps_fcone = 1e-3;
   double eps_bound = 1e-6;
+  double relaxation = 1.0;   // extension, not in the reference: ADMM over-relaxation (fccqp_options::relaxation)
 };
 
 // src/fcc_qp.hpp:37-40
@@ -92,7 +93,7 @@ class FCCQP {
   void set_max_iter(int n) { check(fccqp_set_max_iter(h_, n)); }
   void set_options(FCCQPOptions opt) {
     fccqp_options o;
-    o.max_iter = opt.max_iter; o.reserved = 0; o.rho = opt.rho;
+    o.max_iter = opt.max_iter; o.reserved = 0; o.rho = opt.rho; o.relaxation = opt.relaxation;
     o.eps_fcone = opt.eps_fcone; o.eps_bound = opt.eps_bound;
     check(fccqp_set_options(h_, &o));
   }
@@ -214,6 +215,7 @@ class FCCQPBatch {
   void set_max_iter(int n) { if (n <= 0) throw std::invalid_argument("max_iter must be > 0"); opt_.max_iter = n; }
   void set_options(FCCQPOptions o) {
     opt_.max_iter = o.max_iter; opt_.rho = o.rho; opt_.eps_fcone = o.eps_fcone; opt_.eps_bound = o.eps_bound;
+    opt_.relaxation = o.relaxation;
   }
   void set_warm_start(bool warm_start) { warm_ = warm_start; }
 

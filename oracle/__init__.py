@@ -85,6 +85,7 @@ class Oracle:
             f("get_state").argtypes = [C.c_void_p, _dp, _dp, _dp]
             f("set_state").argtypes = [C.c_void_p, _dp, _dp, _dp]
             self.lib.fccqp_oracle_project_cone3.argtypes = [_dp, C.c_double, _dp]
+            self.lib.fccqp_oracle_set_relaxation.argtypes = [C.c_double]
             self.lib.fccqp_oracle_cone_violation.restype = C.c_double
             self.lib.fccqp_oracle_cone_violation.argtypes = [_dp, C.c_int, _dp]
             self.lib.fccqp_oracle_bound_violation.restype = C.c_double
@@ -92,6 +93,12 @@ class Oracle:
 
     def fn(self, name):
         return getattr(self.lib, self.p + name)
+
+    def set_relaxation(self, alpha: float) -> None:
+        """Over-relaxation of the C restatement (port only; checks the product's opt-in extension).
+        Process-wide; reset to 1.0 (the reference's iteration) when done."""
+        assert self.kind == "port"
+        self.lib.fccqp_oracle_set_relaxation(float(alpha))
 
     def hardware_threads(self) -> int:
         return int(self.fn("hardware_threads")())

@@ -433,6 +433,10 @@ static double inf_norm_like_reference(const double* v, int len) {
 }
 
 /* fcc_qp.cpp:57-112 */
+/* process-wide over-relaxation of the restatement (tests of the product's extension only; default 1 = reference) */
+static double g_relaxation = 1.0;
+void fccqp_oracle_set_relaxation(double alpha) { g_relaxation = alpha; }
+
 static void do_admm(fccqp_oracle* o, const double* b, const double* mu, const double* lb,
                     const double* ub) {
   const int n = o->n, N = o->N, nc = o->nc, lcs = o->lcs;
@@ -457,14 +461,35 @@ static void do_admm(fccqp_oracle* o, const double* b, const double* mu, const do
     ldlt_solve(N, o->ldlt, o->tr, o->b_kkt, o->kkt_sol);
     memcpy(o->x, o->kkt_sol, sizeof(double) * (size_t)n);
 
-    for (int i = 0; i < n; ++i) o->x_bar[i] = clampd(o->x[i] + o->mu_x[i], lb[i], ub[i]);
-    for (int c = 0; c < nc / 3; ++c) {
-      double f[3];
-      for (int k = 0; k < 3; ++k) f[k] = o->x[lcs + 3 * c + k] + o->mu_lambda_c[3 * c + k];
-      fccqp_oracle_project_cone3(f, mu[c], o->lambda_c_bar + 3 * c);
+    /* Extension of the product (include/fccqp.h, fccqp_options::relaxation), NOT in the reference:
+     * x_hat = alpha x + (1 - alpha) x_bar_prev takes the place of x in the z-update, the residuals and the
+     * dual update.  alpha == 1 (the default) is the reference's code path, statement for statement. */
+    const double alpha = g_relaxation;
+    if (alpha == 1.0) {
+      for (int i = 0; i < n; ++i) o->x_bar[i] = clampd(o->x[i] + o->mu_x[i], lb[i], ub[i]);
+      for (int c = 0; c < nc / 3; ++c) {
+        double f[3];
+        for (int k = 0; k < 3; ++k) f[k] = o->x[lcs + 3 * c + k] + o->mu_lambda_c[3 * c + k];
+        fccqp_oracle_project_cone3(f, mu[c], o->lambda_c_bar + 3 * c);
+      }
+      for (int i = 0; i < n; ++i) o->x_res[i] = o->x[i] - o->x_bar[i];
+      for (int i = 0; i < nc; ++i) o->lambda_c_res[i] = o->x[lcs + i] - o->lambda_c_bar[i];
+    } else {
+      for (int i = 0; i < n; ++i) {
+        const double xh = fma(alpha, o->x[i], (1.0 - alpha) * o->x_bar[i]);
+        o->x_bar[i] = clampd(xh + o->mu_x[i], lb[i], ub[i]);
+        o->x_res[i] = xh - o->x_bar[i];
+      }
+      for (int c = 0; c < nc / 3; ++c) {
+        double f[3], lh[3];
+        for (int k = 0; k < 3; ++k) {
+          lh[k] = fma(alpha, o->x[lcs + 3 * c + k], (1.0 - alpha) * o->lambda_c_bar[3 * c + k]);
+          f[k] = lh[k] + o->mu_lambda_c[3 * c + k];
+        }
+        fccqp_oracle_project_cone3(f, mu[c], o->lambda_c_bar + 3 * c);
+        for (int k = 0; k < 3; ++k) o->lambda_c_res[3 * c + k] = lh[k] - o->lambda_c_bar[3 * c + k];
+      }
     }
-    for (int i = 0; i < n; ++i) o->x_res[i] = o->x[i] - o->x_bar[i];
-    for (int i = 0; i < nc; ++i) o->lambda_c_res[i] = o->x[lcs + i] - o->lambda_c_bar[i];
     o->x_res_norm = inf_norm_like_reference(o->x_res, n);
     o->lambda_c_res_norm = inf_norm_like_reference(o->lambda_c_res, nc);
 

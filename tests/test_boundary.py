@@ -30,11 +30,12 @@ def test_header_symbols_exported(nat):
 
 
 def test_struct_layout_matches_header(nat):
-    # fccqp_options: 2 x int32 + 3 x double; fccqp_details: 2 x int32 + 6 x double
-    assert C.sizeof(nat.Options) == 32 and C.sizeof(nat.Details) == 56
+    # fccqp_options: 2 x int32 + 4 x double (ABI 2: + relaxation); fccqp_details: 2 x int32 + 6 x double
+    assert C.sizeof(nat.Options) == 40 and C.sizeof(nat.Details) == 56
     o = nat.Options()
     nat.lib().fccqp_default_options(C.byref(o))
     assert (o.max_iter, o.rho, o.eps_fcone, o.eps_bound) == (1000, 1e-6, 1e-3, 1e-6)  # src/fcc_qp.hpp:30-35
+    assert o.relaxation == 1.0                                                        # extension: 1 = the reference
 
 
 def _has_gpu(nat):
