@@ -147,7 +147,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "QP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -337,11 +337,28 @@ def run_ours(args):
                                     "sample": f"first {sample} QPs of the same tiled log, cold, solved {reps}x, {tot:.1f} s"}
         except Exception as e:  # pragma: no cover
             line["cpu_baseline"] = {"value": None, "unit": "QP/s", "cores": 0, "kind": "port", "sample": repr(e)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of the contract, on the process's real stdout."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # Only the JSON line may reach stdout: library banners (e.g. "NCCL version ..." at communicator
+    # creation) are written to file descriptor 1 behind Python's back, so fd 1 is pointed at stderr for
+    # the whole run and the line goes to a private duplicate of the original stdout.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
