@@ -14,7 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # FCCQP_LIB: developer override (e.g. an instrumented -DFCCQP_DEV build of the same sources)
 LIB_PATH = os.environ.get("FCCQP_LIB") or os.path.join(_HERE, "libfccqp_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
+STRUCTURE_AUTO, STRUCTURE_DENSE, STRUCTURE_CAPS = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
 STATUS_SUCCESS, STATUS_MAX_ITERATIONS, STATUS_NUMERICAL_ISSUE = 0, 1, 2
 E_INVALID, E_CUDA, E_UNSUPPORTED = -1, -2, -3
@@ -61,6 +62,7 @@ class BatchDesc(C.Structure):
         ("bounds_viol", C.c_void_p), ("fcone_viol", C.c_void_p),
         ("stream", C.c_void_p),
         ("device_seconds", _dp),
+        ("structure", C.c_int32), ("struct_caps", C.c_int32 * 3),
     ]
 
 
@@ -92,6 +94,7 @@ EXPORTS = [
     "fccqp_get_solution", "fccqp_get_warm_state", "fccqp_set_warm_state", "fccqp_batch_solve",
     "fccqp_release_workspaces", "fccqp_kernel_launch_count", "fccqp_last_launch_info",
     "fccqp_alloc_pinned", "fccqp_free_pinned", "fccqp_wbc_assemble",
+    "fccqp_last_struct_info", "fccqp_set_structure",
 ]
 
 _lib = None
@@ -125,6 +128,8 @@ def lib() -> C.CDLL:
     L.fccqp_batch_solve.argtypes = [C.POINTER(BatchDesc)]
     L.fccqp_kernel_launch_count.restype = C.c_int64
     L.fccqp_last_launch_info.argtypes = [_ip, _ip, _ip, _ip]
+    L.fccqp_last_struct_info.argtypes = [_ip, _ip, _ip, _ip, _ip]
+    L.fccqp_set_structure.argtypes = [C.c_void_p, C.c_int]
     L.fccqp_alloc_pinned.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     L.fccqp_free_pinned.argtypes = [C.c_void_p]
     L.fccqp_wbc_assemble.argtypes = [C.POINTER(WbcDesc)]
@@ -141,6 +146,16 @@ def last_launch_info() -> dict:
     g, b, s, c = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
     lib().fccqp_last_launch_info(C.byref(g), C.byref(b), C.byref(s), C.byref(c))
     return dict(grid=g.value, block=b.value, smem_bytes=s.value, ctas_per_sm=c.value)
+
+
+def last_struct_info() -> dict:
+    """What the last batch launch did about problem structure (``fccqp_last_struct_info``); ``deferred`` is
+    valid once the stream of that call has been synchronised."""
+    used, rows, dense, deferred = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+    caps = (C.c_int32 * 3)()
+    lib().fccqp_last_struct_info(C.byref(used), caps, C.byref(rows), C.byref(dense), C.byref(deferred))
+    return dict(used=bool(used.value), caps=tuple(int(c) for c in caps), rows=rows.value, rows_dense=dense.value,
+                deferred=deferred.value)
 
 
 def pinned_empty(shape, dtype):

@@ -73,6 +73,12 @@ class FCCQPBatch:
             raise ValueError("precision must be 'fp64' or 'fp32_data'")
         self.precision = precision
         self.options = FCCQPOptionsB()
+        # Problem structure (include/fccqp.h, fccqp_structure): "auto" sizes the structure-exploiting kernel from a
+        # probe of the batch -- for device tensors on the first Solve() only (one stream synchronisation), the
+        # bounds found are reused afterwards (QPs beyond them still run, on the general kernel, and the probe is
+        # repeated when many do); "probe" probes on every call; "dense" never reduces; a 3-tuple gives the bounds.
+        self.structure = "auto"
+        self._caps = None
         self.warm_start = False
         self.time_kernel = True
         self._state = None     # (x, mu_x, mu_c) arrays / tensors
@@ -140,7 +146,33 @@ class FCCQPBatch:
         d.device, d.memory_space, d.precision = self.device, mem, (1 if self.precision == "fp32_data" else 0)
         o = self.options
         d.options = nat.Options(int(o.max_iter), 0, float(o.rho), float(o.eps_fcone), float(o.eps_bound), float(o.relaxation))
+        st = self.structure
+        if st == "dense":
+            d.structure = nat.STRUCTURE_DENSE
+        elif isinstance(st, (tuple, list)):
+            d.structure = nat.STRUCTURE_CAPS
+            d.struct_caps[:] = [int(c) for c in st]
+        elif st == "auto" and mem == nat.MEM_DEVICE and self._caps is not None:
+            d.structure = nat.STRUCTURE_CAPS
+            d.struct_caps[:] = list(self._caps)
+        elif st in ("auto", "probe"):
+            d.structure = nat.STRUCTURE_AUTO
+        else:
+            raise ValueError("structure must be 'auto', 'probe', 'dense' or a (nr, ndp, nd0) tuple")
         return d
+
+    def _after_device_call(self, B: int, probed: bool):
+        """Bookkeeping of the cached structure bounds ("auto" with device tensors)."""
+        if self.structure != "auto":
+            return
+        info = nat.last_struct_info()
+        if probed:
+            self._caps = info["caps"] if info["used"] else (self.n, 0, 0)   # (n, 0, 0): nothing to reduce
+        self._check_deferred = info["used"]
+
+    def structure_info(self) -> dict:
+        """``fccqp_last_struct_info`` of the last launch of this process (synchronise first for ``deferred``)."""
+        return nat.last_struct_info()
 
     def _check_shapes(self, shp, B):
         n, m, nc = self.n, self.m, self.nc
@@ -248,7 +280,12 @@ class FCCQPBatch:
         n_iter = torch.empty(B, dtype=torch.int32, device=dev)
         status = torch.empty(B, dtype=torch.int32, device=dev)
         res = torch.empty((4, B), dtype=torch.float64, device=dev)
+        if self.structure == "auto" and self._caps is not None and getattr(self, "_check_deferred", False):
+            # the previous launch has long been consumed by now: many QPs beyond the cached bounds -> probe again
+            if nat.last_struct_info()["deferred"] > B // 16:
+                self._caps = None
         d = self._desc(B, nat.MEM_DEVICE)
+        probed = d.structure == nat.STRUCTURE_AUTO
         d.warm_start = int(warm)
         bs = lambda a, full_ndim: int(a.stride(0)) if a.dim() == full_ndim and B > 1 else (
             int(a.stride(0)) if a.dim() == full_ndim else 0)
@@ -271,6 +308,7 @@ class FCCQPBatch:
         with torch.cuda.device(dev):
             nat.check(nat.lib().fccqp_batch_solve(C.byref(d)))
         wall = time.perf_counter() - t0
+        self._after_device_call(B, probed)
         # keep the inputs alive until the (possibly asynchronous) launch has consumed them
         self._keepalive = (Q, b, A_eq, b_eq, mu, lb, ub)
         self._state = (x, mux, muc)

@@ -19,6 +19,7 @@
 
 #include "../../include/fccqp.h"
 #include "fccqp_kernel.cuh"
+#include "fccqp_struct.cuh"
 
 namespace {
 
@@ -26,7 +27,16 @@ thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 struct LaunchInfo { int grid = 0, block = 0, smem = 0, ctas_per_sm = 0; };
 LaunchInfo g_last_launch;
+// what the last batch launch did about problem structure (fccqp_last_struct_info)
+struct StructInfo { int used = 0, nr = 0, ndp = 0, nd0 = 0, rows = 0, rows_dense = 0, device = 0; };
+StructInfo g_last_struct;
 std::mutex g_info_mu;
+
+// How launch_solve decides about the structure-exploiting kernel (fccqp_batch_desc::structure).
+struct StructHint {
+  int mode = FCCQP_STRUCTURE_AUTO;   // AUTO: probe on the device (one tiny kernel + a stream sync); DENSE: never; CAPS: given
+  int caps[3] = {0, 0, 0};           // nr, ndp, nd0
+};
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -46,25 +56,22 @@ int fail(int code, const char* fmt, ...) {
                   __FILE__, __LINE__);                                                       \
   } while (0)
 
-constexpr int kCounterRing = 256;
-
 // Per-device context: properties, work counters, global scratch, host-path staging.
 struct DeviceCtx {
   int device = -1;
   int num_sms = 0;
   int max_smem_optin = 0;
   int clock_khz = 0;
-  unsigned int* counters = nullptr;
-  int next_counter = 0;
   // host-path staging (grow only)
   char* stage = nullptr;
   size_t stage_bytes = 0;
   cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // pinned bounce buffer for outputs whose destination is pageable host memory (grow only)
   char* hstage = nullptr;
   size_t hstage_bytes = 0;
   cudaEvent_t chunk_ev[16] = {};
+  unsigned int* h_deferred = nullptr;   // pinned: QPs the structure-exploiting kernel handed to the general one (last launch)
+  int* h_probe = nullptr;               // pinned [4]: result of the structure probe
   std::mutex mu;       // guards counters / gscratch / occupancy cache
   std::mutex host_mu;  // serialises FCCQP_MEM_HOST calls (they share the staging buffer)
   std::map<std::pair<const void*, size_t>, int> occupancy;  // (kernel, smem) -> CTAs/SM
@@ -89,7 +96,6 @@ int get_ctx(int device, DeviceCtx** out) {
   CUDA_TRY(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device));
   CUDA_TRY(cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   CUDA_TRY(cudaDeviceGetAttribute(&ctx->clock_khz, cudaDevAttrClockRate, device));
-  CUDA_TRY(cudaMalloc(&ctx->counters, kCounterRing * sizeof(unsigned int)));
   {
     // stream-ordered scratch (cudaMallocAsync in the shared-structure path) stays in the pool across
     // synchronisation points instead of going back to the OS after every call
@@ -101,9 +107,10 @@ int get_ctx(int device, DeviceCtx** out) {
     cudaGetLastError();
   }
   for (auto& s : ctx->streams) CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-  CUDA_TRY(cudaEventCreate(&ctx->ev0));
-  CUDA_TRY(cudaEventCreate(&ctx->ev1));
   for (auto& e : ctx->chunk_ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CUDA_TRY(cudaMallocHost(&ctx->h_deferred, sizeof(unsigned int)));
+  *ctx->h_deferred = 0;
+  CUDA_TRY(cudaMallocHost(&ctx->h_probe, 4 * sizeof(int)));
   *out = ctx.get();
   g_ctx[device] = std::move(ctx);
   return FCCQP_OK;
@@ -138,9 +145,48 @@ int pick_kernel(const DeviceCtx& ctx, int n, int m, int nc, KernelFn* fn, int* t
   return FCCQP_OK;
 }
 
+// Structure-exploiting kernel instances (fccqp_struct.cuh): threads >= max(n, padded reduced KKT size).
+int pick_struct_kernel(const fccqp::StructLayout& sl, int n, KernelFn* fn, int* threads) {
+  const int need = n > sl.N8c ? n : sl.N8c;
+  if (need <= 64) { *threads = 64; *fn = (KernelFn)fccqp::fccqp_struct_kernel<64, 8>; }
+  else if (need <= 96) { *threads = 96; *fn = (KernelFn)fccqp::fccqp_struct_kernel<96, 5>; }
+  else if (need <= 128) { *threads = 128; *fn = (KernelFn)fccqp::fccqp_struct_kernel<128, 4>; }
+  else if (need <= 256) { *threads = 256; *fn = (KernelFn)fccqp::fccqp_struct_kernel<256, 2>; }
+  else return 1;
+  return 0;
+}
+
+// Host-side twin of fccqp::struct_classify for callers whose data is in host memory (no probe launch,
+// no stream sync): counts of one QP.  Returns false for a structurally singular QP.
+bool host_classify(int n, int m, const double* Q, long long q_rs, long long q_cs, const double* A, long long a_rs,
+                   long long a_cs, int* nr, int* ndp, int* nd0) {
+  std::vector<int> rowcnt(m > 0 ? m : 1, 0), one_row(n, -1);
+  std::vector<char> type(n, 0);
+  bool ok = true;
+  for (int j = 0; j < n; ++j) {
+    bool sep = true;
+    for (int i = 0; i < n && sep; ++i)
+      if (i != j && (Q[i * q_rs + j * q_cs] != 0.0 || Q[j * q_rs + i * q_cs] != 0.0)) sep = false;
+    const double qd = Q[j * q_rs + j * q_cs];
+    int nnz = 0, kr = 0;
+    for (int k = 0; k < m; ++k) if (A[k * a_rs + j * a_cs] != 0.0) { ++nnz; kr = k; }
+    if (!sep || !(qd >= 0.0)) type[j] = fccqp::VT_R;
+    else if (qd < 1e-200) { type[j] = fccqp::VT_D0; if (nnz == 0) ok = false; }
+    else if (nnz <= 1) { type[j] = fccqp::VT_D1; if (nnz == 1) { one_row[j] = kr; ++rowcnt[kr]; } }
+    else type[j] = fccqp::VT_DP;
+  }
+  *nr = *ndp = *nd0 = 0;
+  for (int j = 0; j < n; ++j) {
+    if (type[j] == fccqp::VT_D1 && one_row[j] >= 0 && rowcnt[one_row[j]] > 1) type[j] = fccqp::VT_DP;
+    if (type[j] == fccqp::VT_R) ++*nr; else if (type[j] == fccqp::VT_DP) ++*ndp; else if (type[j] == fccqp::VT_D0) ++*nd0;
+  }
+  return ok;
+}
+
 // Launches the fused solve on `stream` for device-resident data described by p
-// (work_counter / gscratch are filled in here).
-int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool in_f32 = false) {
+// (work counters / device-side lists are allocated here, stream-ordered).
+int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool in_f32 = false,
+                 const StructHint* hint_in = nullptr) {
   if (p.B == 0) return FCCQP_OK;
   KernelFn fn, fn_shared, fn_f32; int threads; size_t smem;
   int rc = pick_kernel(ctx, p.n, p.m, p.nc, &fn, &threads, &smem, &fn_shared, &fn_f32);
@@ -154,37 +200,60 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool
   // developer switch: ADMM iteration at which long-running QPs complete inv(L) (huge value = never)
   static const int fia = getenv("FCCQP_FULL_INVERSE_AT") ? atoi(getenv("FCCQP_FULL_INVERSE_AT")) : 8;
   p.full_inverse_at = fia < 1 ? 1 : fia;
-  int ctas_per_sm = 0;
-  unsigned int* counter2 = nullptr;
-  {
+  // developer switch (read per call, tests toggle it): 0 = no iterative refinement of the reduced cold pre-solve
+  p.struct_refine = getenv("FCCQP_STRUCT_REFINE") ? atoi(getenv("FCCQP_STRUCT_REFINE")) : 1;
+  auto occupancy_of = [&](KernelFn f, int thr, size_t sm, int* out) -> int {
     std::lock_guard<std::mutex> lk(ctx.mu);
-    const auto key = std::make_pair((const void*)fn, smem);
+    const auto key = std::make_pair((const void*)f, sm);
     auto it = ctx.occupancy.find(key);
-    if (it == ctx.occupancy.end()) {
-      // the attribute is per kernel, the smem size per (n, m, nc): raise it to the device maximum once
-      CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx.max_smem_optin));
-      if (!f32) CUDA_TRY(cudaFuncSetAttribute(fn_shared, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx.max_smem_optin));
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, fn, threads, smem));
-      if (ctas_per_sm < 1) return fail(FCCQP_E_UNSUPPORTED, "kernel does not fit on an SM (smem %zu B)", smem);
-      ctx.occupancy[key] = ctas_per_sm;
-    } else {
-      ctas_per_sm = it->second;
-    }
-    p.work_counter = ctx.counters + ctx.next_counter;
-    ctx.next_counter = (ctx.next_counter + 1) % kCounterRing;
-    counter2 = ctx.counters + ctx.next_counter;   // second launch of the shared-structure path
-    ctx.next_counter = (ctx.next_counter + 1) % kCounterRing;
-  }
+    if (it != ctx.occupancy.end()) { *out = it->second; return FCCQP_OK; }
+    // the attribute is per kernel, the smem size per problem shape: raise it to the device maximum once
+    CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx.max_smem_optin));
+    int c = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, f, thr, sm));
+    if (c < 1) return fail(FCCQP_E_UNSUPPORTED, "kernel does not fit on an SM (smem %zu B)", sm);
+    ctx.occupancy[key] = c;
+    *out = c;
+    return FCCQP_OK;
+  };
+  int ctas_per_sm = 0;
+  if ((rc = occupancy_of(fn, threads, smem, &ctas_per_sm))) return rc;
   static const int cta_cap = getenv("FCCQP_CTAS_PER_SM") ? atoi(getenv("FCCQP_CTAS_PER_SM")) : 0;  // developer aid
   if (cta_cap > 0 && cta_cap < ctas_per_sm) ctas_per_sm = cta_cap;
   int grid = ctas_per_sm * ctx.num_sms;
   if (grid > p.B) grid = p.B;
-  CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned int), stream));
+
+  // Stream-ordered scratch of this call: [0] work counter, [1] second work counter, [2] length of the
+  // device-side QP list, [3] spare, [4..7] structure probe, [8..8+B) the list.  One allocation per call, so
+  // any number of calls may be in flight on any number of streams.
+  unsigned int* scr = nullptr;
+  CUDA_TRY(cudaMallocAsync(&scr, ((size_t)p.B + 8) * sizeof(unsigned int), stream));
+  CUDA_TRY(cudaMemsetAsync(scr, 0, 8 * sizeof(unsigned int), stream));
+  p.work_counter = scr;
+  unsigned int* const counter2 = scr + 1;
+  unsigned int* const list_count = scr + 2;
+  int* const list = reinterpret_cast<int*>(scr + 8);
+  auto finish = [&](int launches, const LaunchInfo& li, const StructInfo& si) -> int {
+    CUDA_TRY(cudaFreeAsync(scr, stream));
+    g_launches.fetch_add(launches);
+    std::lock_guard<std::mutex> lk(g_info_mu);
+    g_last_launch = li;
+    g_last_struct = si;
+    return FCCQP_OK;
+  };
+  StructInfo no_struct;
+  no_struct.rows = no_struct.rows_dense = p.lay.N8;
+  no_struct.device = ctx.device;
+
   // Shared-structure batches (one Q and one A_eq for the whole batch, cold): two launches, each with
   // its KKT factorization cached per CTA (SolveParams::shared_mode).  Worth it once every CTA sees
   // several QPs; FCCQP_NO_SHARED=1 forces the general path (tests compare the two).
   static const bool no_shared = getenv("FCCQP_NO_SHARED") != nullptr;
   const bool shared_structure = !no_shared && !f32 && p.q_bs == 0 && (p.m == 0 || p.a_bs == 0) && p.B >= 4 * ctas_per_sm * ctx.num_sms;
+  if (shared_structure) {
+    int c2 = 0;
+    if ((rc = occupancy_of(fn_shared, threads, smem, &c2))) return rc;
+  }
   if (shared_structure && p.warm) {
     // warm shared-structure batch (an MPC loop re-solving around one linearisation with carried duals):
     // no pre-solve, so ONE launch of the ADMM mode over all QPs with the rho-KKT operator cached per CTA
@@ -192,25 +261,13 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool
     b.shared_mode = 2;
     fn_shared<<<grid, threads, smem, stream>>>(b);
     CUDA_TRY(cudaGetLastError());
-    g_launches.fetch_add(1);
-    {
-      std::lock_guard<std::mutex> lk(g_info_mu);
-      g_last_launch = {grid, threads, (int)smem, ctas_per_sm};
-    }
-    return FCCQP_OK;
+    return finish(1, {grid, threads, (int)smem, ctas_per_sm}, no_struct);
   }
-  unsigned int* scratch = nullptr;   // [0] = pending count, [1..B] = pending QP indices
-  if (shared_structure && cudaMallocAsync(&scratch, ((size_t)p.B + 1) * sizeof(unsigned int), stream) != cudaSuccess) {
-    cudaGetLastError();                // no stream-ordered allocator here: the general path below still applies
-    scratch = nullptr;
-  }
-  if (shared_structure && scratch) {
-    CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(unsigned int), stream));
-    CUDA_TRY(cudaMemsetAsync(counter2, 0, sizeof(unsigned int), stream));
+  if (shared_structure) {
     fccqp::SolveParams a = p;
     a.shared_mode = 1;
-    a.pending_count = scratch;
-    a.pending_list = reinterpret_cast<int*>(scratch + 1);
+    a.pending_count = list_count;
+    a.pending_list = list;
     static const bool timing = getenv("FCCQP_SHARED_TIMING") != nullptr;   // developer aid: per-launch times
     cudaEvent_t te[3] = {nullptr, nullptr, nullptr};
     if (timing) { for (auto& e : te) CUDA_TRY(cudaEventCreate(&e)); CUDA_TRY(cudaEventRecord(te[0], stream)); }
@@ -219,15 +276,15 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool
     if (timing) CUDA_TRY(cudaEventRecord(te[1], stream));
     fccqp::SolveParams b = p;
     b.shared_mode = 2;
-    b.count_dev = scratch;
-    b.index_list = reinterpret_cast<const int*>(scratch + 1);
+    b.count_dev = list_count;
+    b.index_list = list;
     b.work_counter = counter2;
     fn_shared<<<grid, threads, smem, stream>>>(b);
     CUDA_TRY(cudaGetLastError());
     if (timing) {
       unsigned int pending = 0;
       CUDA_TRY(cudaEventRecord(te[2], stream));
-      CUDA_TRY(cudaMemcpyAsync(&pending, scratch, sizeof(pending), cudaMemcpyDeviceToHost, stream));
+      CUDA_TRY(cudaMemcpyAsync(&pending, list_count, sizeof(pending), cudaMemcpyDeviceToHost, stream));
       CUDA_TRY(cudaEventSynchronize(te[2]));
       CUDA_TRY(cudaStreamSynchronize(stream));
       float m1 = 0.f, m2 = 0.f;
@@ -235,14 +292,67 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool
       fprintf(stderr, "[fccqp shared] B=%d pre-solve launch %.3f ms, ADMM launch %.3f ms over %u QPs\n", p.B, m1, m2, pending);
       for (auto& e : te) cudaEventDestroy(e);
     }
-    CUDA_TRY(cudaFreeAsync(scratch, stream));
-    g_launches.fetch_add(2);
-    {
-      std::lock_guard<std::mutex> lk(g_info_mu);
-      g_last_launch = {grid, threads, (int)smem, ctas_per_sm};
-    }
-    return FCCQP_OK;
+    return finish(2, {grid, threads, (int)smem, ctas_per_sm}, no_struct);
   }
+
+  // ---- structure-exploiting kernel (fccqp_struct.cuh): QPs whose separable variables can be eliminated
+  // analytically run on a reduced KKT system; the others (if any) are appended to a device-side list and
+  // taken by the general kernel in a second launch.
+  const bool no_struct_env = getenv("FCCQP_NO_STRUCT") != nullptr;   // developer switch, read per call
+  StructHint hint;
+  if (hint_in) hint = *hint_in;
+  static const bool dev_instr = getenv("FCCQP_PROFILE") != nullptr || getenv("FCCQP_TRACE") != nullptr;
+  if (!no_struct_env && !dev_instr && !f32 && hint.mode != FCCQP_STRUCTURE_DENSE && p.n <= 256 && p.m <= 256 && p.m > 0) {
+    int caps[3] = {hint.caps[0], hint.caps[1], hint.caps[2]};
+    bool ok = true;
+    if (hint.mode != FCCQP_STRUCTURE_CAPS) {
+      // probe: classify up to 128 QPs spread over the batch, take the largest structure seen
+      const int ns = p.B < 128 ? p.B : 128;
+      int* d_probe = reinterpret_cast<int*>(scr + 4);
+      if (p.n <= 128 && p.m <= 128) fccqp::fccqp_struct_probe_kernel<128><<<ns, 128, 0, stream>>>(p, ns, d_probe);
+      else fccqp::fccqp_struct_probe_kernel<256><<<ns, 256, 0, stream>>>(p, ns, d_probe);
+      CUDA_TRY(cudaGetLastError());
+      int h[4] = {0, 0, 0, 0};
+      {
+        std::lock_guard<std::mutex> lk(ctx.mu);   // the pinned landing pad is per device
+        CUDA_TRY(cudaMemcpyAsync(ctx.h_probe, d_probe, sizeof(h), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        memcpy(h, ctx.h_probe, sizeof(h));
+      }
+      g_launches.fetch_add(1);
+      caps[0] = h[0]; caps[1] = h[1]; caps[2] = h[2];
+      ok = h[3] == 0;
+    }
+    if (ok && caps[0] >= 0 && caps[0] <= p.n && caps[1] >= 0 && caps[2] >= 0 && caps[0] + caps[1] + caps[2] <= p.n) {
+      fccqp::StructLayout sl(p.n, p.m, p.nc, caps[0], caps[1], caps[2]);
+      KernelFn sfn = nullptr; int sthreads = 0;
+      // worth it when at least one tile row of the KKT matrix goes away
+      if (sl.N8c + 8 <= p.lay.N8 && sl.bytes() <= (size_t)ctx.max_smem_optin && pick_struct_kernel(sl, p.n, &sfn, &sthreads) == 0) {
+        int sctas = 0;
+        if ((rc = occupancy_of(sfn, sthreads, sl.bytes(), &sctas))) return rc;
+        if (cta_cap > 0 && cta_cap < sctas) sctas = cta_cap;
+        int sgrid = sctas * ctx.num_sms;
+        if (sgrid > p.B) sgrid = p.B;
+        fccqp::SolveParams a = p;
+        a.slay = sl;
+        a.pending_count = list_count;
+        a.pending_list = list;
+        sfn<<<sgrid, sthreads, sl.bytes(), stream>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        fccqp::SolveParams b = p;
+        b.count_dev = list_count;
+        b.index_list = list;
+        b.work_counter = counter2;
+        fn<<<grid, threads, smem, stream>>>(b);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(ctx.h_deferred, list_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+        StructInfo si;
+        si.used = 1; si.nr = caps[0]; si.ndp = caps[1]; si.nd0 = caps[2]; si.rows = sl.N8c; si.rows_dense = p.lay.N8; si.device = ctx.device;
+        return finish(2, {sgrid, sthreads, (int)sl.bytes(), sctas}, si);
+      }
+    }
+  }
+
   static const bool profile = getenv("FCCQP_PROFILE") != nullptr;  // developer aid: phase cycle counters
   unsigned long long* d_prof = nullptr;
   if (profile) {
@@ -287,12 +397,7 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool
       fprintf(stderr, "   %-14s %10.0f cyc/QP  %5.1f%%\n", names[i], h[14] ? (double)h[i] / (double)h[14] : 0.0,
               tot > 0 ? 100.0 * (double)h[i] / tot : 0.0);
   }
-  g_launches.fetch_add(1);
-  {
-    std::lock_guard<std::mutex> lk(g_info_mu);
-    g_last_launch = {grid, threads, (int)smem, ctas_per_sm};
-  }
-  return FCCQP_OK;
+  return finish(1, {grid, threads, (int)smem, ctas_per_sm}, no_struct);
 }
 
 int check_dims(int n, int m, int nc, int lcs) {
@@ -323,6 +428,7 @@ struct fccqp_solver {
   int n, m, nc, lcs, device;
   fccqp_options opt;
   int warm = 0;
+  int structure = FCCQP_STRUCTURE_AUTO;
   bool has_state = false;  // a Solve has happened (x_ is meaningful)
   DeviceCtx* ctx = nullptr;
   cudaStream_t stream = nullptr;
@@ -357,6 +463,23 @@ int fccqp_device_count(void) {
   return c;
 }
 int64_t fccqp_kernel_launch_count(void) { return g_launches.load(); }
+int fccqp_last_struct_info(int* used, int* caps, int* rows, int* rows_dense, int* deferred) {
+  StructInfo si;
+  { std::lock_guard<std::mutex> lk(g_info_mu); si = g_last_struct; }
+  if (used) *used = si.used;
+  if (caps) { caps[0] = si.nr; caps[1] = si.ndp; caps[2] = si.nd0; }
+  if (rows) *rows = si.rows;
+  if (rows_dense) *rows_dense = si.rows_dense;
+  if (deferred) {
+    *deferred = 0;
+    if (si.used) {
+      std::lock_guard<std::mutex> lk(g_ctx_mu);
+      auto it = g_ctx.find(si.device);
+      if (it != g_ctx.end() && it->second->h_deferred) *deferred = (int)*it->second->h_deferred;
+    }
+  }
+  return FCCQP_OK;
+}
 int fccqp_last_launch_info(int* grid, int* block, int* smem_bytes, int* ctas_per_sm) {
   std::lock_guard<std::mutex> lk(g_info_mu);
   if (grid) *grid = g_last_launch.grid;
@@ -449,6 +572,13 @@ int fccqp_set_warm_start(fccqp_handle h, int warm) {
   h->warm = warm != 0;
   return FCCQP_OK;
 }
+int fccqp_set_structure(fccqp_handle h, int structure) {
+  if (!h) return fail(FCCQP_E_INVALID, "null handle");
+  if (structure != FCCQP_STRUCTURE_AUTO && structure != FCCQP_STRUCTURE_DENSE)
+    return fail(FCCQP_E_INVALID, "structure must be FCCQP_STRUCTURE_AUTO or FCCQP_STRUCTURE_DENSE");
+  h->structure = structure;
+  return FCCQP_OK;
+}
 int fccqp_contact_vars_start(fccqp_handle h) { return h ? h->lcs : -1; }
 
 int fccqp_solve(fccqp_handle h, const double* Q, ptrdiff_t q_rs, ptrdiff_t q_cs, const double* b,
@@ -508,7 +638,13 @@ int fccqp_solve(fccqp_handle h, const double* Q, ptrdiff_t q_rs, ptrdiff_t q_cs,
   p.n_iter = h->d_iout; p.status = h->d_iout + 1;
   p.res_b = h->d_out; p.res_f = h->d_out + 1; p.bviol = h->d_out + 2; p.fviol = h->d_out + 3;
   p.cycles = h->d_cycles;
-  int rc = launch_solve(*h->ctx, p, h->stream);
+  // the data is right here on the host: classify it here (no probe launch, no extra synchronisation)
+  StructHint hint;
+  hint.mode = FCCQP_STRUCTURE_DENSE;
+  if (h->structure == FCCQP_STRUCTURE_AUTO && m > 0 &&
+      host_classify(n, m, sQ, n, 1, sA, k_a_rs, k_a_cs, &hint.caps[0], &hint.caps[1], &hint.caps[2]))
+    hint.mode = FCCQP_STRUCTURE_CAPS;
+  int rc = launch_solve(*h->ctx, p, h->stream, false, &hint);
   if (rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(h->h_out, h->d_x, sizeof(double) * (n + 8), cudaMemcpyDeviceToHost, h->stream));   // packed outputs
   CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -610,14 +746,25 @@ int fccqp_batch_solve(const fccqp_batch_desc* desc) {
     p.n_iter = d.n_iter; p.status = d.status;
     p.res_b = d.res_bounds; p.res_f = d.res_fcone; p.bviol = d.bounds_viol; p.fviol = d.fcone_viol;
     cudaStream_t st = (cudaStream_t)d.stream;
-    if (d.device_seconds) CUDA_TRY(cudaEventRecord(ctx->ev0, st));
-    rc = launch_solve(*ctx, p, st, d.precision == FCCQP_PRECISION_FP32_DATA);
-    if (rc) return rc;
+    StructHint hint;
+    hint.mode = d.structure;
+    hint.caps[0] = d.struct_caps[0]; hint.caps[1] = d.struct_caps[1]; hint.caps[2] = d.struct_caps[2];
+    // timing events are per call: concurrent callers on one device must not share them
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (d.device_seconds) {
-      CUDA_TRY(cudaEventRecord(ctx->ev1, st));
-      CUDA_TRY(cudaEventSynchronize(ctx->ev1));
+      CUDA_TRY(cudaEventCreate(&ev0));
+      CUDA_TRY(cudaEventCreate(&ev1));
+      CUDA_TRY(cudaEventRecord(ev0, st));
+    }
+    rc = launch_solve(*ctx, p, st, d.precision == FCCQP_PRECISION_FP32_DATA, &hint);
+    if (rc) { if (ev0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); } return rc; }
+    if (d.device_seconds) {
       float ms = 0.f;
-      CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+      cudaError_t e = cudaEventRecord(ev1, st);
+      if (e == cudaSuccess) e = cudaEventSynchronize(ev1);
+      if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ev0, ev1);
+      cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+      if (e != cudaSuccess) return fail(FCCQP_E_CUDA, "event timing failed: %s", cudaGetErrorString(e));
       *d.device_seconds = 1e-3 * ms;
     }
     return FCCQP_OK;
@@ -705,6 +852,27 @@ int fccqp_batch_solve(const fccqp_batch_desc* desc) {
   struct Pending { int chunk; void* dst; const void* src; size_t bytes; };
   std::vector<Pending> pending;
 
+  // structure of the batch, from the host copy of the data (a sample of up to 64 QPs; no device probe,
+  // no synchronisation inside the chunk pipeline)
+  StructHint hint;
+  hint.mode = d.structure;
+  hint.caps[0] = d.struct_caps[0]; hint.caps[1] = d.struct_caps[1]; hint.caps[2] = d.struct_caps[2];
+  if (hint.mode == FCCQP_STRUCTURE_AUTO) {
+    hint.mode = FCCQP_STRUCTURE_DENSE;
+    if (es == sizeof(double) && m > 0 && !(q_shared && a_shared)) {
+      const int ns = B < 64 ? B : 64;
+      bool ok = true;
+      for (int sidx = 0; sidx < ns && ok; ++sidx) {
+        const long long qp = ns > 1 ? (long long)sidx * (B - 1) / (ns - 1) : 0;
+        int c[3];
+        ok = host_classify(n, m, d.Q + (q_shared ? 0 : qp * (long long)n * n), d.q_row_stride, d.q_col_stride,
+                           d.A_eq + (a_shared ? 0 : qp * (long long)m * n), d.a_row_stride, d.a_col_stride, &c[0], &c[1], &c[2]);
+        for (int k = 0; k < 3; ++k) if (c[k] > hint.caps[k]) hint.caps[k] = c[k];
+      }
+      if (ok) hint.mode = FCCQP_STRUCTURE_CAPS;
+    }
+  }
+
   int nchunks = (B + 4095) / 4096;
   if (nchunks > 16) nchunks = 16;
   if (nchunks < 1) nchunks = 1;
@@ -744,7 +912,7 @@ int fccqp_batch_solve(const fccqp_batch_desc* desc) {
     p.n_iter = d_niter + lo; p.status = d_status + lo;
     double* res = dp(sres);
     p.res_b = res + lo; p.res_f = res + (size_t)B + lo; p.bviol = res + 2 * (size_t)B + lo; p.fviol = res + 3 * (size_t)B + lo;
-    rc = launch_solve(*ctx, p, st, es == sizeof(float));
+    rc = launch_solve(*ctx, p, st, es == sizeof(float), &hint);
     if (rc) return rc;
     // D2H: straight into the caller's buffer when it is page-locked (a true asynchronous DMA);
     // otherwise into the pinned bounce buffer, copied out below once the chunk's event has fired

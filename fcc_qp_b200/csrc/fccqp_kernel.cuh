@@ -93,6 +93,70 @@ struct Layout {
   size_t bytes() const { return (size_t)doubles_total * sizeof(double); }
 };
 
+// Shared-memory carve-up of the structure-exploiting kernel (fccqp_struct.cuh), sized by CAPS on the
+// per-QP structure: nr (variables whose Q row has off-diagonal entries -- they stay in the KKT
+// system), ndp (separable variables, i.e. diagonal-only Q rows with positive cost, whose A_eq column has
+// two or more entries -- eliminated analytically, column kept as tiles), nd0 (separable variables
+// with zero cost -- kept as the trailing block of the KKT system).  Separable variables with an
+// empty or one-entry A_eq column cost no storage at all.  QPs that exceed the caps are handed to the
+// general kernel.
+struct StructLayout {
+  int n, m, nc;
+  int n8, m8, mt;
+  int nr8c, ndp8c, dptc, nd08c;
+  int N8c, NBc, NB32c, NTc, NBTc;
+  int off_M, off_AP, off_dinv, off_dneg, off_tbuf, off_ybuf, off_sred, off_rf, off_vd, off_hinv, off_d1c, off_beq;
+  int off_qd, off_xs, off_lcbar, off_muc, off_mu, off_red, off_int;
+  // int region (offsets in ints from off_int)
+  int io_vtype, io_vpos, io_rlist, io_dplist, io_d0list, io_d1var, io_rowcnt, io_sepf, io_wtot, ints_total;
+  int doubles_total;
+  static inline int up2(int v) { return (v + 1) & ~1; }
+  static inline int up8(int v) { return (v + 7) & ~7; }
+  StructLayout() = default;
+  StructLayout(int n_, int m_, int nc_, int nr_cap, int ndp_cap, int nd0_cap) {
+    n = n_; m = m_; nc = nc_;
+    n8 = up8(n); m8 = up8(m); mt = m8 >> 3;
+    nr8c = up8(nr_cap); ndp8c = up8(ndp_cap); dptc = ndp8c >> 3; nd08c = up8(nd0_cap);
+    N8c = nr8c + m8 + nd08c; NBc = N8c >> 3;
+    NB32c = (N8c + 31) >> 5; NTc = NB32c * 32;
+    NBTc = NBc * (NBc + 1) / 2;
+    int o = 0;
+    off_M = o;     o += NBTc * 64;
+    off_AP = o;    o += mt * dptc * 64;
+    off_dinv = o;  o += NTc;
+    off_dneg = o;  o += NTc;
+    off_tbuf = o;  o += NTc;
+    off_ybuf = o;  o += NTc;
+    off_sred = o;  o += NTc;
+    off_rf = o;    o += n8;
+    off_vd = o;    o += ndp8c + 8;
+    off_hinv = o;  o += ndp8c + 8;
+    off_d1c = o;   o += m8 + 8;
+    off_beq = o;   o += m8 + 8;
+    off_qd = o;    o += n8;
+    off_xs = o;    o += n8 + 8;
+    off_lcbar = o; o += up2(nc + 2);
+    off_muc = o;   o += up2(nc + 2);
+    off_mu = o;    o += up2(nc / 3 + 2);
+    off_red = o;   o += 4 * 32;
+    off_int = o;
+    int io = 8;                      // [0] work index, [1..7] spare
+    io_vtype = io;  io += n8;
+    io_vpos = io;   io += n8;
+    io_rlist = io;  io += nr8c + 8;
+    io_dplist = io; io += ndp8c + 8;
+    io_d0list = io; io += nd08c + 8;
+    io_d1var = io;  io += m8 + 8;
+    io_rowcnt = io; io += m8 + 8;
+    io_sepf = io;   io += n8;
+    io_wtot = io;   io += 32 * 3;
+    ints_total = io;
+    o += (io + 1) / 2;
+    doubles_total = o;
+  }
+  size_t bytes() const { return (size_t)doubles_total * sizeof(double); }
+};
+
 struct SolveParams {
   int B, n, m, nc, lcs;
   int max_iter, warm;
@@ -126,6 +190,8 @@ struct SolveParams {
   unsigned long long* prof;    // optional [16]: per-phase cycle counters (developer profiling)
   unsigned long long* trace;   // optional [8][4096]: (clock << 8 | tag) events of CTA 0's first QP (developer tracing)
   Layout lay;                  // filled in by launch_solve
+  StructLayout slay;           // structure-exploiting kernel (fccqp_struct.cuh); filled in by launch_solve
+  int struct_refine;           // that kernel: one step of iterative refinement on the cold pre-solve
 };
 
 __device__ __forceinline__ double warp_max(double v) {
@@ -984,9 +1050,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
   const long long q_slow = p.q_cs <= p.q_rs ? p.q_rs : p.q_cs;
   const long long q_fast = p.q_cs <= p.q_rs ? p.q_cs : p.q_rs;
 
-  const int Btot = (kShared && p.count_dev) ? (int)*p.count_dev : p.B;
-  const bool resume = shared_mode == 2;   // x0 of the pre-solve launch is in p.x, pass 0 is done
+  const int Btot = p.count_dev ? (int)*p.count_dev : p.B;
+  // cold ADMM launch of a shared-structure batch: x0 of the pre-solve launch is in p.x, pass 0 is done.
+  // (A WARM batch launched directly in mode 2 has had no pre-solve launch: equality-constrained QPs still
+  // take pass 0 there, fcc_qp.cpp:159.)
+  const bool resume = shared_mode == 2 && !p.warm;
   int cached_pass = -1;                     // shared-structure modes: which KKT factorization sits in M
+  int factor_flag = 0;                      // 2: the factorization in M had the wrong inertia / a non-finite pivot
   double sigma_cached = 1.0;
   for (;;) {
     __syncthreads();  // previous QP fully retired (smem reuse) before taking new work
@@ -994,7 +1064,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
     __syncthreads();
     const int qslot = *s_work;
     if (qslot >= Btot) break;
-    const int qp = (kShared && p.index_list) ? p.index_list[qslot] : qslot;
+    const int qp = p.index_list ? p.index_list[qslot] : qslot;
 #ifdef FCCQP_DEV
     trbuf = (trcount++ == trsel) ? trbase : nullptr;
 #endif
@@ -1273,6 +1343,18 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
       factor_tiles<kThreads>(M, dinv, dneg, NB, NB32 FCCQP_TRACE_ARGS);
       FCCQP_PROF(3);
       fact_cycles += (unsigned long long)(clock64() - t_f0);
+      {
+        // Inertia of the quasi-definite KKT matrix: positive pivots on the variable rows (and all pads),
+        // negative ones on the constraint rows.  Anything else means Q + sigma A'A (or Q + rho I) is not
+        // positive definite on this QP or A_eq lost row rank -- the unpivoted factors are meaningless even
+        // when x comes out finite (the reference pivots / falls back to COD there): NUMERICAL_ISSUE.
+        bool badp = false;
+        if (is_row) {
+          const double dn = dneg[t];   // -d_t
+          badp = !isfinite(dn) || (is_c ? !(dn > 0.0) : !(dn < 0.0));
+        }
+        factor_flag = __syncthreads_or(badp) ? 2 : 0;
+      }
       if (shared_mode != 0) {
         // shared structure: [K^{-1}]_{x,:} as an explicit operator, kept for every later QP of this CTA
         complete_inverse<kThreads>(M, NB);
@@ -1283,6 +1365,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
       TR(20);
       }
       }  // lazy factorization
+      if (factor_flag) status_flag = 2;
 
         // ---- K3 right-hand side
         double acc = 0.0;

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define FCCQP_ABI_VERSION 2
+#define FCCQP_ABI_VERSION 3
 
 typedef enum fccqp_error {
   FCCQP_OK = 0,
@@ -100,6 +100,9 @@ int fccqp_get_options(fccqp_handle h, fccqp_options* opt);
 int fccqp_set_rho(fccqp_handle h, double rho);
 int fccqp_set_max_iter(fccqp_handle h, int max_iter);
 int fccqp_set_warm_start(fccqp_handle h, int warm_start);
+/* Extension: fccqp_structure for this object's solves (AUTO classifies each QP on the host -- its data is
+ * host memory -- and sizes the reduced kernel for it; DENSE always runs the general kernel). */
+int fccqp_set_structure(fccqp_handle h, int structure);
 /* contact_vars_start(), src/fcc_qp.hpp:121 */
 int fccqp_contact_vars_start(fccqp_handle h);
 
@@ -136,6 +139,22 @@ typedef enum fccqp_memory_space { FCCQP_MEM_HOST = 0, FCCQP_MEM_DEVICE = 1 } fcc
  * the ill-conditioned, nearly cost-free force directions -- and 1e-8 on the objective; iteration counts
  * unchanged). */
 typedef enum fccqp_precision { FCCQP_PRECISION_FP64 = 0, FCCQP_PRECISION_FP32_DATA = 1 } fccqp_precision;
+
+/* Problem structure.  Whole-body-control QPs are mostly made of variables that enter the
+ * cost only through their own square (torques, constraint forces, slacks: diagonal-only rows of Q).  The
+ * solver detects them PER QP on the device and factors a reduced KKT system without them (src/fcc_qp.cpp:141-150
+ * assembles, and :62-71 / :159-178 factor, the full (n+m) x (n+m) matrix); QPs without such structure, or whose
+ * reduced system fails its inertia check, run on the general kernel in the same call.  Results are those of
+ * FCCQP::Solve either way (parity bar unchanged).
+ *   FCCQP_STRUCTURE_AUTO   size the reduced kernel from a probe of up to 128 QPs of the batch (device memory:
+ *                          one small extra launch and ONE stream synchronisation inside the call; host memory:
+ *                          classified on the host, no synchronisation)
+ *   FCCQP_STRUCTURE_DENSE  never reduce (the general kernel only; fully asynchronous, graph-capturable)
+ *   FCCQP_STRUCTURE_CAPS   struct_caps = upper bounds {variables with off-diagonal cost entries, separable
+ *                          variables whose A_eq column has >= 2 entries, zero-cost separable variables} valid for
+ *                          the batch (e.g. from fccqp_last_struct_info after an AUTO call on the same kind of
+ *                          data): no probe, no synchronisation; QPs beyond the caps still run, on the general kernel */
+typedef enum fccqp_structure { FCCQP_STRUCTURE_AUTO = 0, FCCQP_STRUCTURE_DENSE = 1, FCCQP_STRUCTURE_CAPS = 2 } fccqp_structure;
 
 typedef struct fccqp_batch_desc {
   int32_t abi_version;     /* FCCQP_ABI_VERSION */
@@ -177,6 +196,8 @@ typedef struct fccqp_batch_desc {
   void* stream;            /* cudaStream_t for FCCQP_MEM_DEVICE (NULL = default stream).
                               Device calls are asynchronous on this stream. */
   double* device_seconds;  /* optional HOST pointer: kernel time by CUDA events (forces a sync) */
+  int32_t structure;       /* enum fccqp_structure; 0 = AUTO */
+  int32_t struct_caps[3];  /* FCCQP_STRUCTURE_CAPS only */
 } fccqp_batch_desc;
 
 int fccqp_batch_solve(const fccqp_batch_desc* desc);
@@ -229,6 +250,11 @@ int fccqp_wbc_assemble(const fccqp_wbc_desc* desc);
  * by this library since load, and the launch geometry of the last batch call. */
 int64_t fccqp_kernel_launch_count(void);
 int fccqp_last_launch_info(int* grid, int* block, int* smem_bytes, int* ctas_per_sm);
+/* What the last batch launch did about problem structure: used = 1 if the reduced kernel ran; caps[3] = the
+ * structure bounds its layout was sized for (pass them back as FCCQP_STRUCTURE_CAPS); rows / rows_dense = padded
+ * KKT rows factored per QP by the reduced and by the general kernel; deferred = QPs the reduced kernel handed to
+ * the general one (valid once the stream of that call has been synchronised).  Any pointer may be NULL. */
+int fccqp_last_struct_info(int* used, int* caps, int* rows, int* rows_dense, int* deferred);
 
 #ifdef __cplusplus
 }
