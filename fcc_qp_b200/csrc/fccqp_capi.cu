@@ -202,6 +202,8 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool
   p.full_inverse_at = fia < 1 ? 1 : fia;
   // developer switch (read per call, tests toggle it): 0 = no iterative refinement of the reduced cold pre-solve
   p.struct_refine = getenv("FCCQP_STRUCT_REFINE") ? atoi(getenv("FCCQP_STRUCT_REFINE")) : 1;
+  p.struct_prefetch = getenv("FCCQP_STRUCT_PREFETCH") ? atoi(getenv("FCCQP_STRUCT_PREFETCH")) : 1;
+  p.struct_bulk = getenv("FCCQP_STRUCT_BULK") ? atoi(getenv("FCCQP_STRUCT_BULK")) : 1;
   auto occupancy_of = [&](KernelFn f, int thr, size_t sm, int* out) -> int {
     std::lock_guard<std::mutex> lk(ctx.mu);
     const auto key = std::make_pair((const void*)f, sm);
@@ -301,7 +303,7 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool
   const bool no_struct_env = getenv("FCCQP_NO_STRUCT") != nullptr;   // developer switch, read per call
   StructHint hint;
   if (hint_in) hint = *hint_in;
-  static const bool dev_instr = getenv("FCCQP_PROFILE") != nullptr || getenv("FCCQP_TRACE") != nullptr;
+  static const bool dev_instr = getenv("FCCQP_TRACE") != nullptr;
   if (!no_struct_env && !dev_instr && !f32 && hint.mode != FCCQP_STRUCTURE_DENSE && p.n <= 256 && p.m <= 256 && p.m > 0) {
     int caps[3] = {hint.caps[0], hint.caps[1], hint.caps[2]};
     bool ok = true;
@@ -324,7 +326,7 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool
       ok = h[3] == 0;
     }
     if (ok && caps[0] >= 0 && caps[0] <= p.n && caps[1] >= 0 && caps[2] >= 0 && caps[0] + caps[1] + caps[2] <= p.n) {
-      fccqp::StructLayout sl(p.n, p.m, p.nc, caps[0], caps[1], caps[2]);
+      fccqp::StructLayout sl(p.n, p.m, p.nc, caps[0], caps[1] + caps[2], caps[2]);   // D+ store: pass 1 eliminates D0 too
       KernelFn sfn = nullptr; int sthreads = 0;
       // worth it when at least one tile row of the KKT matrix goes away
       if (sl.N8c + 8 <= p.lay.N8 && sl.bytes() <= (size_t)ctx.max_smem_optin && pick_struct_kernel(sl, p.n, &sfn, &sthreads) == 0) {
@@ -337,8 +339,29 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool
         a.slay = sl;
         a.pending_count = list_count;
         a.pending_list = list;
+        static const bool sprofile = getenv("FCCQP_PROFILE") != nullptr;  // developer aid: phase cycle counters
+        unsigned long long* d_sprof = nullptr;
+        if (sprofile) {
+          CUDA_TRY(cudaMalloc(&d_sprof, 16 * sizeof(unsigned long long)));
+          CUDA_TRY(cudaMemsetAsync(d_sprof, 0, 16 * sizeof(unsigned long long), stream));
+          a.prof = d_sprof;
+        }
         sfn<<<sgrid, sthreads, sl.bytes(), stream>>>(a);
         CUDA_TRY(cudaGetLastError());
+        if (sprofile) {
+          unsigned long long h[16];
+          CUDA_TRY(cudaMemcpyAsync(h, d_sprof, sizeof(h), cudaMemcpyDeviceToHost, stream));
+          CUDA_TRY(cudaStreamSynchronize(stream));
+          CUDA_TRY(cudaFree(d_sprof));
+          static const char* names[10] = {"fetch+vectors", "classify", "zero+scatter", "wait-copies", "C+diag", "factor", "x-solve",
+                                          "-", "project/exit", "epilogue"};
+          double tot = 0;
+          for (int i = 0; i < 10; ++i) tot += (double)h[i];
+          fprintf(stderr, "[fccqp struct profile] B=%d grid=%d qps=%llu cycles/QP=%.0f\n", p.B, sgrid, h[14], h[14] ? tot / (double)h[14] : 0.0);
+          for (int i = 0; i < 10; ++i)
+            fprintf(stderr, "   %-14s %10.0f cyc/QP  %5.1f%%\n", names[i], h[14] ? (double)h[i] / (double)h[14] : 0.0,
+                    tot > 0 ? 100.0 * (double)h[i] / tot : 0.0);
+        }
         fccqp::SolveParams b = p;
         b.count_dev = list_count;
         b.index_list = list;
@@ -605,15 +628,11 @@ int fccqp_solve(fccqp_handle h, const double* Q, ptrdiff_t q_rs, ptrdiff_t q_cs,
   if (q_cs == 1) for (int i = 0; i < n; ++i) memcpy(sQ + (size_t)i * n, Q + i * q_rs, sizeof(double) * n);
   else if (q_rs == 1) for (int j = 0; j < n; ++j) memcpy(sQ + (size_t)j * n, Q + j * q_cs, sizeof(double) * n);  // symmetric
   else for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) sQ[(size_t)i * n + j] = Q[i * q_rs + j * q_cs];
-  long long k_a_rs, k_a_cs;
-  if (a_rs == 1 && a_cs != 1) {  // column-major (Eigen): keep columns contiguous
-    for (int j = 0; j < n; ++j) memcpy(sA + (size_t)j * m, A + j * a_cs, sizeof(double) * m);
-    k_a_rs = 1; k_a_cs = m;
-  } else {
-    for (int i = 0; i < m; ++i)
-      for (int j = 0; j < n; ++j) sA[(size_t)i * n + j] = A[i * a_rs + j * a_cs];
-    k_a_rs = n; k_a_cs = 1;
-  }
+  // A_eq: always packed row-major (a column-major Eigen matrix is transposed here, m x n is small): the kernels'
+  // row-wise 16-byte passes then apply whatever the caller's layout
+  const long long k_a_rs = n, k_a_cs = 1;
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < n; ++j) sA[(size_t)i * n + j] = A[i * a_rs + j * a_cs];
   memcpy(sb, b, sizeof(double) * n);
   if (m) memcpy(sbeq, b_eq, sizeof(double) * m);
   if (nc) memcpy(smu, mu, sizeof(double) * (nc / 3));

@@ -108,7 +108,8 @@ struct StructLayout {
   int off_M, off_AP, off_dinv, off_dneg, off_tbuf, off_ybuf, off_sred, off_rf, off_vd, off_hinv, off_d1c, off_beq;
   int off_qd, off_xs, off_lcbar, off_muc, off_mu, off_red, off_int;
   // int region (offsets in ints from off_int)
-  int io_vtype, io_vpos, io_rlist, io_dplist, io_d0list, io_d1var, io_rowcnt, io_sepf, io_wtot, ints_total;
+  int io_vtype, io_vpos, io_rlist, io_dplist, io_d0list, io_d1var, io_rowcnt, io_wtot, io_nzflag, io_colcnt, io_colk, ints_total;
+  int stage_cap;   // doubles of the [M | AP] region: staging space of the classification (>= 4 rows of Q)
   int doubles_total;
   static inline int up2(int v) { return (v + 1) & ~1; }
   static inline int up8(int v) { return (v + 7) & ~7; }
@@ -123,6 +124,8 @@ struct StructLayout {
     int o = 0;
     off_M = o;     o += NBTc * 64;
     off_AP = o;    o += mt * dptc * 64;
+    if (o < 4 * n8) o = 4 * n8;     // (tiny reduced systems: keep room to stage a few rows of Q)
+    stage_cap = o;
     off_dinv = o;  o += NTc;
     off_dneg = o;  o += NTc;
     off_tbuf = o;  o += NTc;
@@ -138,7 +141,7 @@ struct StructLayout {
     off_lcbar = o; o += up2(nc + 2);
     off_muc = o;   o += up2(nc + 2);
     off_mu = o;    o += up2(nc / 3 + 2);
-    off_red = o;   o += 4 * 32;
+    off_red = o;   o += 4 * 32 + 16;   // + 16: developer phase counters
     off_int = o;
     int io = 8;                      // [0] work index, [1..7] spare
     io_vtype = io;  io += n8;
@@ -148,8 +151,10 @@ struct StructLayout {
     io_d0list = io; io += nd08c + 8;
     io_d1var = io;  io += m8 + 8;
     io_rowcnt = io; io += m8 + 8;
-    io_sepf = io;   io += n8;
     io_wtot = io;   io += 32 * 3;
+    io_nzflag = io; io += n8;
+    io_colcnt = io; io += n8;
+    io_colk = io;   io += n8;
     ints_total = io;
     o += (io + 1) / 2;
     doubles_total = o;
@@ -192,6 +197,8 @@ struct SolveParams {
   Layout lay;                  // filled in by launch_solve
   StructLayout slay;           // structure-exploiting kernel (fccqp_struct.cuh); filled in by launch_solve
   int struct_refine;           // that kernel: one step of iterative refinement on the cold pre-solve
+  int struct_prefetch;         // that kernel: bulk L2 prefetch of the next QP's Q and A_eq
+  int struct_bulk;             // that kernel: bulk-async (TMA) staging of dense Q / A_eq blocks (0: per-row cp.async)
 };
 
 __device__ __forceinline__ double warp_max(double v) {
@@ -382,12 +389,19 @@ __device__ __forceinline__ void factor_diag_tile(double* __restrict__ tile, doub
 // Named barriers (ids 1..15; 0 is __syncthreads): producer warps arrive, consumer warps sync,
 // `count` = all threads taking part either way.  The fence makes the producer's shared-memory
 // writes visible before the arrival is counted.
-__device__ __forceinline__ void bar_arrive(int id, int count) {
+// The barrier id is an IMMEDIATE (kBase or kBase + 1, picked by `odd`): with a register operand ptxas has
+// to assume that all 16 hardware barriers of the CTA are in use, and the SM runs out of barriers at
+// 4 resident CTAs whatever the shared-memory and register budget says.
+template <int kBase>
+__device__ __forceinline__ void bar_arrive(int odd, int count) {
   __threadfence_block();
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+  if (odd) asm volatile("bar.arrive %0, %1;" ::"n"(kBase + 1), "r"(count) : "memory");
+  else asm volatile("bar.arrive %0, %1;" ::"n"(kBase), "r"(count) : "memory");
 }
-__device__ __forceinline__ void bar_sync(int id, int count) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+template <int kBase>
+__device__ __forceinline__ void bar_sync(int odd, int count) {
+  if (odd) asm volatile("bar.sync %0, %1;" ::"n"(kBase + 1), "r"(count) : "memory");
+  else asm volatile("bar.sync %0, %1;" ::"n"(kBase), "r"(count) : "memory");
 }
 
 #ifdef FCCQP_DEV
@@ -583,7 +597,7 @@ __device__ __noinline__ void factor_tiles(double* __restrict__ M, double* __rest
       if (lane == 0) factor_diag_tile(dt, dinv + 8 * j, dneg + 8 * j);
       __syncwarp();
       TR(12);
-      if (j > 0) bar_sync(3 + ((j - 1) & 1), kThreads);   // helpers finished step j-1
+      if (j > 0) bar_sync<3>((j - 1) & 1, kThreads);   // helpers finished step j-1
       if (j + 1 < NB) {
         const double2 li = ld2(dt + fragC), di = ld2(dinv + 8 * j + 2 * fq);
         double* lp = M + tile_off(j + 1, j) + fragC;
@@ -600,14 +614,14 @@ __device__ __noinline__ void factor_tiles(double* __restrict__ M, double* __rest
         dmma(t2.x, t2.y, -wy, l.y);
         st2(lp + 64, make_double2(t1.x + t2.x, t1.y + t2.y));
       }
-      bar_arrive(1 + (j & 1), kThreads);                  // column j: inv(L_jj), D_j, L_{j+1,j} ready
+      bar_arrive<1>(j & 1, kThreads);                     // column j: inv(L_jj), D_j, L_{j+1,j} ready
       TR(13);
     }
-    bar_sync(3 + ((NB - 1) & 1), kThreads);
+    bar_sync<3>((NB - 1) & 1, kThreads);
   } else {
 #pragma unroll 1
     for (int j = 0; j < NB; ++j) {
-      bar_sync(1 + (j & 1), kThreads);
+      bar_sync<1>(j & 1, kThreads);
       TR(10);
       const double2 li = ld2(M + tile_off(j, j) + fragC), di = ld2(dinv + 8 * j + 2 * fq);
       // own tile rows i >= j+2, i = warp-1 (mod kHelpers), four at a time
@@ -620,7 +634,7 @@ __device__ __noinline__ void factor_tiles(double* __restrict__ M, double* __rest
         else helper_step<2>(M, dneg, i0, kHelpers, j, li, di, fragC, fq, cnt FCCQP_TRACE_ARGS);
       }
       TR(11);
-      bar_arrive(3 + (j & 1), kThreads);
+      bar_arrive<3>(j & 1, kThreads);
     }
   }
   __syncthreads();

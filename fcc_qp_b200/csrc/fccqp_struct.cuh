@@ -57,67 +57,192 @@ struct VarClass {
 
 // Pointers into the int scratch region of StructLayout.
 struct StructInts {
-  int *vtype, *vpos, *rlist, *dplist, *d0list, *d1var, *rowcnt, *sepf, *wtot;
+  int *vtype, *vpos, *rlist, *dplist, *d0list, *d1var, *rowcnt, *wtot, *nzflag, *colcnt, *colk;
 };
+
+// ---- bulk-async (TMA) staging: one thread issues ONE cp.async.bulk for a whole matrix (or as many rows of it as
+// fit), completion is signalled on an mbarrier every thread then waits on.  No per-thread address
+// arithmetic, no registers, nothing to unroll.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async8_s(unsigned smem_dst, const double* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  // (generic-proxy accesses to the destination by this CTA are ordered before by the caller's __syncthreads)
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MBAR_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MBAR_DONE_%=;\n"
+      "bra MBAR_WAIT_%=;\n"
+      "MBAR_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 
 // Classification of one QP (all threads of the CTA).  Reads ALL of Q and A_eq once (the algorithmic
 // read of the path: they are inputs, every entry matters); what the assembly reads again afterwards
 // comes from L1/L2.  Returns nonzero when the QP does not fit (caps) or is structurally singular
 // (a zero-cost variable that no constraint touches).
+//
+// The matrices are STAGED into `stg` -- the tile region of the KKT matrix, idle until the assembly -- as
+// many rows at a time as fit: ONE bulk-async copy (TMA, cp.async.bulk + mbarrier) per chunk when the
+// matrix is a dense contiguous block, per-row cp.async otherwise; every byte is in flight at once and
+// no register is held.  The staged rows are then walked column-wise: thread groups take interleaved
+// rows, a thread owns a column pair (16-byte shared loads).  (Q is symmetric: column j has an
+// off-diagonal entry iff row j has.)  Compact rolled loops on purpose: this runs once per QP, and
+// straight-line unrolled load batches cost more in instruction fetch than they save.
+struct StageCtl {
+  unsigned long long* bar;   // mbarrier of the bulk copies
+  unsigned phase;            // its parity (flips with every completed copy)
+  bool q_bulk, a_bulk;       // dense contiguous 16-byte aligned blocks
+};
+
 template <int kThreads>
-__device__ __forceinline__ int struct_classify(const int n, const int m, const int m8, const double* __restrict__ Qg,
-                                               const long long q_slow, const long long q_fast,
-                                               const double* __restrict__ Ag, const long long a_rs, const long long a_cs,
-                                               double* __restrict__ qd_s, const StructInts& I, const int capR,
-                                               const int capP, const int cap0, VarClass& vc, int& nr, int& ndp, int& nd0) {
+__device__ __forceinline__ int struct_classify(const int n, const int m, const int n8, const int m8,
+                                               const double* __restrict__ Qg, const long long q_slow, const long long q_fast,
+                                               const bool q_vec, const double* __restrict__ Ag, const long long a_rs,
+                                               const long long a_cs, const bool a_vec, double* __restrict__ stg,
+                                               const int stg_cap, StageCtl& sc, double* __restrict__ qd_s,
+                                               double* __restrict__ colv, const StructInts& I, const int capR, const int capP,
+                                               const int cap0, VarClass& vc, int& nr, int& ndp, int& nd0) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kWarps = kThreads / 32;
-  constexpr int kCol = kThreads / 32;   // n <= kThreads: at most kCol columns per lane
-  // ---- Q: one warp per row (read along the contiguous direction of the symmetric matrix), two rows in flight
+  const int rpc = stg_cap / n;   // rows per chunk (>= 1 by construction of the layout)
+  // column pairs and row groups of the scans (n even: thread -> (group, pair); n odd: thread -> column, one group)
+  const bool pairs = (n & 1) == 0;
+  const int npair = pairs ? (n >> 1) : n;
+  const int ngrp = max(1, kThreads / npair);
+  const int grp = tid / npair, cp = tid - grp * npair;
+  const bool scan = grp < ngrp;
+  for (int e = tid; e < m8 + 8; e += kThreads) { I.rowcnt[e] = 0; I.d1var[e] = -1; }
+  for (int e = tid; e < n8; e += kThreads) { I.nzflag[e] = 0; I.colcnt[e] = 0; }
+  // ---- Q: separable <=> no off-diagonal entry in column j; diagonal entry
+  bool nzx = false, nzy = false;
 #pragma unroll 1
-  for (int i0 = warp; i0 < n; i0 += 2 * kWarps) {
-    const int i1 = i0 + kWarps;
-    const bool has1 = i1 < n;
-    const double* r0 = Qg + (long long)i0 * q_slow;
-    const double* r1 = Qg + (long long)(has1 ? i1 : i0) * q_slow;
-    double va[kCol], vb[kCol];
-#pragma unroll
-    for (int u = 0; u < kCol; ++u) {
-      const int c = lane + 32 * u;
-      va[u] = c < n ? r0[(long long)c * q_fast] : 0.0;
-      vb[u] = c < n ? r1[(long long)c * q_fast] : 0.0;
+  for (int row0 = 0; row0 < n; row0 += rpc) {
+    const int rows = min(rpc, n - row0);
+    if (sc.q_bulk) {
+      if (tid == 0) bulk_g2s(stg, Qg + (size_t)row0 * n, (unsigned)(rows * n * sizeof(double)), sc.bar);
+      mbar_wait(sc.bar, sc.phase);
+      sc.phase ^= 1u;
+    } else {
+      if (q_vec) {
+#pragma unroll 1
+        for (int i = warp; i < rows; i += kWarps) {
+          const double* src = Qg + (size_t)(row0 + i) * q_slow;
+          for (int c = 2 * lane; c < n; c += 64) cp_async16(stg + i * n + c, src + c);
+        }
+      } else {
+#pragma unroll 1
+        for (int i = warp; i < rows; i += kWarps) {
+          const double* src = Qg + (long long)(row0 + i) * q_slow;
+          for (int c = lane; c < n; c += 32) cp_async8(stg + i * n + c, src + (long long)c * q_fast);
+        }
+      }
+      cp_async_wait_all();
+      __syncthreads();
     }
-    bool nza = false, nzb = false;
-#pragma unroll
-    for (int u = 0; u < kCol; ++u) {
-      const int c = lane + 32 * u;
-      if (c < n) {
-        if (c == i0) qd_s[i0] = va[u]; else nza = nza || (va[u] != 0.0);
-        if (has1) { if (c == i1) qd_s[i1] = vb[u]; else nzb = nzb || (vb[u] != 0.0); }
+    if (scan) {
+      if (pairs) {
+        const int c0 = 2 * cp;
+#pragma unroll 2
+        for (int i = grp; i < rows; i += ngrp) {
+          const double2 v = ld2(stg + i * n + c0);
+          const int gi = row0 + i;
+          if (gi == c0) qd_s[gi] = v.x; else nzx = nzx || (v.x != 0.0);
+          if (gi == c0 + 1) qd_s[gi] = v.y; else nzy = nzy || (v.y != 0.0);
+        }
+      } else {
+#pragma unroll 2
+        for (int i = grp; i < rows; i += ngrp) {
+          const double v = stg[i * n + cp];
+          if (row0 + i == cp) qd_s[cp] = v; else nzx = nzx || (v != 0.0);
+        }
       }
     }
-    nza = __any_sync(0xffffffffu, nza);
-    nzb = __any_sync(0xffffffffu, nzb);
-    if (lane == 0) { I.sepf[i0] = nza ? 0 : 1; if (has1) I.sepf[i1] = nzb ? 0 : 1; }
+    __syncthreads();
   }
-  // ---- A_eq: one thread per column (coalesced for row-major A): entry count, last entry
-  int nnz = 0, kr = 0;
-  double av = 0.0;
-  if (tid < n) {
-    const double* col = Ag + (long long)tid * a_cs;
-#pragma unroll 8
-    for (int k = 0; k < m; ++k) {
-      const double v = col[(long long)k * a_rs];
-      if (v != 0.0) { ++nnz; kr = k; av = v; }
+  if (scan) {
+    if (pairs) { if (nzx) atomicOr(&I.nzflag[2 * cp], 1); if (nzy) atomicOr(&I.nzflag[2 * cp + 1], 1); }
+    else if (nzx) atomicOr(&I.nzflag[cp], 1);
+  }
+  // ---- A_eq: entry count of every column, and its entry if there is only one
+  int cx = 0, cy = 0, kx = 0, ky = 0;
+  double vx = 0.0, vy = 0.0;
+#pragma unroll 1
+  for (int row0 = 0; row0 < m; row0 += rpc) {
+    const int rows = min(rpc, m - row0);
+    if (sc.a_bulk) {
+      if (tid == 0) bulk_g2s(stg, Ag + (size_t)row0 * n, (unsigned)(rows * n * sizeof(double)), sc.bar);
+      mbar_wait(sc.bar, sc.phase);
+      sc.phase ^= 1u;
+    } else {
+      if (a_vec) {
+#pragma unroll 1
+        for (int k = warp; k < rows; k += kWarps) {
+          const double* src = Ag + (size_t)(row0 + k) * a_rs;
+          for (int c = 2 * lane; c < n; c += 64) cp_async16(stg + k * n + c, src + c);
+        }
+      } else {
+#pragma unroll 1
+        for (int k = warp; k < rows; k += kWarps) {
+          const double* src = Ag + (long long)(row0 + k) * a_rs;
+          for (int c = lane; c < n; c += 32) cp_async8(stg + k * n + c, src + (long long)c * a_cs);
+        }
+      }
+      cp_async_wait_all();
+      __syncthreads();
+    }
+    if (scan) {
+      if (pairs) {
+#pragma unroll 2
+        for (int k = grp; k < rows; k += ngrp) {
+          const double2 v = ld2(stg + k * n + 2 * cp);
+          if (v.x != 0.0) { ++cx; kx = row0 + k; vx = v.x; }
+          if (v.y != 0.0) { ++cy; ky = row0 + k; vy = v.y; }
+        }
+      } else {
+#pragma unroll 2
+        for (int k = grp; k < rows; k += ngrp) {
+          const double v = stg[k * n + cp];
+          if (v != 0.0) { ++cx; kx = row0 + k; vx = v; }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // (several groups with entries in one column: the count says >= 2 and the entry is not used)
+  if (scan) {
+    const int c0 = pairs ? 2 * cp : cp;
+    // (atomic exchanges: two groups may both write here -- then the count is >= 2 and nobody reads the entry)
+    if (cx) {
+      atomicAdd(&I.colcnt[c0], cx); atomicExch(&I.colk[c0], kx);
+      atomicExch(reinterpret_cast<unsigned long long*>(colv + c0), (unsigned long long)__double_as_longlong(vx));
+    }
+    if (cy) {
+      atomicAdd(&I.colcnt[c0 + 1], cy); atomicExch(&I.colk[c0 + 1], ky);
+      atomicExch(reinterpret_cast<unsigned long long*>(colv + c0 + 1), (unsigned long long)__double_as_longlong(vy));
     }
   }
-  for (int e = tid; e < m8 + 8; e += kThreads) { I.rowcnt[e] = 0; I.d1var[e] = -1; }
   __syncthreads();
-  int type = VT_NONE;
-  double qd = 0.0;
+  int type = VT_NONE, nnz = 0, kr = 0;
+  double qd = 0.0, av = 0.0;
   if (tid < n) {
+    nnz = I.colcnt[tid];
+    if (nnz == 1) { kr = I.colk[tid]; av = colv[tid]; }
     qd = qd_s[tid];
-    if (!I.sepf[tid] || !(qd >= 0.0)) type = VT_R;          // (NaN or negative curvature: leave it to the dense block)
+    if (I.nzflag[tid] || !(qd >= 0.0)) type = VT_R;          // (NaN or negative curvature: leave it to the dense block)
     else if (qd < 1e-200) type = VT_D0;
     else type = nnz <= 1 ? VT_D1 : VT_DP;
     if (type == VT_D1 && nnz == 1) atomicAdd(&I.rowcnt[kr], 1);
@@ -140,7 +265,7 @@ __device__ __forceinline__ int struct_classify(const int n, const int m, const i
   }
   const unsigned lt = (1u << lane) - 1u;
   const int nr8 = (nr + 7) & ~7;
-  int bad = (nr > capR || ndp > capP || nd0 > cap0) ? 1 : 0;   // block-uniform
+  int bad = (nr > capR || ndp + nd0 > capP || nd0 > cap0) ? 1 : 0;   // block-uniform (capP covers pass 1: D+ and D0)
   int pos = 0;
   if (!bad && tid < n) {
     if (type == VT_R) { pos = oR + __popc(bR & lt); I.rlist[pos] = tid; }
@@ -160,8 +285,12 @@ __device__ __forceinline__ int struct_classify(const int n, const int m, const i
 // shared-memory layout of the solve kernel from it.
 template <int kThreads>
 __global__ void __launch_bounds__(kThreads) fccqp_struct_probe_kernel(const SolveParams p, const int ns, int* __restrict__ out) {
-  __shared__ double qd_s[kThreads];
-  __shared__ int ints[5 * kThreads + 2 * (kThreads + 16) + 96];
+  constexpr int kStage = 3072;   // staged doubles: >= 12 rows of the widest supported matrix
+  __shared__ __align__(16) double stg[kStage];
+  __shared__ __align__(16) double qd_s[kThreads];
+  __shared__ __align__(16) double colv[kThreads];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ int ints[8 * kThreads + 2 * (kThreads + 16) + 96];
   StructInts I;
   int* q = ints;
   I.vtype = q; q += kThreads;
@@ -169,31 +298,51 @@ __global__ void __launch_bounds__(kThreads) fccqp_struct_probe_kernel(const Solv
   I.rlist = q; q += kThreads;
   I.dplist = q; q += kThreads;
   I.d0list = q; q += kThreads;
+  I.nzflag = q; q += kThreads;
+  I.colcnt = q; q += kThreads;
+  I.colk = q; q += kThreads;
   I.d1var = q; q += kThreads + 16;
   I.rowcnt = q; q += kThreads + 16;
   I.wtot = q;
-  __shared__ int sepf[kThreads];
-  I.sepf = sepf;
   const int s = blockIdx.x;
   const long long qp = ns > 1 ? (long long)s * (p.B - 1) / (ns - 1) : 0;
   const long long q_slow = p.q_cs <= p.q_rs ? p.q_rs : p.q_cs;
   const long long q_fast = p.q_cs <= p.q_rs ? p.q_cs : p.q_rs;
-  const int m8 = (p.m + 7) & ~7;
+  const int n8 = (p.n + 7) & ~7, m8 = (p.m + 7) & ~7;
+  const double* Qg = p.Q + (size_t)qp * p.q_bs;
+  const double* Ag = p.A + (size_t)qp * p.a_bs;
+  const bool q_vec = q_fast == 1 && (p.n & 1) == 0 && (q_slow & 1) == 0 && (reinterpret_cast<uintptr_t>(Qg) & 15) == 0;
+  const bool a_vec = p.a_cs == 1 && (p.n & 1) == 0 && (p.a_rs & 1) == 0 && (reinterpret_cast<uintptr_t>(Ag) & 15) == 0;
+  StageCtl sc;
+  sc.bar = &bar; sc.phase = 0;
+  sc.q_bulk = q_vec && q_slow == p.n;
+  sc.a_bulk = a_vec && p.a_rs == p.n;
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
   VarClass vc;
   int nr, ndp, nd0;
-  const int bad = struct_classify<kThreads>(p.n, p.m, m8, p.Q + (size_t)qp * p.q_bs, q_slow, q_fast,
-                                            p.A + (size_t)qp * p.a_bs, p.a_rs, p.a_cs, qd_s, I, 1 << 30, 1 << 30, 1 << 30,
-                                            vc, nr, ndp, nd0);
+  const int bad = struct_classify<kThreads>(p.n, p.m, n8, m8, Qg, q_slow, q_fast, q_vec, Ag, p.a_rs, p.a_cs, a_vec, stg, kStage, sc,
+                                            qd_s, colv, I, 1 << 30, 1 << 30, 1 << 30, vc, nr, ndp, nd0);
   if (threadIdx.x == 0) {
     atomicMax(out, nr); atomicMax(out + 1, ndp); atomicMax(out + 2, nd0);
     if (bad) atomicAdd(out + 3, 1);
   }
 }
 
+// L2 prefetch of a contiguous global range (16-byte granules inside [ptr, ptr + bytes)): one bulk-async
+// instruction, no shared memory, no completion to wait for.
+__device__ __forceinline__ void l2_prefetch(const void* ptr, size_t bytes) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(ptr);
+  const uintptr_t lo = (a + 15) & ~(uintptr_t)15, hi = (a + bytes) & ~(uintptr_t)15;
+  if (hi > lo)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"((unsigned)(hi - lo)) : "memory");
+}
+
 // x-update through the reduced system.  r = this thread's entry of the full-space right-hand side
-// (variable rows; the constraint rows' b_eq is in shared memory).  Returns x_j for variable threads.
-// use_op: the factors have been replaced by the explicit inverse of the reduced matrix (long-running
-// QPs).  refine: one step of iterative refinement against the original Q and A_eq (cold pre-solve).
+// (variable rows; the constraint rows' b_eq is in shared memory, left out when `homog`).  Returns x_j
+// for variable threads.  use_op: the factors have been replaced by the explicit inverse of the
+// reduced matrix (long-running QPs).  refine: one step of iterative refinement against the original
+// Q and A_eq (cold pre-solve).
 struct StructQP {
   int nr, nr8, ndp, dpt, nd0, NB, NB32, N8;
 };
@@ -203,9 +352,9 @@ __device__ __forceinline__ double struct_xsolve(const SolveParams& p, const Stru
                                                 const StructInts& I, const StructQP& S, const VarClass& vc,
                                                 const double* __restrict__ Qg, const double* __restrict__ Ag,
                                                 const long long q_slow, const long long q_fast, const double r,
-                                                const double hi, const double shift, const bool use_op, const bool refine) {
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  constexpr int kWarps = kThreads / 32;
+                                                const double hi, const double shift, const bool use_op, const bool homog,
+                                                const bool refine) {
+  const int t = threadIdx.x;
   const int n = p.n, m = p.m;
   double* const M = smem + L.off_M;
   const double* const AP = smem + L.off_AP;
@@ -217,6 +366,7 @@ __device__ __forceinline__ double struct_xsolve(const SolveParams& p, const Stru
   double* const vd = smem + L.off_vd;
   double* const d1c = smem + L.off_d1c;
   const double* const beqs = smem + L.off_beq;
+  const double* const qd_s = smem + L.off_qd;
   double* const xs = smem + L.off_xs;
   const bool is_x = t < n;
   const int m8 = L.m8, dptc = L.dptc;
@@ -238,7 +388,7 @@ __device__ __forceinline__ double struct_xsolve(const SolveParams& p, const Stru
     double s = 0.0;
 #pragma unroll 1
     for (int kt = 0; kt < S.dpt; ++kt) s += row_dot8(arow + 64 * kt, (yrow & 7) >> 1, vd + 8 * kt);
-    acc = beqs[yrow] - s;
+    acc = (homog ? 0.0 : beqs[yrow]) - s;
     if (I.d1var[yrow] >= 0) acc -= d1c[yrow];
   } else if (row_0) acc = rf[I.d0list[zrow]];
   double val;
@@ -271,31 +421,55 @@ __device__ __forceinline__ double struct_xsolve(const SolveParams& p, const Stru
     return x;
   };
   if (refine) {
-    // residual of the ORIGINAL KKT system at (x, y); it vanishes on the eliminated variables by
-    // construction, so its R / constraint / D0 entries are the residual of the reduced system
+    // Residual of the ORIGINAL KKT system at (x, y): it vanishes on the eliminated variables by construction,
+    // so its R / constraint / D0 entries are the residual of the reduced system.  Q and A_eq come from
+    // L1/L2 (this CTA read them a moment ago); threads [0, m) take the constraint rows, the others the R and D0
+    // variables, kLB loads in flight each.
+    constexpr int kLB = 4;
     const double x = recover();
     if (is_x) xs[t] = x;
     __syncthreads();
+    if (t < m) {
+      const double* arow = Ag + (long long)t * p.a_rs;
+      double sa = 0.0;
 #pragma unroll 1
-    for (int k = warp; k < m; k += kWarps) {
-      const double* arow = Ag + (long long)k * p.a_rs;
-      double s = 0.0;
-      for (int j = lane; j < n; j += 32) s = fma(arow[(long long)j * p.a_cs], xs[j], s);
-      s = warp_sum(s);
-      if (lane == 0) d1c[k] = beqs[k] - s;
-    }
-    if (is_x && (vc.type == VT_R || vc.type == VT_D0)) {
-      double s0 = (vc.qd + shift) * x, s1 = 0.0;
-      if (vc.type == VT_R) {
-        s0 = shift * x;
-        const double* qcol = Qg + (long long)t * q_fast;
-#pragma unroll 4
-        for (int a = 0; a < S.nr; ++a) s0 = fma(qcol[(long long)I.rlist[a] * q_slow], sred[a], s0);
+      for (int j0 = 0; j0 < n; j0 += kLB) {
+        double v[kLB];
+#pragma unroll
+        for (int u = 0; u < kLB; ++u) v[u] = j0 + u < n ? arow[(long long)(j0 + u) * p.a_cs] : 0.0;
+#pragma unroll
+        for (int u = 0; u < kLB; ++u) sa = fma(v[u], j0 + u < n ? xs[j0 + u] : 0.0, sa);
       }
-      const double* acol = Ag + (long long)t * p.a_cs;
-#pragma unroll 4
-      for (int k = 0; k < m; ++k) s1 = fma(acol[(long long)k * p.a_rs], ys[k], s1);
-      rf[t] = r - (s0 + s1);
+      d1c[t] = beqs[t] - sa;
+    } else {
+      const int stride = kThreads - m > 0 ? kThreads - m : 1;
+#pragma unroll 1
+      for (int idx = t - m; idx < S.nr + S.nd0; idx += stride) {
+        const bool isR = idx < S.nr;
+        const int j = isR ? I.rlist[idx] : I.d0list[idx - S.nr];
+        double s0 = (isR ? shift : qd_s[j] + shift) * xs[j], s1 = 0.0;
+        if (isR) {
+          const double* qcol = Qg + (long long)j * q_fast;
+#pragma unroll 1
+          for (int a0 = 0; a0 < S.nr; a0 += kLB) {
+            double v[kLB];
+#pragma unroll
+            for (int u = 0; u < kLB; ++u) v[u] = a0 + u < S.nr ? qcol[(long long)I.rlist[a0 + u] * q_slow] : 0.0;
+#pragma unroll
+            for (int u = 0; u < kLB; ++u) s0 = fma(v[u], a0 + u < S.nr ? sred[a0 + u] : 0.0, s0);
+          }
+        }
+        const double* acol = Ag + (long long)j * p.a_cs;
+#pragma unroll 1
+        for (int k0 = 0; k0 < m; k0 += kLB) {
+          double v[kLB];
+#pragma unroll
+          for (int u = 0; u < kLB; ++u) v[u] = k0 + u < m ? acol[(long long)(k0 + u) * p.a_rs] : 0.0;
+#pragma unroll
+          for (int u = 0; u < kLB; ++u) s1 = fma(v[u], k0 + u < m ? ys[k0 + u] : 0.0, s1);
+        }
+        rf[j] -= s0 + s1;   // rf[j] held r_j
+      }
     }
     __syncthreads();
     double acc2 = 0.0;
@@ -312,6 +486,19 @@ __device__ __forceinline__ double struct_xsolve(const SolveParams& p, const Stru
   }
   return recover();
 }
+
+#ifdef FCCQP_DEV
+#define SPROF(slot)                                                        \
+  do {                                                                     \
+    if (p.prof && tid == 0) {                                              \
+      const long long t_now = clock64();                                   \
+      s_prof[slot] += (unsigned long long)(t_now - t_prof);                \
+      t_prof = t_now;                                                      \
+    }                                                                      \
+  } while (0)
+#else
+#define SPROF(slot) do { } while (0)
+#endif
 
 template <int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(const SolveParams p) {
@@ -336,12 +523,22 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
   double* const vmu = smem + L.off_mu;
   double* const red = smem + L.off_red;
   int* const ibuf = reinterpret_cast<int*>(smem + L.off_int);
-  int* const s_work = ibuf;
+  int* const s_work = ibuf;   // [0] this QP, [1] the next one (already being prefetched into L2)
   StructInts I;
   I.vtype = ibuf + L.io_vtype; I.vpos = ibuf + L.io_vpos; I.rlist = ibuf + L.io_rlist; I.dplist = ibuf + L.io_dplist;
-  I.d0list = ibuf + L.io_d0list; I.d1var = ibuf + L.io_d1var; I.rowcnt = ibuf + L.io_rowcnt; I.sepf = ibuf + L.io_sepf;
-  I.wtot = ibuf + L.io_wtot;
+  I.d0list = ibuf + L.io_d0list; I.d1var = ibuf + L.io_d1var; I.rowcnt = ibuf + L.io_rowcnt; I.wtot = ibuf + L.io_wtot;
+  I.nzflag = ibuf + L.io_nzflag; I.colcnt = ibuf + L.io_colcnt; I.colk = ibuf + L.io_colk;
+  double* const rf = smem + L.off_rf;
+  StageCtl sc;
+  sc.bar = reinterpret_cast<unsigned long long*>(ibuf + 2);   // 8-byte aligned slot of the int region
+  sc.phase = 0;
+  if (tid == 0) mbar_init(sc.bar, 1);
 
+#ifdef FCCQP_DEV
+  unsigned long long* const s_prof = reinterpret_cast<unsigned long long*>(smem + L.off_red + 4 * 32);   // [16], layout pads it
+  long long t_prof = 0;
+  if (p.prof && tid == 0) { for (int i = 0; i < 16; ++i) s_prof[i] = 0; t_prof = clock64(); }
+#endif
   int parity = 0;
   const int t = tid;
   const bool is_x = t < n;
@@ -350,15 +547,26 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
   const int fragC = (fr << 3) + (((fq ^ (fr >> 1)) & 3) << 1);
   const long long q_slow = p.q_cs <= p.q_rs ? p.q_rs : p.q_cs;
   const long long q_fast = p.q_cs <= p.q_rs ? p.q_cs : p.q_rs;
+  // dense per-QP blocks can be prefetched with one bulk instruction each
+  const bool q_dense = q_fast == 1 && q_slow == n;
+  const bool a_dense = (p.a_cs == 1 && p.a_rs == n) || (p.a_rs == 1 && p.a_cs == m);
 
+  // Work indices are fetched one QP ahead (thread 0 keeps the next one in a register): the atomic's round trip
+  // hides behind the QP in flight, and the index is known early enough to pull that QP's data into L2.
+  int w_next = 0;
+  if (tid == 0) w_next = (int)atomicAdd(p.work_counter, 1u);
   for (;;) {
     __syncthreads();  // previous QP fully retired (smem reuse) before taking new work
-    if (tid == 0) *s_work = (int)atomicAdd(p.work_counter, 1u);
+    if (tid == 0) {
+      s_work[0] = w_next;
+      if (w_next < p.B) w_next = (int)atomicAdd(p.work_counter, 1u);
+    }
     __syncthreads();
-    const int qp = *s_work;
+    const int qp = s_work[0];
     if (qp >= p.B) break;
     const double* Qg = p.Q + (size_t)qp * p.q_bs;
     const double* Ag = p.A + (size_t)qp * p.a_bs;
+    SPROF(0);
 
     // ---------------- K0: vectors ----------------
     double v_b = 0.0, v_lb = 0.0, v_ub = 0.0, v_mux = 0.0, v_xbar = 0.0, v_x = 0.0;
@@ -367,16 +575,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
       v_b = p.b[(size_t)qp * p.b_bs + t];
       v_lb = p.lb[(size_t)qp * p.lb_bs + t];
       v_ub = p.ub[(size_t)qp * p.ub_bs + t];
-      if (!isinf(v_lb) || !isinf(v_ub)) finite_bounds = 1;
       if (p.warm) { v_x = p.x[(size_t)qp * n + t]; v_mux = p.mu_x[(size_t)qp * n + t]; }
     }
     if (t < m) beqs[t] = p.beq[(size_t)qp * p.beq_bs + t];
-    if (t < n8) xs[t] = v_x;
     if (t < nc / 3) vmu[t] = p.mu[(size_t)qp * p.mu_bs + t];
     if (t < nc) muc[t] = p.warm ? p.mu_c[(size_t)qp * nc + t] : 0.0;
     for (int e = t; e < L.ndp8c + 8; e += kThreads) { vd[e] = 0.0; hinv[e] = 0.0; }
-    const bool eqc = (nc == 0) && (__syncthreads_or(finite_bounds) == 0);   // fcc_qp.cpp:132-133
-    const bool presolve = eqc || !p.warm;                                      // fcc_qp.cpp:159
 
     const long long t_start = clock64();
     unsigned long long fact_cycles = 0;
@@ -384,19 +588,29 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
     int n_iter = 0;
     double res_x = 0.0, res_c = 0.0;
 
-    // ---------------- classification (reads all of Q and A_eq) ----------------
+    // ---------------- classification (reads all of Q and A_eq; the vector loads above are still in flight) ----------------
     VarClass vc;
     StructQP S;
-    bool defer = struct_classify<kThreads>(n, m, m8, Qg, q_slow, q_fast, Ag, p.a_rs, p.a_cs, qd_s, I, L.nr8c, L.ndp8c,
-                                           L.nd08c, vc, S.nr, S.ndp, S.nd0) != 0;
+    const bool q_vec = q_fast == 1 && (n & 1) == 0 && (q_slow & 1) == 0 && (reinterpret_cast<uintptr_t>(Qg) & 15) == 0;
+    const bool a_vec = p.a_cs == 1 && (n & 1) == 0 && (p.a_rs & 1) == 0 && (reinterpret_cast<uintptr_t>(Ag) & 15) == 0;
+    sc.q_bulk = q_vec && q_slow == n && p.struct_bulk;
+    sc.a_bulk = a_vec && p.a_rs == n && p.struct_bulk;
+    bool defer = struct_classify<kThreads>(n, m, n8, m8, Qg, q_slow, q_fast, q_vec, Ag, p.a_rs, p.a_cs, a_vec, M, L.stage_cap, sc,
+                                           qd_s, rf, I, L.nr8c, L.ndp8c, L.nd08c, vc, S.nr, S.ndp, S.nd0) != 0;
+    SPROF(1);
+    if (tid == 0 && w_next < p.B && p.struct_prefetch) {
+      // the next QP of this CTA: start pulling its Q and A_eq into L2 (one bulk-async instruction each); by the
+      // time the CTA gets to it, its stage-in reads are L2 hits
+      if (q_dense) l2_prefetch(p.Q + (size_t)w_next * p.q_bs, (size_t)n * n * sizeof(double));
+      if (a_dense) l2_prefetch(p.A + (size_t)w_next * p.a_bs, (size_t)m * n * sizeof(double));
+    }
     S.nr8 = (S.nr + 7) & ~7;
-    S.dpt = (S.ndp + 7) >> 3;
-    const int nd08 = (S.nd0 + 7) & ~7;
-    S.N8 = S.nr8 + m8 + nd08;
-    S.NB = S.N8 >> 3;
-    S.NB32 = (S.N8 + 31) >> 5;
     const int NBr = S.nr8 >> 3;
     const int yrow = t - S.nr8;
+    if (is_x && (!isinf(v_lb) || !isinf(v_ub))) finite_bounds = 1;
+    if (t < n8) xs[t] = v_x;
+    const bool eqc = (nc == 0) && (__syncthreads_or(finite_bounds) == 0);   // fcc_qp.cpp:132-133
+    const bool presolve = eqc || !p.warm;                                      // fcc_qp.cpp:159
 
     // pass 0: cold pre-solve (shift 0);  pass 1: ADMM (shift rho).  Same lazy scheme as the general kernel:
     // x-update 0 of a cold solve is the identity, the rho-KKT system is only factored for QPs that iterate.
@@ -410,9 +624,24 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
       }
       const int iters = pass == 0 ? 1 : p.max_iter;
       const double shift = pass == 0 ? 0.0 : p.rho;
-      const double hi = (vc.type == VT_DP || vc.type == VT_D1) ? 1.0 / (vc.qd + shift) : 0.0;
+      // In the ADMM pass the zero-cost variables have h = rho > 0 like everybody else: they are eliminated too
+      // (keeping them as a trailing block with a rho-sized pivot costs three digits; tools/proto), so the
+      // reduced system of pass 1 is [R, constraints] only.
+      VarClass ve = vc;
+      StructQP Se = S;
+      if (pass == 1 && S.nd0 > 0) {
+        if (vc.type == VT_D0) { ve.type = VT_DP; ve.pos = S.ndp + (vc.pos - S.nr8 - m8); }
+        Se.ndp = S.ndp + S.nd0;
+        Se.nd0 = 0;
+      }
+      Se.dpt = (Se.ndp + 7) >> 3;
+      Se.N8 = S.nr8 + m8 + ((Se.nd0 + 7) & ~7);
+      Se.NB = Se.N8 >> 3;
+      Se.NB32 = (Se.N8 + 31) >> 5;
+      const double hi = (ve.type == VT_DP || ve.type == VT_D1) ? 1.0 / (ve.qd + shift) : 0.0;
       bool factored = false;
       bool full_inverse = false;
+      double v_xbase = 0.0;
 
 #pragma unroll 1
       for (int iter = 0; iter < iters; ++iter) {
@@ -423,58 +652,83 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
             const long long t_f0 = clock64();
             // ---------------- assemble the reduced KKT matrix (lower tiles) and the D+ columns ----------------
             {
-              const int nbt = (S.NB * (S.NB + 1)) >> 1;
+              const int nbt = (Se.NB * (Se.NB + 1)) >> 1;
               const double2 z2 = make_double2(0.0, 0.0);
               for (int e = t; e < nbt * 32; e += kThreads) st2(M + 2 * e, z2);
               for (int e = t; e < mt * dptc * 32; e += kThreads) st2(AP + 2 * e, z2);
             }
+            if (is_x) { I.vtype[t] = ve.type; I.vpos[t] = ve.pos; }
             __syncthreads();
-            // Q_RR: one warp per reduced row
-#pragma unroll 1
-            for (int a = warp; a < S.nr; a += kWarps) {
-              const double* qrow = Qg + (long long)I.rlist[a] * q_slow;
-              for (int bb = lane; bb <= a; bb += 32) cp_async8(M + mat_off(a, bb), qrow + (long long)I.rlist[bb] * q_fast);
-            }
-            // A_eq: R columns -> constraint rows of the matrix, D0 columns -> transposed into the trailing rows,
-            // D+ columns -> AP tiles (row tile I, column tile kt at (I * dptc + kt) * 64)
-            if (p.a_cs == 1 || p.a_rs != 1) {
-#pragma unroll 1
-              for (int k = warp; k < m; k += kWarps) {
-                const double* arow = Ag + (long long)k * p.a_rs;
-                const int yr = S.nr8 + k;
-                for (int j = lane; j < n; j += 32) {
-                  const int ty = I.vtype[j], ps = I.vpos[j];
-                  const double* src = arow + (long long)j * p.a_cs;
-                  if (ty == VT_R) cp_async8(M + mat_off(yr, ps), src);
-                  else if (ty == VT_D0) cp_async8(M + mat_off(ps, yr), src);
-                  else if (ty == VT_DP) cp_async8(AP + (size_t)((k >> 3) * dptc + (ps >> 3)) * 64 + el_off(k & 7, ps & 7), src);
-                }
+            // Q_RR -> top-left tiles; A_eq: R columns -> constraint rows of the matrix, D0 columns -> transposed into
+            // the trailing rows, D+ columns -> AP tiles (row tile I, column tile kt at (I * dptc + kt) * 64).  Second
+            // read of the data (L1/L2), element-wise asynchronous copies straight to their tile positions; a lane
+            // keeps the same columns (lane, lane + 32, ...) for every row, so their class and position are loop
+            // invariants.  Row-major A_eq walks rows per warp, column-major A_eq (Eigen callers) columns per warp.
+            {
+              constexpr int kCol = kThreads / 32;
+              const unsigned mS = smem_u32(M), apS = smem_u32(AP);
+              // per owned column: class, position, and the row-independent part of its byte offset inside a tile row
+              // (tile column * 512 + (c & 1) * 8; the 16-byte chunk (c >> 1) is XOR-swizzled with the row below)
+              int cty[kCol], cps[kCol], cof[kCol], chf[kCol];
+#pragma unroll
+              for (int u = 0; u < kCol; ++u) {
+                const int j = lane + 32 * u;
+                cty[u] = j < n ? I.vtype[j] : VT_NONE;
+                cps[u] = j < n ? I.vpos[j] : 0;
+                cof[u] = ((cps[u] >> 3) << 9) + ((cps[u] & 1) << 3);
+                chf[u] = (cps[u] & 7) >> 1;
               }
-            } else {
-              // column-major A_eq (Eigen callers): one warp per column, lanes along it
 #pragma unroll 1
-              for (int j = warp; j < n; j += kWarps) {
-                const int ty = I.vtype[j], ps = I.vpos[j];
-                if (ty == VT_D1) continue;
-                const double* acol = Ag + (long long)j * p.a_cs;
-                for (int k = lane; k < m; k += 32) {
-                  const int yr = S.nr8 + k;
-                  const double* src = acol + k;
-                  if (ty == VT_R) cp_async8(M + mat_off(yr, ps), src);
-                  else if (ty == VT_D0) cp_async8(M + mat_off(ps, yr), src);
-                  else cp_async8(AP + (size_t)((k >> 3) * dptc + (ps >> 3)) * 64 + el_off(k & 7, ps & 7), src);
+              for (int a = warp; a < S.nr; a += kWarps) {
+                const double* qrow = Qg + (long long)I.rlist[a] * q_slow;
+                const unsigned rowS = mS + (unsigned)tile_off(a >> 3, 0) * 8u + ((a & 7) << 6);
+                const int rh = (a & 7) >> 1;
+#pragma unroll
+                for (int u = 0; u < kCol; ++u)
+                  if (cty[u] == VT_R && cps[u] <= a)
+                    cp_async8_s(rowS + cof[u] + (((chf[u] ^ rh) & 3) << 4), qrow + (long long)(lane + 32 * u) * q_fast);
+              }
+              if (p.a_cs == 1 || p.a_rs != 1) {
+#pragma unroll 1
+                for (int k = warp; k < m; k += kWarps) {
+                  const double* arow = Ag + (long long)k * p.a_rs;
+                  const int yr = S.nr8 + k, rh = (k & 7) >> 1;
+                  const unsigned rowM = mS + (unsigned)tile_off(yr >> 3, 0) * 8u + ((k & 7) << 6);
+                  const unsigned rowP = apS + (unsigned)((k >> 3) * dptc) * 512u + ((k & 7) << 6);
+#pragma unroll
+                  for (int u = 0; u < kCol; ++u) {
+                    const int ty = cty[u];
+                    const double* src = arow + (long long)(lane + 32 * u) * p.a_cs;
+                    if (ty == VT_R || ty == VT_DP) cp_async8_s((ty == VT_R ? rowM : rowP) + cof[u] + (((chf[u] ^ rh) & 3) << 4), src);
+                    else if (ty == VT_D0) cp_async8(M + mat_off(cps[u], yr), src);
+                  }
+                }
+              } else {
+#pragma unroll 1
+                for (int j = warp; j < n; j += kWarps) {
+                  const int ty = I.vtype[j], ps = I.vpos[j];
+                  if (ty == VT_D1) continue;
+                  const double* acol = Ag + (long long)j * p.a_cs;
+                  for (int k = lane; k < m; k += 32) {
+                    const int yr = S.nr8 + k;
+                    if (ty == VT_R) cp_async8(M + mat_off(yr, ps), acol + k);
+                    else if (ty == VT_D0) cp_async8(M + mat_off(ps, yr), acol + k);
+                    else cp_async8(AP + (size_t)((k >> 3) * dptc + (ps >> 3)) * 64 + el_off(k & 7, ps & 7), acol + k);
+                  }
                 }
               }
             }
             // decoupled unit pivots on the pads, cost of the zero-cost block, 1/h of the D+ columns
-            if (t < S.N8) {
-              const bool pad = (t >= S.nr && t < S.nr8) || (yrow >= m && yrow < m8) || (t >= S.nr8 + m8 + S.nd0);
+            if (t < Se.N8) {
+              const bool pad = (t >= S.nr && t < S.nr8) || (yrow >= m && yrow < m8) || (t >= S.nr8 + m8 + Se.nd0);
               if (pad) M[mat_off(t, t)] = 1.0;
             }
-            if (vc.type == VT_D0) M[mat_off(vc.pos, vc.pos)] = vc.qd + shift;
-            if (vc.type == VT_DP) hinv[vc.pos] = hi;
+            if (ve.type == VT_D0) M[mat_off(ve.pos, ve.pos)] = ve.qd + shift;
+            if (ve.type == VT_DP) hinv[ve.pos] = hi;
+            SPROF(2);
             cp_async_wait_all();
             __syncthreads();
+            SPROF(3);
             if (t < S.nr && shift != 0.0) M[mat_off(t, t)] += shift;
             // -C on the constraint block: C_IJ = sum_kt AP_I,kt diag(1/h) AP_J,kt'  (one tile per warp and round)
             {
@@ -489,7 +743,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
                 const double* ai = AP + (size_t)(Ic * dptc) * 64 + fragC;
                 const double* aj = AP + (size_t)(Jc * dptc) * 64 + fragC;
 #pragma unroll 1
-                for (int kt = 0; kt < S.dpt; ++kt) {
+                for (int kt = 0; kt < Se.dpt; ++kt) {
                   const double2 a = ld2(ai + 64 * kt), b = ld2(aj + 64 * kt), h = ld2(hinv + 8 * kt + 2 * fq);
                   dmma(ca.x, ca.y, a.x * h.x, b.x);
                   dmma(cb.x, cb.y, a.y * h.y, b.y);
@@ -500,19 +754,21 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
             __syncthreads();
             // one-entry columns: a^2 / h on one diagonal entry each (at most one such column per row); the pad
             // rows of the constraint block get their unit pivot back (the tile store above overwrote it)
-            if (vc.type == VT_D1 && vc.nnz == 1) M[mat_off(S.nr8 + vc.krow, S.nr8 + vc.krow)] -= vc.aval * vc.aval * hi;
+            if (ve.type == VT_D1 && ve.nnz == 1) M[mat_off(S.nr8 + ve.krow, S.nr8 + ve.krow)] -= ve.aval * ve.aval * hi;
             if (yrow >= m && yrow < m8) M[mat_off(t, t)] = 1.0;
             __syncthreads();
+            SPROF(4);
 #ifdef FCCQP_DEV
-            { unsigned long long* trbuf = nullptr; int trn = 0; factor_tiles<kThreads>(M, dinv, dneg, S.NB, S.NB32, trbuf, trn); }
+            { unsigned long long* trbuf = nullptr; int trn = 0; factor_tiles<kThreads>(M, dinv, dneg, Se.NB, Se.NB32, trbuf, trn); }
 #else
-            factor_tiles<kThreads>(M, dinv, dneg, S.NB, S.NB32);
+            factor_tiles<kThreads>(M, dinv, dneg, Se.NB, Se.NB32);
 #endif
+            SPROF(5);
             fact_cycles += (unsigned long long)(clock64() - t_f0);
             // inertia (+ on R and D0 rows and all pads, - on the constraint rows): anything else goes to the general kernel
             {
               bool badp = false;
-              if (t < S.N8) {
+              if (t < Se.N8) {
                 const double dn = dneg[t];
                 const bool neg = yrow >= 0 && yrow < m;
                 badp = !isfinite(dn) || (neg ? !(dn > 0.0) : !(dn < 0.0));
@@ -521,26 +777,32 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
             }
           }  // lazy factorization
 
-          // ---- right-hand side of this thread's variable (constraint rows: b_eq, in shared memory)
-          double r = 0.0;
-          if (is_x) {
-            if (pass == 0) r = -v_b;
-            else {
-              // -(b + q_rho), q_rho = -rho (xbar - mu_x) with the cone segment overwritten (fcc_qp.cpp:81-83)
-              const double w = in_cone ? (lcbar[t - lcs] - muc[t - lcs]) : (v_xbar - v_mux);
-              r = -(v_b - p.rho * w);
+          // -(b + q_rho), q_rho = -rho (xbar - mu_x) with the cone segment overwritten (fcc_qp.cpp:81-83); w = 0 in pass 0
+          const double w = (pass == 1 && is_x) ? (in_cone ? (lcbar[t - lcs] - muc[t - lcs]) : (v_xbar - v_mux)) : 0.0;
+          // Long-running QP (iteration full_inverse_at): first x_base = the solve for w = 0 through the factors
+          // (rep 0), then the explicit inverse of the reduced matrix; every later x-update is
+          // x_base + (one symmetric product with the rho w part).  One call site: the solve is inlined once.
+          const bool make_op = pass == 1 && !full_inverse && iter >= p.full_inverse_at;
+#pragma unroll 1
+          for (int rep = make_op ? 0 : 1; rep < 2; ++rep) {
+            const bool base_solve = rep == 0;
+            const bool op = !base_solve && full_inverse;
+            double r = 0.0;
+            if (is_x) r = (base_solve || pass == 0) ? -v_b : (op ? p.rho * w : -(v_b - p.rho * w));
+            const double res = struct_xsolve<kThreads>(p, L, smem, I, Se, ve, Qg, Ag, q_slow, q_fast, r, hi, shift, op, op,
+                                                       pass == 0 && p.struct_refine != 0);
+            if (base_solve) {
+              v_xbase = res;
+              __syncthreads();
+              complete_inverse<kThreads>(M, Se.NB);
+              form_g<kThreads>(M, dinv, Se.NB, Se.NB, Se.NB);
+              full_inverse = true;
+            } else {
+              val = op ? v_xbase + res : res;
             }
           }
-          if (!full_inverse && pass == 1 && iter >= p.full_inverse_at) {
-            // long-running QP: explicit inverse of the reduced matrix, every later x-update is one symmetric product
-            __syncthreads();
-            complete_inverse<kThreads>(M, S.NB);
-            form_g<kThreads>(M, dinv, S.NB, S.NB, S.NB);
-            full_inverse = true;
-          }
-          val = struct_xsolve<kThreads>(p, L, smem, I, S, vc, Qg, Ag, q_slow, q_fast, r, hi, shift, full_inverse,
-                                        pass == 0 && p.struct_refine != 0);
         }  // x-update solve
+        SPROF(6);
 
         if (pass == 0) {
           v_x = val;
@@ -583,8 +845,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
         if (conv || iter + 1 == iters) {
           block_reduce2<false>(rx, rc, red, parity);
           res_x = rx; res_c = rc;
-          if (conv) { n_iter = iter; break; }
+          if (conv) { n_iter = iter; SPROF(8); break; }
         }
+        SPROF(8);
       }
     }
 
@@ -626,7 +889,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
         atomicAdd(p.cycles + 1, (unsigned long long)(clock64() - t_start));
       }
     }
+    SPROF(9);
+#ifdef FCCQP_DEV
+    if (p.prof && tid == 0) s_prof[14] += 1;
+#endif
   }
+#ifdef FCCQP_DEV
+  if (p.prof && tid == 0)
+    for (int i = 0; i < 16; ++i) atomicAdd(p.prof + i, s_prof[i]);
+#endif
 }
 
 }  // namespace fccqp

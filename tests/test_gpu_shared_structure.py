@@ -44,7 +44,9 @@ def test_shared_structure_matches_general_path_and_oracle(name, B):
 
     zs, its, sts, launches_shared = run(Q1.expand(B, qp.n, qp.n), A1.expand(B, qp.m, qp.n))       # batch stride 0
     zg, itg, stg, launches_general = run(torch.as_tensor(qp.Q, device=dev), torch.as_tensor(qp.A_eq, device=dev))
-    assert launches_shared == 2 and launches_general == 1           # the shared path really ran
+    # the shared path really ran (2 launches); the materialised batch takes the structure-exploiting kernel
+    # (probe + reduced kernel + general kernel over the handed-over list = 3) or the general kernel alone (1)
+    assert launches_shared == 2 and launches_general in (1, 3)
     rel = lambda z, ref: (np.abs(z - ref).max(1) / np.maximum(1.0, np.abs(ref).max(1))).max()
     assert rel(zs, zg) <= 1e-7
     assert (its != itg).mean() <= 0.01
