@@ -353,8 +353,18 @@ __device__ __forceinline__ double struct_xsolve(const SolveParams& p, const Stru
                                                 const double* __restrict__ Qg, const double* __restrict__ Ag,
                                                 const long long q_slow, const long long q_fast, const double r,
                                                 const double hi, const double shift, const bool use_op, const bool homog,
-                                                const bool refine) {
+                                                const bool refine
+#ifdef FCCQP_DEV
+                                                , unsigned long long* s_prof, long long& t_prof
+#endif
+                                                ) {
   const int t = threadIdx.x;
+#ifdef FCCQP_DEV
+  const int tid = t;
+#define XPROF(slot) do { if (p.prof && tid == 0) { const long long t_now = clock64(); s_prof[slot] += (unsigned long long)(t_now - t_prof); t_prof = t_now; } } while (0)
+#else
+#define XPROF(slot) do { } while (0)
+#endif
   const int n = p.n, m = p.m;
   double* const M = smem + L.off_M;
   const double* const AP = smem + L.off_AP;
@@ -391,6 +401,7 @@ __device__ __forceinline__ double struct_xsolve(const SolveParams& p, const Stru
     acc = (homog ? 0.0 : beqs[yrow]) - s;
     if (I.d1var[yrow] >= 0) acc -= d1c[yrow];
   } else if (row_0) acc = rf[I.d0list[zrow]];
+  XPROF(6);
   double val;
 #ifdef FCCQP_DEV
   unsigned long long* trbuf = nullptr; int trn = 0;
@@ -400,6 +411,7 @@ __device__ __forceinline__ double struct_xsolve(const SolveParams& p, const Stru
   if (use_op) val = g_apply(M, tbuf, acc, S.NB, S.N8);
   else val = kkt_solve(M, dinv, tbuf, ybuf, acc, S.NB, S.NB32, S.N8);
 #endif
+  XPROF(7);
   if (t < S.N8) sred[t] = val;
   __syncthreads();
   const double* ys = sred + S.nr8;
@@ -483,8 +495,11 @@ __device__ __forceinline__ double struct_xsolve(const SolveParams& p, const Stru
 #endif
     if (t < S.N8) sred[t] = val + dv;
     __syncthreads();
+    XPROF(10);
   }
-  return recover();
+  const double xr = recover();
+  XPROF(11);
+  return xr;
 }
 
 #ifdef FCCQP_DEV
@@ -667,16 +682,22 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
             {
               constexpr int kCol = kThreads / 32;
               const unsigned mS = smem_u32(M), apS = smem_u32(AP);
-              // per owned column: class, position, and the row-independent part of its byte offset inside a tile row
-              // (tile column * 512 + (c & 1) * 8; the 16-byte chunk (c >> 1) is XOR-swizzled with the row below)
-              int cty[kCol], cps[kCol], cof[kCol], chf[kCol];
+              // per owned column: kind (0 R, 1 D+, 2 D0, 3 nothing to copy), the 16-byte chunk it sits in (XOR-swizzled with
+              // the other index below) and the row-independent part of its destination: R / D+ columns: byte offset inside a
+              // tile row (tile column * 512 + (c & 1) * 8); D0 columns (stored TRANSPOSED, the variable is the row): the
+              // shared address of that row.  Branch-free inner loops: lanes of one warp hold columns of every kind.
+              int ckind[kCol], cps[kCol], chf[kCol];
+              unsigned cof[kCol];
 #pragma unroll
               for (int u = 0; u < kCol; ++u) {
                 const int j = lane + 32 * u;
-                cty[u] = j < n ? I.vtype[j] : VT_NONE;
-                cps[u] = j < n ? I.vpos[j] : 0;
-                cof[u] = ((cps[u] >> 3) << 9) + ((cps[u] & 1) << 3);
-                chf[u] = (cps[u] & 7) >> 1;
+                const int ty = j < n ? I.vtype[j] : VT_NONE;
+                const int ps = j < n ? I.vpos[j] : 0;
+                ckind[u] = ty == VT_R ? 0 : (ty == VT_DP ? 1 : (ty == VT_D0 ? 2 : 3));
+                cps[u] = ps;
+                chf[u] = (ps & 7) >> 1;
+                cof[u] = ty == VT_D0 ? mS + (unsigned)tile_off(ps >> 3, 0) * 8u + ((ps & 7) << 6)
+                                     : (unsigned)(((ps >> 3) << 9) + ((ps & 1) << 3));
               }
 #pragma unroll 1
               for (int a = warp; a < S.nr; a += kWarps) {
@@ -685,7 +706,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
                 const int rh = (a & 7) >> 1;
 #pragma unroll
                 for (int u = 0; u < kCol; ++u)
-                  if (cty[u] == VT_R && cps[u] <= a)
+                  if (ckind[u] == 0 && cps[u] <= a)
                     cp_async8_s(rowS + cof[u] + (((chf[u] ^ rh) & 3) << 4), qrow + (long long)(lane + 32 * u) * q_fast);
               }
               if (p.a_cs == 1 || p.a_rs != 1) {
@@ -695,12 +716,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
                   const int yr = S.nr8 + k, rh = (k & 7) >> 1;
                   const unsigned rowM = mS + (unsigned)tile_off(yr >> 3, 0) * 8u + ((k & 7) << 6);
                   const unsigned rowP = apS + (unsigned)((k >> 3) * dptc) * 512u + ((k & 7) << 6);
+                  const unsigned colT = (unsigned)(((yr >> 3) << 9) + ((yr & 1) << 3));   // this row as a COLUMN of a D0 row
 #pragma unroll
                   for (int u = 0; u < kCol; ++u) {
-                    const int ty = cty[u];
-                    const double* src = arow + (long long)(lane + 32 * u) * p.a_cs;
-                    if (ty == VT_R || ty == VT_DP) cp_async8_s((ty == VT_R ? rowM : rowP) + cof[u] + (((chf[u] ^ rh) & 3) << 4), src);
-                    else if (ty == VT_D0) cp_async8(M + mat_off(cps[u], yr), src);
+                    const int kd = ckind[u];
+                    const unsigned base = kd == 0 ? rowM : (kd == 1 ? rowP : colT);
+                    if (kd < 3) cp_async8_s(base + cof[u] + (((chf[u] ^ rh) & 3) << 4), arow + (long long)(lane + 32 * u) * p.a_cs);
                   }
                 }
               } else {
@@ -789,8 +810,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
             const bool op = !base_solve && full_inverse;
             double r = 0.0;
             if (is_x) r = (base_solve || pass == 0) ? -v_b : (op ? p.rho * w : -(v_b - p.rho * w));
+#ifdef FCCQP_DEV
+            const double res = struct_xsolve<kThreads>(p, L, smem, I, Se, ve, Qg, Ag, q_slow, q_fast, r, hi, shift, op, op,
+                                                       pass == 0 && p.struct_refine != 0, s_prof, t_prof);
+#else
             const double res = struct_xsolve<kThreads>(p, L, smem, I, Se, ve, Qg, Ag, q_slow, q_fast, r, hi, shift, op, op,
                                                        pass == 0 && p.struct_refine != 0);
+#endif
             if (base_solve) {
               v_xbase = res;
               __syncthreads();
@@ -802,7 +828,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
             }
           }
         }  // x-update solve
-        SPROF(6);
+        SPROF(12);
 
         if (pass == 0) {
           v_x = val;
