@@ -146,12 +146,13 @@ int pick_kernel(const DeviceCtx& ctx, int n, int m, int nc, KernelFn* fn, int* t
 }
 
 // Structure-exploiting kernel instances (fccqp_struct.cuh): threads >= max(n, padded reduced KKT size).
-int pick_struct_kernel(const fccqp::StructLayout& sl, int n, KernelFn* fn, int* threads) {
+// front: 0 = register front end (row-major 16-byte aligned Q / A_eq, even n), 1 = staged front end (any layout).
+int pick_struct_kernel(const fccqp::StructLayout& sl, int n, int front, KernelFn* fn, int* threads) {
   const int need = n > sl.N8c ? n : sl.N8c;
-  if (need <= 64) { *threads = 64; *fn = (KernelFn)fccqp::fccqp_struct_kernel<64, 8>; }
-  else if (need <= 96) { *threads = 96; *fn = (KernelFn)fccqp::fccqp_struct_kernel<96, 5>; }
-  else if (need <= 128) { *threads = 128; *fn = (KernelFn)fccqp::fccqp_struct_kernel<128, 4>; }
-  else if (need <= 256) { *threads = 256; *fn = (KernelFn)fccqp::fccqp_struct_kernel<256, 2>; }
+  if (need <= 64) { *threads = 64; *fn = front ? (KernelFn)fccqp::fccqp_struct_kernel<64, 8, 1> : (KernelFn)fccqp::fccqp_struct_kernel<64, 8, 0>; }
+  else if (need <= 96) { *threads = 96; *fn = front ? (KernelFn)fccqp::fccqp_struct_kernel<96, 5, 1> : (KernelFn)fccqp::fccqp_struct_kernel<96, 5, 0>; }
+  else if (need <= 128) { *threads = 128; *fn = front ? (KernelFn)fccqp::fccqp_struct_kernel<128, 4, 1> : (KernelFn)fccqp::fccqp_struct_kernel<128, 4, 0>; }
+  else if (need <= 256) { *threads = 256; *fn = front ? (KernelFn)fccqp::fccqp_struct_kernel<256, 2, 1> : (KernelFn)fccqp::fccqp_struct_kernel<256, 2, 0>; }
   else return 1;
   return 0;
 }
@@ -329,7 +330,15 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool
       fccqp::StructLayout sl(p.n, p.m, p.nc, caps[0], caps[1] + caps[2], caps[2]);   // D+ store: pass 1 eliminates D0 too
       KernelFn sfn = nullptr; int sthreads = 0;
       // worth it when at least one tile row of the KKT matrix goes away
-      if (sl.N8c + 8 <= p.lay.N8 && sl.bytes() <= (size_t)ctx.max_smem_optin && pick_struct_kernel(sl, p.n, &sfn, &sthreads) == 0) {
+      // front end: registers (16-byte row loads straight from L2) when both matrices are row-major, aligned and even,
+      // else staged through shared memory (FCCQP_STRUCT_FRONT=staged forces the latter; ablation in profiles/)
+      const long long q_slow = p.q_cs <= p.q_rs ? p.q_rs : p.q_cs, q_fast = p.q_cs <= p.q_rs ? p.q_cs : p.q_rs;
+      const char* front_env = getenv("FCCQP_STRUCT_FRONT");
+      const bool reg_front = !(front_env && !strcmp(front_env, "staged")) && (p.n & 1) == 0 && q_fast == 1 && (q_slow & 1) == 0 &&
+                             (p.q_bs & 1) == 0 && (reinterpret_cast<uintptr_t>(p.Q) & 15) == 0 && p.a_cs == 1 && (p.a_rs & 1) == 0 &&
+                             (p.a_bs & 1) == 0 && (reinterpret_cast<uintptr_t>(p.A) & 15) == 0;
+      if (sl.N8c + 8 <= p.lay.N8 && sl.bytes() <= (size_t)ctx.max_smem_optin &&
+          pick_struct_kernel(sl, p.n, reg_front ? 0 : 1, &sfn, &sthreads) == 0) {
         int sctas = 0;
         if ((rc = occupancy_of(sfn, sthreads, sl.bytes(), &sctas))) return rc;
         if (cta_cap > 0 && cta_cap < sctas) sctas = cta_cap;

@@ -107,6 +107,7 @@ struct StructLayout {
   int N8c, NBc, NB32c, NTc, NBTc;
   int off_M, off_AP, off_dinv, off_dneg, off_tbuf, off_ybuf, off_sred, off_rf, off_vd, off_hinv, off_d1c, off_beq;
   int off_qd, off_xs, off_lcbar, off_muc, off_mu, off_red, off_int;
+  int off_part;    // [warps][n8] per-warp partial column sums (iterative refinement of the register front end)
   // int region (offsets in ints from off_int)
   int io_vtype, io_vpos, io_rlist, io_dplist, io_d0list, io_d1var, io_rowcnt, io_wtot, io_nzflag, io_colcnt, io_colk, ints_total;
   int stage_cap;   // doubles of the [M | AP] region: staging space of the classification (>= 4 rows of Q)
@@ -132,6 +133,11 @@ struct StructLayout {
     off_ybuf = o;  o += NTc;
     off_sred = o;  o += NTc;
     off_rf = o;    o += n8;
+    {
+      const int need = n > N8c ? n : N8c;   // thread count of the kernel instance (pick_struct_kernel)
+      const int warps = need <= 64 ? 2 : (need <= 96 ? 3 : (need <= 128 ? 4 : 8));
+      off_part = o;  o += warps * n8;
+    }
     off_vd = o;    o += ndp8c + 8;
     off_hinv = o;  o += ndp8c + 8;
     off_d1c = o;   o += m8 + 8;

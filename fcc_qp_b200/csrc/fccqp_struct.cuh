@@ -108,6 +108,60 @@ struct StageCtl {
   bool q_bulk, a_bulk;       // dense contiguous 16-byte aligned blocks
 };
 
+// Second half of the classification, common to both front ends: the per-column findings (off-diagonal flag and
+// diagonal entry of Q; entry count, row and value of the last entry of the A_eq column) become a class and a position per
+// variable.  All threads of the CTA.
+template <int kThreads>
+__device__ __forceinline__ int struct_classify_finish(const int n, const int m8, const double* __restrict__ qd_s,
+                                                      const double* __restrict__ colv, const StructInts& I, const int capR,
+                                                      const int capP, const int cap0, VarClass& vc, int& nr, int& ndp, int& nd0) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kThreads / 32;
+  __syncthreads();
+  int type = VT_NONE, nnz = 0, kr = 0;
+  double qd = 0.0, av = 0.0;
+  if (tid < n) {
+    nnz = I.colcnt[tid];
+    if (nnz == 1) { kr = I.colk[tid]; av = colv[tid]; }
+    qd = qd_s[tid];
+    if (I.nzflag[tid] || !(qd >= 0.0)) type = VT_R;          // (NaN or negative curvature: leave it to the dense block)
+    else if (qd < 1e-200) type = VT_D0;
+    else type = nnz <= 1 ? VT_D1 : VT_DP;
+    if (type == VT_D1 && nnz == 1) atomicAdd(&I.rowcnt[kr], 1);
+  }
+  __syncthreads();
+  // two one-entry columns on the same constraint row: keep them as general columns
+  if (type == VT_D1 && nnz == 1 && I.rowcnt[kr] > 1) type = VT_DP;
+  const unsigned bR = __ballot_sync(0xffffffffu, type == VT_R);
+  const unsigned bP = __ballot_sync(0xffffffffu, type == VT_DP);
+  const unsigned b0 = __ballot_sync(0xffffffffu, type == VT_D0);
+  if (lane == 0) { I.wtot[3 * warp] = __popc(bR); I.wtot[3 * warp + 1] = __popc(bP); I.wtot[3 * warp + 2] = __popc(b0); }
+  __syncthreads();
+  int oR = 0, oP = 0, o0 = 0;
+  nr = 0; ndp = 0; nd0 = 0;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) {
+    const int a = I.wtot[3 * w], b = I.wtot[3 * w + 1], c = I.wtot[3 * w + 2];
+    if (w < warp) { oR += a; oP += b; o0 += c; }
+    nr += a; ndp += b; nd0 += c;
+  }
+  const unsigned lt = (1u << lane) - 1u;
+  const int nr8 = (nr + 7) & ~7;
+  int bad = (nr > capR || ndp + nd0 > capP || nd0 > cap0) ? 1 : 0;   // block-uniform (capP covers pass 1: D+ and D0)
+  int pos = 0;
+  if (!bad && tid < n) {
+    if (type == VT_R) { pos = oR + __popc(bR & lt); I.rlist[pos] = tid; }
+    else if (type == VT_DP) { pos = oP + __popc(bP & lt); I.dplist[pos] = tid; }
+    else if (type == VT_D0) { const int q = o0 + __popc(b0 & lt); I.d0list[q] = tid; pos = nr8 + m8 + q; }
+    else { pos = kr; if (nnz == 1) I.d1var[kr] = tid; }
+    I.vtype[tid] = type;
+    I.vpos[tid] = pos;
+  }
+  bad |= __syncthreads_or(type == VT_D0 && nnz == 0);
+  vc.type = type; vc.pos = pos; vc.krow = kr; vc.nnz = nnz; vc.aval = av; vc.qd = qd;
+  return bad;
+}
+
 template <int kThreads>
 __device__ __forceinline__ int struct_classify(const int n, const int m, const int n8, const int m8,
                                                const double* __restrict__ Qg, const long long q_slow, const long long q_fast,
@@ -235,49 +289,213 @@ __device__ __forceinline__ int struct_classify(const int n, const int m, const i
       atomicExch(reinterpret_cast<unsigned long long*>(colv + c0 + 1), (unsigned long long)__double_as_longlong(vy));
     }
   }
-  __syncthreads();
-  int type = VT_NONE, nnz = 0, kr = 0;
-  double qd = 0.0, av = 0.0;
-  if (tid < n) {
-    nnz = I.colcnt[tid];
-    if (nnz == 1) { kr = I.colk[tid]; av = colv[tid]; }
-    qd = qd_s[tid];
-    if (I.nzflag[tid] || !(qd >= 0.0)) type = VT_R;          // (NaN or negative curvature: leave it to the dense block)
-    else if (qd < 1e-200) type = VT_D0;
-    else type = nnz <= 1 ? VT_D1 : VT_DP;
-    if (type == VT_D1 && nnz == 1) atomicAdd(&I.rowcnt[kr], 1);
-  }
-  __syncthreads();
-  // two one-entry columns on the same constraint row: keep them as general columns
-  if (type == VT_D1 && nnz == 1 && I.rowcnt[kr] > 1) type = VT_DP;
-  const unsigned bR = __ballot_sync(0xffffffffu, type == VT_R);
-  const unsigned bP = __ballot_sync(0xffffffffu, type == VT_DP);
-  const unsigned b0 = __ballot_sync(0xffffffffu, type == VT_D0);
-  if (lane == 0) { I.wtot[3 * warp] = __popc(bR); I.wtot[3 * warp + 1] = __popc(bP); I.wtot[3 * warp + 2] = __popc(b0); }
-  __syncthreads();
-  int oR = 0, oP = 0, o0 = 0;
-  nr = 0; ndp = 0; nd0 = 0;
+  return struct_classify_finish<kThreads>(n, m8, qd_s, colv, I, capR, capP, cap0, vc, nr, ndp, nd0);
+}
+
+// ---- register front end ------------------------------------------------------------------------------
+// For row-major, 16-byte aligned Q and A_eq with an even number of columns (what numpy / torch callers hand
+// over) neither pass needs staging: a warp reads whole matrix rows with one 16-byte load per lane and column
+// pair, kRows rows in flight, straight from L2 (the previous QP of this CTA prefetched them there with ONE
+// bulk-async instruction per matrix, l2_prefetch below).  Pass 1 classifies from registers, pass 2 (after the
+// class and position of every column are known) reads the rows that are still needed a second time and
+// stores every element at its place in the tile matrix.  No shared-memory staging, no asynchronous-copy queue,
+// a few hundred instructions per warp.
+__device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+__device__ __forceinline__ void sts8(unsigned smem_dst, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(smem_dst), "d"(v) : "memory");
+}
+
+// pairs of columns per lane (lane + 32 u), rows in flight per warp: kPairs * kRows = 8 loads of 16 bytes per lane
+template <int kThreads> struct FrontGeom {
+  static constexpr int kPairs = (kThreads / 2 + 31) / 32;
+  static constexpr int kRows = kPairs >= 4 ? 2 : (kPairs == 2 ? 4 : 8);
+};
+
+template <int kThreads>
+__device__ __forceinline__ int struct_classify_ldg(const int n, const int m, const int n8, const int m8,
+                                                   const double* __restrict__ Qg, const long long q_slow,
+                                                   const double* __restrict__ Ag, const long long a_rs,
+                                                   double* __restrict__ qd_s, double* __restrict__ colv, const StructInts& I,
+                                                   const int capR, const int capP, const int cap0, VarClass& vc, int& nr,
+                                                   int& ndp, int& nd0) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kThreads / 32;
+  constexpr int kPairs = FrontGeom<kThreads>::kPairs, kRows = FrontGeom<kThreads>::kRows;
+  const int npair = n >> 1;
+  for (int e = tid; e < m8 + 8; e += kThreads) { I.rowcnt[e] = 0; I.d1var[e] = -1; }
+  for (int e = tid; e < n8; e += kThreads) I.colcnt[e] = 0;
+  // ---- Q (symmetric): variable i is separable <=> row i has no off-diagonal entry
+#pragma unroll 1
+  for (int i0 = warp; i0 < n; i0 += kWarps * kRows) {
+    double2 v[kRows][kPairs];
 #pragma unroll
-  for (int w = 0; w < kWarps; ++w) {
-    const int a = I.wtot[3 * w], b = I.wtot[3 * w + 1], c = I.wtot[3 * w + 2];
-    if (w < warp) { oR += a; oP += b; o0 += c; }
-    nr += a; ndp += b; nd0 += c;
+    for (int r = 0; r < kRows; ++r) {
+      const int i = i0 + r * kWarps;
+#pragma unroll
+      for (int u = 0; u < kPairs; ++u) {
+        const int cp = lane + 32 * u;
+        v[r][u] = (i < n && cp < npair) ? ldg2(Qg + (size_t)i * q_slow + 2 * cp) : make_double2(0.0, 0.0);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const int i = i0 + r * kWarps;
+      if (i < n) {   // warp-uniform
+        bool nz = false;
+#pragma unroll
+        for (int u = 0; u < kPairs; ++u) {
+          const int c0 = 2 * (lane + 32 * u);
+          if (c0 == i) qd_s[i] = v[r][u].x; else nz = nz || (v[r][u].x != 0.0);
+          if (c0 + 1 == i) qd_s[i] = v[r][u].y; else nz = nz || (v[r][u].y != 0.0);
+        }
+        nz = __any_sync(0xffffffffu, nz);
+        if (lane == 0) I.nzflag[i] = nz ? 1 : 0;
+      }
+    }
   }
-  const unsigned lt = (1u << lane) - 1u;
-  const int nr8 = (nr + 7) & ~7;
-  int bad = (nr > capR || ndp + nd0 > capP || nd0 > cap0) ? 1 : 0;   // block-uniform (capP covers pass 1: D+ and D0)
-  int pos = 0;
-  if (!bad && tid < n) {
-    if (type == VT_R) { pos = oR + __popc(bR & lt); I.rlist[pos] = tid; }
-    else if (type == VT_DP) { pos = oP + __popc(bP & lt); I.dplist[pos] = tid; }
-    else if (type == VT_D0) { const int q = o0 + __popc(b0 & lt); I.d0list[q] = tid; pos = nr8 + m8 + q; }
-    else { pos = kr; if (nnz == 1) I.d1var[kr] = tid; }
-    I.vtype[tid] = type;
-    I.vpos[tid] = pos;
+  // ---- A_eq: entry count of every column, and its entry if there is only one
+  int cx[kPairs], cy[kPairs], kx[kPairs], ky[kPairs];
+  double vx[kPairs], vy[kPairs];
+#pragma unroll
+  for (int u = 0; u < kPairs; ++u) { cx[u] = cy[u] = kx[u] = ky[u] = 0; vx[u] = vy[u] = 0.0; }
+#pragma unroll 1
+  for (int k0 = warp; k0 < m; k0 += kWarps * kRows) {
+    double2 v[kRows][kPairs];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const int k = k0 + r * kWarps;
+#pragma unroll
+      for (int u = 0; u < kPairs; ++u) {
+        const int cp = lane + 32 * u;
+        v[r][u] = (k < m && cp < npair) ? ldg2(Ag + (size_t)k * a_rs + 2 * cp) : make_double2(0.0, 0.0);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const int k = k0 + r * kWarps;
+#pragma unroll
+      for (int u = 0; u < kPairs; ++u) {
+        if (v[r][u].x != 0.0) { ++cx[u]; kx[u] = k; vx[u] = v[r][u].x; }
+        if (v[r][u].y != 0.0) { ++cy[u]; ky[u] = k; vy[u] = v[r][u].y; }
+      }
+    }
   }
-  bad |= __syncthreads_or(type == VT_D0 && nnz == 0);
-  vc.type = type; vc.pos = pos; vc.krow = kr; vc.nnz = nnz; vc.aval = av; vc.qd = qd;
-  return bad;
+  __syncthreads();   // colcnt zeroed by everybody
+  // (several warps with entries in one column: the count says >= 2 and the entry is not used)
+#pragma unroll
+  for (int u = 0; u < kPairs; ++u) {
+    const int c0 = 2 * (lane + 32 * u);
+    if (cx[u]) {
+      atomicAdd(&I.colcnt[c0], cx[u]); atomicExch(&I.colk[c0], kx[u]);
+      atomicExch(reinterpret_cast<unsigned long long*>(colv + c0), (unsigned long long)__double_as_longlong(vx[u]));
+    }
+    if (cy[u]) {
+      atomicAdd(&I.colcnt[c0 + 1], cy[u]); atomicExch(&I.colk[c0 + 1], ky[u]);
+      atomicExch(reinterpret_cast<unsigned long long*>(colv + c0 + 1), (unsigned long long)__double_as_longlong(vy[u]));
+    }
+  }
+  return struct_classify_finish<kThreads>(n, m8, qd_s, colv, I, capR, capP, cap0, vc, nr, ndp, nd0);
+}
+
+// Pass 2 of the register front end: Q_RR -> top-left tiles (lower triangle), A_eq: R columns -> constraint rows of
+// the matrix, D0 columns -> transposed into the trailing rows, D+ columns -> AP tiles.  I.vtype / I.vpos hold the
+// classes and positions of THIS pass (the ADMM pass eliminates the zero-cost variables too).  The destination region
+// has been zeroed (barrier in between).
+template <int kThreads>
+__device__ __forceinline__ void struct_scatter_ldg(const int n, const int m, const int nr, const int nr8, const int dptc,
+                                                   const double* __restrict__ Qg, const long long q_slow,
+                                                   const double* __restrict__ Ag, const long long a_rs,
+                                                   double* __restrict__ M, double* __restrict__ AP, const StructInts& I) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kWarps = kThreads / 32;
+  constexpr int kPairs = FrontGeom<kThreads>::kPairs, kRows = FrontGeom<kThreads>::kRows;
+  const int npair = n >> 1;
+  const unsigned mS = smem_u32(M), apS = smem_u32(AP);
+  // per owned column: kind (0 R, 1 D+, 2 D0, 3 nothing to store), the 16-byte chunk it sits in (XOR-swizzled with the
+  // other index) and the row-independent part of its destination: R / D+ columns: byte offset inside a tile row
+  // (tile column * 512 + (c & 1) * 8); D0 columns (stored TRANSPOSED, the variable is the row): the shared address
+  // of that row.
+  int kind[kPairs][2], ps[kPairs][2], chf[kPairs][2];
+  unsigned cof[kPairs][2];
+#pragma unroll
+  for (int u = 0; u < kPairs; ++u)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = 2 * (lane + 32 * u) + h;
+      const int ty = j < n ? I.vtype[j] : VT_NONE;
+      const int q = j < n ? I.vpos[j] : 0;
+      kind[u][h] = ty == VT_R ? 0 : (ty == VT_DP ? 1 : (ty == VT_D0 ? 2 : 3));
+      ps[u][h] = q;
+      chf[u][h] = (q & 7) >> 1;
+      cof[u][h] = ty == VT_D0 ? mS + (unsigned)tile_off(q >> 3, 0) * 8u + ((q & 7) << 6)
+                              : (unsigned)(((q >> 3) << 9) + ((q & 1) << 3));
+    }
+  // ---- Q: rows of the R variables, columns up to the diagonal
+#pragma unroll 1
+  for (int a0 = warp; a0 < nr; a0 += kWarps * kRows) {
+    double2 v[kRows][kPairs];
+    int ri[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const int a = a0 + r * kWarps;
+      ri[r] = a < nr ? I.rlist[a] : -1;
+    }
+#pragma unroll
+    for (int r = 0; r < kRows; ++r)
+#pragma unroll
+      for (int u = 0; u < kPairs; ++u) {
+        const int cp = lane + 32 * u;
+        v[r][u] = (ri[r] >= 2 * cp && cp < npair && (kind[u][0] == 0 || kind[u][1] == 0))
+                      ? ldg2(Qg + (size_t)ri[r] * q_slow + 2 * cp) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const int a = a0 + r * kWarps;
+      if (a < nr) {
+        const unsigned rowS = mS + (unsigned)tile_off(a >> 3, 0) * 8u + ((a & 7) << 6);
+        const int rh = (a & 7) >> 1;
+#pragma unroll
+        for (int u = 0; u < kPairs; ++u) {
+          if (kind[u][0] == 0 && ps[u][0] <= a) sts8(rowS + cof[u][0] + (((chf[u][0] ^ rh) & 3) << 4), v[r][u].x);
+          if (kind[u][1] == 0 && ps[u][1] <= a) sts8(rowS + cof[u][1] + (((chf[u][1] ^ rh) & 3) << 4), v[r][u].y);
+        }
+      }
+    }
+  }
+  // ---- A_eq: every row, every column that is stored
+#pragma unroll 1
+  for (int k0 = warp; k0 < m; k0 += kWarps * kRows) {
+    double2 v[kRows][kPairs];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const int k = k0 + r * kWarps;
+#pragma unroll
+      for (int u = 0; u < kPairs; ++u) {
+        const int cp = lane + 32 * u;
+        v[r][u] = (k < m && cp < npair && (kind[u][0] < 3 || kind[u][1] < 3))
+                      ? ldg2(Ag + (size_t)k * a_rs + 2 * cp) : make_double2(0.0, 0.0);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const int k = k0 + r * kWarps;
+      if (k < m) {
+        const int yr = nr8 + k, rh = (k & 7) >> 1;
+        const unsigned rowM = mS + (unsigned)tile_off(yr >> 3, 0) * 8u + ((k & 7) << 6);
+        const unsigned rowP = apS + (unsigned)((k >> 3) * dptc) * 512u + ((k & 7) << 6);
+        const unsigned colT = (unsigned)(((yr >> 3) << 9) + ((yr & 1) << 3));   // this row as a COLUMN of a D0 row
+#pragma unroll
+        for (int u = 0; u < kPairs; ++u)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int kd = kind[u][h];
+            const unsigned base = kd == 0 ? rowM : (kd == 1 ? rowP : colT);
+            const double val = h ? v[r][u].y : v[r][u].x;
+            if (kd < 3) sts8(base + cof[u][h] + (((chf[u][h] ^ rh) & 3) << 4), val);
+          }
+      }
+    }
+  }
 }
 
 // Probe: classifies `ns` QPs spread evenly over the batch and reports the largest structure seen
@@ -347,7 +565,7 @@ struct StructQP {
   int nr, nr8, ndp, dpt, nd0, NB, NB32, N8;
 };
 
-template <int kThreads>
+template <int kThreads, int kFront>
 __device__ __forceinline__ double struct_xsolve(const SolveParams& p, const StructLayout& L, double* __restrict__ smem,
                                                 const StructInts& I, const StructQP& S, const VarClass& vc,
                                                 const double* __restrict__ Qg, const double* __restrict__ Ag,
@@ -441,53 +659,152 @@ __device__ __forceinline__ double struct_xsolve(const SolveParams& p, const Stru
     const double x = recover();
     if (is_x) xs[t] = x;
     __syncthreads();
-    if (t < m) {
-      const double* arow = Ag + (long long)t * p.a_rs;
-      double sa = 0.0;
-#pragma unroll 1
-      for (int j0 = 0; j0 < n; j0 += kLB) {
-        double v[kLB];
+    double acc2 = 0.0;
+    if (kFront == 0) {
+      // Row-major aligned data: a warp takes whole rows (one 16-byte load per lane and column pair, kRows rows in
+      // flight, L2 hits): row k of A_eq gives the constraint residual b_eq,k - a_k x (warp reduction) and, in the same
+      // sweep, this warp's share of A_eq' y (per-lane column sums, combined across warps in a fixed order below);
+      // row i of an R variable gives (Q x)_i (separable columns are zero in such a row).
+      constexpr int kWarps = kThreads / 32;
+      constexpr int kPairs = FrontGeom<kThreads>::kPairs, kRows = FrontGeom<kThreads>::kRows;
+      const int lane = t & 31, warp = t >> 5;
+      const int npair = n >> 1;
+      double* const part = smem + L.off_part + warp * L.n8;
+      double2 xv[kPairs], cs[kPairs];
 #pragma unroll
-        for (int u = 0; u < kLB; ++u) v[u] = j0 + u < n ? arow[(long long)(j0 + u) * p.a_cs] : 0.0;
-#pragma unroll
-        for (int u = 0; u < kLB; ++u) sa = fma(v[u], j0 + u < n ? xs[j0 + u] : 0.0, sa);
+      for (int u = 0; u < kPairs; ++u) {
+        const int cp = lane + 32 * u;
+        xv[u] = cp < npair ? ld2(xs + 2 * cp) : make_double2(0.0, 0.0);
+        cs[u] = make_double2(0.0, 0.0);
       }
-      d1c[t] = beqs[t] - sa;
-    } else {
-      const int stride = kThreads - m > 0 ? kThreads - m : 1;
 #pragma unroll 1
-      for (int idx = t - m; idx < S.nr + S.nd0; idx += stride) {
-        const bool isR = idx < S.nr;
-        const int j = isR ? I.rlist[idx] : I.d0list[idx - S.nr];
-        double s0 = (isR ? shift : qd_s[j] + shift) * xs[j], s1 = 0.0;
-        if (isR) {
-          const double* qcol = Qg + (long long)j * q_fast;
-#pragma unroll 1
-          for (int a0 = 0; a0 < S.nr; a0 += kLB) {
-            double v[kLB];
+      for (int k0 = warp; k0 < m; k0 += kWarps * kRows) {
+        double2 v[kRows][kPairs];
 #pragma unroll
-            for (int u = 0; u < kLB; ++u) v[u] = a0 + u < S.nr ? qcol[(long long)I.rlist[a0 + u] * q_slow] : 0.0;
+        for (int r = 0; r < kRows; ++r) {
+          const int k = k0 + r * kWarps;
 #pragma unroll
-            for (int u = 0; u < kLB; ++u) s0 = fma(v[u], a0 + u < S.nr ? sred[a0 + u] : 0.0, s0);
+          for (int u = 0; u < kPairs; ++u) {
+            const int cp = lane + 32 * u;
+            v[r][u] = (k < m && cp < npair) ? ldg2(Ag + (size_t)k * p.a_rs + 2 * cp) : make_double2(0.0, 0.0);
           }
         }
-        const double* acol = Ag + (long long)j * p.a_cs;
+        double dot[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          const int k = k0 + r * kWarps;
+          const double yk = k < m ? ys[k] : 0.0;
+          double d = 0.0;
+#pragma unroll
+          for (int u = 0; u < kPairs; ++u) {
+            d = fma(v[r][u].x, xv[u].x, d); d = fma(v[r][u].y, xv[u].y, d);
+            cs[u].x = fma(v[r][u].x, yk, cs[u].x); cs[u].y = fma(v[r][u].y, yk, cs[u].y);
+          }
+          dot[r] = d;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int r = 0; r < kRows; ++r) dot[r] += __shfl_xor_sync(0xffffffffu, dot[r], o);
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          const int k = k0 + r * kWarps;
+          if (lane == 0 && k < m) d1c[k] = beqs[k] - dot[r];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kPairs; ++u) {
+        const int cp = lane + 32 * u;
+        if (cp < npair) st2(part + 2 * cp, cs[u]);
+      }
 #pragma unroll 1
-        for (int k0 = 0; k0 < m; k0 += kLB) {
+      for (int a0 = warp; a0 < S.nr; a0 += kWarps * kRows) {
+        double2 v[kRows][kPairs];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          const int a = a0 + r * kWarps;
+          const int i = a < S.nr ? I.rlist[a] : -1;
+#pragma unroll
+          for (int u = 0; u < kPairs; ++u) {
+            const int cp = lane + 32 * u;
+            v[r][u] = (i >= 0 && cp < npair) ? ldg2(Qg + (size_t)i * q_slow + 2 * cp) : make_double2(0.0, 0.0);
+          }
+        }
+        double dot[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          double d = 0.0;
+#pragma unroll
+          for (int u = 0; u < kPairs; ++u) { d = fma(v[r][u].x, xv[u].x, d); d = fma(v[r][u].y, xv[u].y, d); }
+          dot[r] = d;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int r = 0; r < kRows; ++r) dot[r] += __shfl_xor_sync(0xffffffffu, dot[r], o);
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          const int a = a0 + r * kWarps;
+          if (lane == 0 && a < S.nr) tbuf[a] = dot[r];
+        }
+      }
+      __syncthreads();
+      if (row_R || row_0) {
+        const int j = row_R ? I.rlist[t] : I.d0list[zrow];
+        double s = row_R ? fma(shift, xs[j], tbuf[t]) : (qd_s[j] + shift) * xs[j];
+        const double* pp = smem + L.off_part + j;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) s += pp[w * L.n8];
+        acc2 = rf[j] - s;
+      } else if (row_y) acc2 = d1c[yrow];
+    } else {
+      if (t < m) {
+        const double* arow = Ag + (long long)t * p.a_rs;
+        double sa = 0.0;
+#pragma unroll 1
+        for (int j0 = 0; j0 < n; j0 += kLB) {
           double v[kLB];
 #pragma unroll
-          for (int u = 0; u < kLB; ++u) v[u] = k0 + u < m ? acol[(long long)(k0 + u) * p.a_rs] : 0.0;
+          for (int u = 0; u < kLB; ++u) v[u] = j0 + u < n ? arow[(long long)(j0 + u) * p.a_cs] : 0.0;
 #pragma unroll
-          for (int u = 0; u < kLB; ++u) s1 = fma(v[u], k0 + u < m ? ys[k0 + u] : 0.0, s1);
+          for (int u = 0; u < kLB; ++u) sa = fma(v[u], j0 + u < n ? xs[j0 + u] : 0.0, sa);
         }
-        rf[j] -= s0 + s1;   // rf[j] held r_j
+        d1c[t] = beqs[t] - sa;
+      } else {
+        const int stride = kThreads - m > 0 ? kThreads - m : 1;
+#pragma unroll 1
+        for (int idx = t - m; idx < S.nr + S.nd0; idx += stride) {
+          const bool isR = idx < S.nr;
+          const int j = isR ? I.rlist[idx] : I.d0list[idx - S.nr];
+          double s0 = (isR ? shift : qd_s[j] + shift) * xs[j], s1 = 0.0;
+          if (isR) {
+            const double* qcol = Qg + (long long)j * q_fast;
+#pragma unroll 1
+            for (int a0 = 0; a0 < S.nr; a0 += kLB) {
+              double v[kLB];
+#pragma unroll
+              for (int u = 0; u < kLB; ++u) v[u] = a0 + u < S.nr ? qcol[(long long)I.rlist[a0 + u] * q_slow] : 0.0;
+#pragma unroll
+              for (int u = 0; u < kLB; ++u) s0 = fma(v[u], a0 + u < S.nr ? sred[a0 + u] : 0.0, s0);
+            }
+          }
+          const double* acol = Ag + (long long)j * p.a_cs;
+#pragma unroll 1
+          for (int k0 = 0; k0 < m; k0 += kLB) {
+            double v[kLB];
+#pragma unroll
+            for (int u = 0; u < kLB; ++u) v[u] = k0 + u < m ? acol[(long long)(k0 + u) * p.a_rs] : 0.0;
+#pragma unroll
+            for (int u = 0; u < kLB; ++u) s1 = fma(v[u], k0 + u < m ? ys[k0 + u] : 0.0, s1);
+          }
+          rf[j] -= s0 + s1;   // rf[j] held r_j
+        }
       }
+      __syncthreads();
+      if (row_R) acc2 = rf[I.rlist[t]];
+      else if (row_y) acc2 = d1c[yrow];
+      else if (row_0) acc2 = rf[I.d0list[zrow]];
     }
-    __syncthreads();
-    double acc2 = 0.0;
-    if (row_R) acc2 = rf[I.rlist[t]];
-    else if (row_y) acc2 = d1c[yrow];
-    else if (row_0) acc2 = rf[I.d0list[zrow]];
 #ifdef FCCQP_DEV
     const double dv = kkt_solve(M, dinv, tbuf, ybuf, acc2, S.NB, S.NB32, S.N8, trbuf, trn);
 #else
@@ -515,7 +832,9 @@ __device__ __forceinline__ double struct_xsolve(const SolveParams& p, const Stru
 #define SPROF(slot) do { } while (0)
 #endif
 
-template <int kThreads, int kMinBlocks>
+// kFront: 0 = register front end (row-major, 16-byte aligned Q and A_eq with an even column count; the host checks),
+// 1 = staged front end (any strides; bulk-async / cp.async staging through shared memory).
+template <int kThreads, int kMinBlocks, int kFront>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(const SolveParams p) {
   extern __shared__ __align__(16) double smem[];
   const StructLayout& L = p.slay;
@@ -610,8 +929,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
     const bool a_vec = p.a_cs == 1 && (n & 1) == 0 && (p.a_rs & 1) == 0 && (reinterpret_cast<uintptr_t>(Ag) & 15) == 0;
     sc.q_bulk = q_vec && q_slow == n && p.struct_bulk;
     sc.a_bulk = a_vec && p.a_rs == n && p.struct_bulk;
-    bool defer = struct_classify<kThreads>(n, m, n8, m8, Qg, q_slow, q_fast, q_vec, Ag, p.a_rs, p.a_cs, a_vec, M, L.stage_cap, sc,
-                                           qd_s, rf, I, L.nr8c, L.ndp8c, L.nd08c, vc, S.nr, S.ndp, S.nd0) != 0;
+    bool defer;
+    if (kFront == 0)
+      defer = struct_classify_ldg<kThreads>(n, m, n8, m8, Qg, q_slow, Ag, p.a_rs, qd_s, rf, I, L.nr8c, L.ndp8c, L.nd08c, vc, S.nr,
+                                            S.ndp, S.nd0) != 0;
+    else
+      defer = struct_classify<kThreads>(n, m, n8, m8, Qg, q_slow, q_fast, q_vec, Ag, p.a_rs, p.a_cs, a_vec, M, L.stage_cap, sc,
+                                        qd_s, rf, I, L.nr8c, L.ndp8c, L.nd08c, vc, S.nr, S.ndp, S.nd0) != 0;
     SPROF(1);
     if (tid == 0 && w_next < p.B && p.struct_prefetch) {
       // the next QP of this CTA: start pulling its Q and A_eq into L2 (one bulk-async instruction each); by the
@@ -679,7 +1003,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
             // read of the data (L1/L2), element-wise asynchronous copies straight to their tile positions; a lane
             // keeps the same columns (lane, lane + 32, ...) for every row, so their class and position are loop
             // invariants.  Row-major A_eq walks rows per warp, column-major A_eq (Eigen callers) columns per warp.
-            {
+            if (kFront == 0) {
+              struct_scatter_ldg<kThreads>(n, m, S.nr, S.nr8, dptc, Qg, q_slow, Ag, p.a_rs, M, AP, I);
+            } else {
               constexpr int kCol = kThreads / 32;
               const unsigned mS = smem_u32(M), apS = smem_u32(AP);
               // per owned column: kind (0 R, 1 D+, 2 D0, 3 nothing to copy), the 16-byte chunk it sits in (XOR-swizzled with
@@ -811,10 +1137,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
             double r = 0.0;
             if (is_x) r = (base_solve || pass == 0) ? -v_b : (op ? p.rho * w : -(v_b - p.rho * w));
 #ifdef FCCQP_DEV
-            const double res = struct_xsolve<kThreads>(p, L, smem, I, Se, ve, Qg, Ag, q_slow, q_fast, r, hi, shift, op, op,
+            const double res = struct_xsolve<kThreads, kFront>(p, L, smem, I, Se, ve, Qg, Ag, q_slow, q_fast, r, hi, shift, op, op,
                                                        pass == 0 && p.struct_refine != 0, s_prof, t_prof);
 #else
-            const double res = struct_xsolve<kThreads>(p, L, smem, I, Se, ve, Qg, Ag, q_slow, q_fast, r, hi, shift, op, op,
+            const double res = struct_xsolve<kThreads, kFront>(p, L, smem, I, Se, ve, Qg, Ag, q_slow, q_fast, r, hi, shift, op, op,
                                                        pass == 0 && p.struct_refine != 0);
 #endif
             if (base_solve) {
