@@ -36,6 +36,8 @@ std::mutex g_info_mu;
 struct StructHint {
   int mode = FCCQP_STRUCTURE_AUTO;   // AUTO: probe on the device (one tiny kernel + a stream sync); DENSE: never; CAPS: given
   int caps[3] = {0, 0, 0};           // nr, ndp, nd0
+  int refine = 0;                    // FCCQP_STRUCTURE_REFINE: one step of iterative refinement on the reduced cold pre-solve
+  void set(int structure) { mode = structure & ~FCCQP_STRUCTURE_REFINE; refine = (structure & FCCQP_STRUCTURE_REFINE) != 0; }
 };
 
 int fail(int code, const char* fmt, ...) {
@@ -146,13 +148,12 @@ int pick_kernel(const DeviceCtx& ctx, int n, int m, int nc, KernelFn* fn, int* t
 }
 
 // Structure-exploiting kernel instances (fccqp_struct.cuh): threads >= max(n, padded reduced KKT size).
-// front: 0 = register front end (row-major 16-byte aligned Q / A_eq, even n), 1 = staged front end (any layout).
-int pick_struct_kernel(const fccqp::StructLayout& sl, int n, int front, KernelFn* fn, int* threads) {
+int pick_struct_kernel(const fccqp::StructLayout& sl, int n, KernelFn* fn, int* threads) {
   const int need = n > sl.N8c ? n : sl.N8c;
-  if (need <= 64) { *threads = 64; *fn = front ? (KernelFn)fccqp::fccqp_struct_kernel<64, 8, 1> : (KernelFn)fccqp::fccqp_struct_kernel<64, 8, 0>; }
-  else if (need <= 96) { *threads = 96; *fn = front ? (KernelFn)fccqp::fccqp_struct_kernel<96, 5, 1> : (KernelFn)fccqp::fccqp_struct_kernel<96, 5, 0>; }
-  else if (need <= 128) { *threads = 128; *fn = front ? (KernelFn)fccqp::fccqp_struct_kernel<128, 4, 1> : (KernelFn)fccqp::fccqp_struct_kernel<128, 4, 0>; }
-  else if (need <= 256) { *threads = 256; *fn = front ? (KernelFn)fccqp::fccqp_struct_kernel<256, 2, 1> : (KernelFn)fccqp::fccqp_struct_kernel<256, 2, 0>; }
+  if (need <= 64) { *threads = 64; *fn = (KernelFn)fccqp::fccqp_struct_kernel<64, 8>; }
+  else if (need <= 96) { *threads = 96; *fn = (KernelFn)fccqp::fccqp_struct_kernel<96, 5>; }
+  else if (need <= 128) { *threads = 128; *fn = (KernelFn)fccqp::fccqp_struct_kernel<128, 4>; }
+  else if (need <= 256) { *threads = 256; *fn = (KernelFn)fccqp::fccqp_struct_kernel<256, 2>; }
   else return 1;
   return 0;
 }
@@ -201,8 +202,9 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool
   // developer switch: ADMM iteration at which long-running QPs complete inv(L) (huge value = never)
   static const int fia = getenv("FCCQP_FULL_INVERSE_AT") ? atoi(getenv("FCCQP_FULL_INVERSE_AT")) : 8;
   p.full_inverse_at = fia < 1 ? 1 : fia;
-  // developer switch (read per call, tests toggle it): 0 = no iterative refinement of the reduced cold pre-solve
-  p.struct_refine = getenv("FCCQP_STRUCT_REFINE") ? atoi(getenv("FCCQP_STRUCT_REFINE")) : 1;
+  // iterative refinement of the reduced cold pre-solve: FCCQP_STRUCTURE_REFINE of the caller (developer override
+  // FCCQP_STRUCT_REFINE=0/1, read per call)
+  p.struct_refine = getenv("FCCQP_STRUCT_REFINE") ? atoi(getenv("FCCQP_STRUCT_REFINE")) : (hint_in ? hint_in->refine : 0);
   p.struct_prefetch = getenv("FCCQP_STRUCT_PREFETCH") ? atoi(getenv("FCCQP_STRUCT_PREFETCH")) : 1;
   p.struct_bulk = getenv("FCCQP_STRUCT_BULK") ? atoi(getenv("FCCQP_STRUCT_BULK")) : 1;
   auto occupancy_of = [&](KernelFn f, int thr, size_t sm, int* out) -> int {
@@ -330,15 +332,7 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool
       fccqp::StructLayout sl(p.n, p.m, p.nc, caps[0], caps[1] + caps[2], caps[2]);   // D+ store: pass 1 eliminates D0 too
       KernelFn sfn = nullptr; int sthreads = 0;
       // worth it when at least one tile row of the KKT matrix goes away
-      // front end: registers (16-byte row loads straight from L2) when both matrices are row-major, aligned and even,
-      // else staged through shared memory (FCCQP_STRUCT_FRONT=staged forces the latter; ablation in profiles/)
-      const long long q_slow = p.q_cs <= p.q_rs ? p.q_rs : p.q_cs, q_fast = p.q_cs <= p.q_rs ? p.q_cs : p.q_rs;
-      const char* front_env = getenv("FCCQP_STRUCT_FRONT");
-      const bool reg_front = !(front_env && !strcmp(front_env, "staged")) && (p.n & 1) == 0 && q_fast == 1 && (q_slow & 1) == 0 &&
-                             (p.q_bs & 1) == 0 && (reinterpret_cast<uintptr_t>(p.Q) & 15) == 0 && p.a_cs == 1 && (p.a_rs & 1) == 0 &&
-                             (p.a_bs & 1) == 0 && (reinterpret_cast<uintptr_t>(p.A) & 15) == 0;
-      if (sl.N8c + 8 <= p.lay.N8 && sl.bytes() <= (size_t)ctx.max_smem_optin &&
-          pick_struct_kernel(sl, p.n, reg_front ? 0 : 1, &sfn, &sthreads) == 0) {
+      if (sl.N8c + 8 <= p.lay.N8 && sl.bytes() <= (size_t)ctx.max_smem_optin && pick_struct_kernel(sl, p.n, &sfn, &sthreads) == 0) {
         int sctas = 0;
         if ((rc = occupancy_of(sfn, sthreads, sl.bytes(), &sctas))) return rc;
         if (cta_cap > 0 && cta_cap < sctas) sctas = cta_cap;
@@ -355,8 +349,22 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool
           CUDA_TRY(cudaMemsetAsync(d_sprof, 0, 16 * sizeof(unsigned long long), stream));
           a.prof = d_sprof;
         }
+        // per-CTA global scratch of the full-space operator of long-running QPs (build_full_op): B, Z, X, Y tiles and 1/h
+        // sized for every variable eliminated; FCCQP_STRUCT_FULLOP=0 keeps the operator in the reduced space (ablation)
+        double* d_opscr = nullptr;
+        {
+          const char* fo = getenv("FCCQP_STRUCT_FULLOP");
+          if (!(fo && atoi(fo) == 0)) {
+            const long long neT = sl.n8 >> 3, NBr = sl.nr8c >> 3, mt = sl.mt;
+            const long long per = (2 * mt * neT + neT * NBr + neT * (neT + 1) / 2) * 64 + 8 * neT;
+            CUDA_TRY(cudaMallocAsync(&d_opscr, (size_t)sgrid * per * sizeof(double), stream));
+            a.op_scratch = d_opscr;
+            a.op_stride = per;
+          }
+        }
         sfn<<<sgrid, sthreads, sl.bytes(), stream>>>(a);
         CUDA_TRY(cudaGetLastError());
+        if (d_opscr) CUDA_TRY(cudaFreeAsync(d_opscr, stream));
         if (sprofile) {
           unsigned long long h[16];
           CUDA_TRY(cudaMemcpyAsync(h, d_sprof, sizeof(h), cudaMemcpyDeviceToHost, stream));
@@ -606,8 +614,9 @@ int fccqp_set_warm_start(fccqp_handle h, int warm) {
 }
 int fccqp_set_structure(fccqp_handle h, int structure) {
   if (!h) return fail(FCCQP_E_INVALID, "null handle");
-  if (structure != FCCQP_STRUCTURE_AUTO && structure != FCCQP_STRUCTURE_DENSE)
-    return fail(FCCQP_E_INVALID, "structure must be FCCQP_STRUCTURE_AUTO or FCCQP_STRUCTURE_DENSE");
+  const int mode = structure & ~FCCQP_STRUCTURE_REFINE;
+  if (mode != FCCQP_STRUCTURE_AUTO && mode != FCCQP_STRUCTURE_DENSE)
+    return fail(FCCQP_E_INVALID, "structure must be FCCQP_STRUCTURE_AUTO or FCCQP_STRUCTURE_DENSE (optionally | FCCQP_STRUCTURE_REFINE)");
   h->structure = structure;
   return FCCQP_OK;
 }
@@ -668,8 +677,10 @@ int fccqp_solve(fccqp_handle h, const double* Q, ptrdiff_t q_rs, ptrdiff_t q_cs,
   p.cycles = h->d_cycles;
   // the data is right here on the host: classify it here (no probe launch, no extra synchronisation)
   StructHint hint;
+  hint.set(h->structure);
+  const bool want_struct = hint.mode == FCCQP_STRUCTURE_AUTO;
   hint.mode = FCCQP_STRUCTURE_DENSE;
-  if (h->structure == FCCQP_STRUCTURE_AUTO && m > 0 &&
+  if (want_struct && m > 0 &&
       host_classify(n, m, sQ, n, 1, sA, k_a_rs, k_a_cs, &hint.caps[0], &hint.caps[1], &hint.caps[2]))
     hint.mode = FCCQP_STRUCTURE_CAPS;
   int rc = launch_solve(*h->ctx, p, h->stream, false, &hint);
@@ -775,7 +786,7 @@ int fccqp_batch_solve(const fccqp_batch_desc* desc) {
     p.res_b = d.res_bounds; p.res_f = d.res_fcone; p.bviol = d.bounds_viol; p.fviol = d.fcone_viol;
     cudaStream_t st = (cudaStream_t)d.stream;
     StructHint hint;
-    hint.mode = d.structure;
+    hint.set(d.structure);
     hint.caps[0] = d.struct_caps[0]; hint.caps[1] = d.struct_caps[1]; hint.caps[2] = d.struct_caps[2];
     // timing events are per call: concurrent callers on one device must not share them
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -883,7 +894,7 @@ int fccqp_batch_solve(const fccqp_batch_desc* desc) {
   // structure of the batch, from the host copy of the data (a sample of up to 64 QPs; no device probe,
   // no synchronisation inside the chunk pipeline)
   StructHint hint;
-  hint.mode = d.structure;
+  hint.set(d.structure);
   hint.caps[0] = d.struct_caps[0]; hint.caps[1] = d.struct_caps[1]; hint.caps[2] = d.struct_caps[2];
   if (hint.mode == FCCQP_STRUCTURE_AUTO) {
     hint.mode = FCCQP_STRUCTURE_DENSE;

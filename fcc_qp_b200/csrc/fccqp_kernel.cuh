@@ -205,6 +205,8 @@ struct SolveParams {
   int struct_refine;           // that kernel: one step of iterative refinement on the cold pre-solve
   int struct_prefetch;         // that kernel: bulk L2 prefetch of the next QP's Q and A_eq
   int struct_bulk;             // that kernel: bulk-async (TMA) staging of dense Q / A_eq blocks (0: per-row cp.async)
+  double* op_scratch;          // that kernel: per-CTA global scratch of the full-space operator of long-running QPs
+  long long op_stride;         //   doubles per CTA (0: the operator stays in the reduced space)
 };
 
 __device__ __forceinline__ double warp_max(double v) {

@@ -292,211 +292,17 @@ __device__ __forceinline__ int struct_classify(const int n, const int m, const i
   return struct_classify_finish<kThreads>(n, m8, qd_s, colv, I, capR, capP, cap0, vc, nr, ndp, nd0);
 }
 
-// ---- register front end ------------------------------------------------------------------------------
+// ---- coalesced row sweeps (iterative refinement) ------------------------------------------------------
 // For row-major, 16-byte aligned Q and A_eq with an even number of columns (what numpy / torch callers hand
-// over) neither pass needs staging: a warp reads whole matrix rows with one 16-byte load per lane and column
-// pair, kRows rows in flight, straight from L2 (the previous QP of this CTA prefetched them there with ONE
-// bulk-async instruction per matrix, l2_prefetch below).  Pass 1 classifies from registers, pass 2 (after the
-// class and position of every column are known) reads the rows that are still needed a second time and
-// stores every element at its place in the tile matrix.  No shared-memory staging, no asynchronous-copy queue,
-// a few hundred instructions per warp.
+// over) a warp reads whole matrix rows with one 16-byte load per lane and column pair, kRows rows in flight.
+// (A register front end built on the same sweeps -- classification and scatter straight from registers, no
+// staging -- was measured against the staged one and lost: profiles/r02_front_end_ldg_vs_staged.log.)
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
-__device__ __forceinline__ void sts8(unsigned smem_dst, double v) {
-  asm volatile("st.shared.f64 [%0], %1;" ::"r"(smem_dst), "d"(v) : "memory");
-}
-
 // pairs of columns per lane (lane + 32 u), rows in flight per warp: kPairs * kRows = 8 loads of 16 bytes per lane
 template <int kThreads> struct FrontGeom {
   static constexpr int kPairs = (kThreads / 2 + 31) / 32;
   static constexpr int kRows = kPairs >= 4 ? 2 : (kPairs == 2 ? 4 : 8);
 };
-
-template <int kThreads>
-__device__ __forceinline__ int struct_classify_ldg(const int n, const int m, const int n8, const int m8,
-                                                   const double* __restrict__ Qg, const long long q_slow,
-                                                   const double* __restrict__ Ag, const long long a_rs,
-                                                   double* __restrict__ qd_s, double* __restrict__ colv, const StructInts& I,
-                                                   const int capR, const int capP, const int cap0, VarClass& vc, int& nr,
-                                                   int& ndp, int& nd0) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int kWarps = kThreads / 32;
-  constexpr int kPairs = FrontGeom<kThreads>::kPairs, kRows = FrontGeom<kThreads>::kRows;
-  const int npair = n >> 1;
-  for (int e = tid; e < m8 + 8; e += kThreads) { I.rowcnt[e] = 0; I.d1var[e] = -1; }
-  for (int e = tid; e < n8; e += kThreads) I.colcnt[e] = 0;
-  // ---- Q (symmetric): variable i is separable <=> row i has no off-diagonal entry
-#pragma unroll 1
-  for (int i0 = warp; i0 < n; i0 += kWarps * kRows) {
-    double2 v[kRows][kPairs];
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-      const int i = i0 + r * kWarps;
-#pragma unroll
-      for (int u = 0; u < kPairs; ++u) {
-        const int cp = lane + 32 * u;
-        v[r][u] = (i < n && cp < npair) ? ldg2(Qg + (size_t)i * q_slow + 2 * cp) : make_double2(0.0, 0.0);
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-      const int i = i0 + r * kWarps;
-      if (i < n) {   // warp-uniform
-        bool nz = false;
-#pragma unroll
-        for (int u = 0; u < kPairs; ++u) {
-          const int c0 = 2 * (lane + 32 * u);
-          if (c0 == i) qd_s[i] = v[r][u].x; else nz = nz || (v[r][u].x != 0.0);
-          if (c0 + 1 == i) qd_s[i] = v[r][u].y; else nz = nz || (v[r][u].y != 0.0);
-        }
-        nz = __any_sync(0xffffffffu, nz);
-        if (lane == 0) I.nzflag[i] = nz ? 1 : 0;
-      }
-    }
-  }
-  // ---- A_eq: entry count of every column, and its entry if there is only one
-  int cx[kPairs], cy[kPairs], kx[kPairs], ky[kPairs];
-  double vx[kPairs], vy[kPairs];
-#pragma unroll
-  for (int u = 0; u < kPairs; ++u) { cx[u] = cy[u] = kx[u] = ky[u] = 0; vx[u] = vy[u] = 0.0; }
-#pragma unroll 1
-  for (int k0 = warp; k0 < m; k0 += kWarps * kRows) {
-    double2 v[kRows][kPairs];
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-      const int k = k0 + r * kWarps;
-#pragma unroll
-      for (int u = 0; u < kPairs; ++u) {
-        const int cp = lane + 32 * u;
-        v[r][u] = (k < m && cp < npair) ? ldg2(Ag + (size_t)k * a_rs + 2 * cp) : make_double2(0.0, 0.0);
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-      const int k = k0 + r * kWarps;
-#pragma unroll
-      for (int u = 0; u < kPairs; ++u) {
-        if (v[r][u].x != 0.0) { ++cx[u]; kx[u] = k; vx[u] = v[r][u].x; }
-        if (v[r][u].y != 0.0) { ++cy[u]; ky[u] = k; vy[u] = v[r][u].y; }
-      }
-    }
-  }
-  __syncthreads();   // colcnt zeroed by everybody
-  // (several warps with entries in one column: the count says >= 2 and the entry is not used)
-#pragma unroll
-  for (int u = 0; u < kPairs; ++u) {
-    const int c0 = 2 * (lane + 32 * u);
-    if (cx[u]) {
-      atomicAdd(&I.colcnt[c0], cx[u]); atomicExch(&I.colk[c0], kx[u]);
-      atomicExch(reinterpret_cast<unsigned long long*>(colv + c0), (unsigned long long)__double_as_longlong(vx[u]));
-    }
-    if (cy[u]) {
-      atomicAdd(&I.colcnt[c0 + 1], cy[u]); atomicExch(&I.colk[c0 + 1], ky[u]);
-      atomicExch(reinterpret_cast<unsigned long long*>(colv + c0 + 1), (unsigned long long)__double_as_longlong(vy[u]));
-    }
-  }
-  return struct_classify_finish<kThreads>(n, m8, qd_s, colv, I, capR, capP, cap0, vc, nr, ndp, nd0);
-}
-
-// Pass 2 of the register front end: Q_RR -> top-left tiles (lower triangle), A_eq: R columns -> constraint rows of
-// the matrix, D0 columns -> transposed into the trailing rows, D+ columns -> AP tiles.  I.vtype / I.vpos hold the
-// classes and positions of THIS pass (the ADMM pass eliminates the zero-cost variables too).  The destination region
-// has been zeroed (barrier in between).
-template <int kThreads>
-__device__ __forceinline__ void struct_scatter_ldg(const int n, const int m, const int nr, const int nr8, const int dptc,
-                                                   const double* __restrict__ Qg, const long long q_slow,
-                                                   const double* __restrict__ Ag, const long long a_rs,
-                                                   double* __restrict__ M, double* __restrict__ AP, const StructInts& I) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int kWarps = kThreads / 32;
-  constexpr int kPairs = FrontGeom<kThreads>::kPairs, kRows = FrontGeom<kThreads>::kRows;
-  const int npair = n >> 1;
-  const unsigned mS = smem_u32(M), apS = smem_u32(AP);
-  // per owned column: kind (0 R, 1 D+, 2 D0, 3 nothing to store), the 16-byte chunk it sits in (XOR-swizzled with the
-  // other index) and the row-independent part of its destination: R / D+ columns: byte offset inside a tile row
-  // (tile column * 512 + (c & 1) * 8); D0 columns (stored TRANSPOSED, the variable is the row): the shared address
-  // of that row.
-  int kind[kPairs][2], ps[kPairs][2], chf[kPairs][2];
-  unsigned cof[kPairs][2];
-#pragma unroll
-  for (int u = 0; u < kPairs; ++u)
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int j = 2 * (lane + 32 * u) + h;
-      const int ty = j < n ? I.vtype[j] : VT_NONE;
-      const int q = j < n ? I.vpos[j] : 0;
-      kind[u][h] = ty == VT_R ? 0 : (ty == VT_DP ? 1 : (ty == VT_D0 ? 2 : 3));
-      ps[u][h] = q;
-      chf[u][h] = (q & 7) >> 1;
-      cof[u][h] = ty == VT_D0 ? mS + (unsigned)tile_off(q >> 3, 0) * 8u + ((q & 7) << 6)
-                              : (unsigned)(((q >> 3) << 9) + ((q & 1) << 3));
-    }
-  // ---- Q: rows of the R variables, columns up to the diagonal
-#pragma unroll 1
-  for (int a0 = warp; a0 < nr; a0 += kWarps * kRows) {
-    double2 v[kRows][kPairs];
-    int ri[kRows];
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-      const int a = a0 + r * kWarps;
-      ri[r] = a < nr ? I.rlist[a] : -1;
-    }
-#pragma unroll
-    for (int r = 0; r < kRows; ++r)
-#pragma unroll
-      for (int u = 0; u < kPairs; ++u) {
-        const int cp = lane + 32 * u;
-        v[r][u] = (ri[r] >= 2 * cp && cp < npair && (kind[u][0] == 0 || kind[u][1] == 0))
-                      ? ldg2(Qg + (size_t)ri[r] * q_slow + 2 * cp) : make_double2(0.0, 0.0);
-      }
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-      const int a = a0 + r * kWarps;
-      if (a < nr) {
-        const unsigned rowS = mS + (unsigned)tile_off(a >> 3, 0) * 8u + ((a & 7) << 6);
-        const int rh = (a & 7) >> 1;
-#pragma unroll
-        for (int u = 0; u < kPairs; ++u) {
-          if (kind[u][0] == 0 && ps[u][0] <= a) sts8(rowS + cof[u][0] + (((chf[u][0] ^ rh) & 3) << 4), v[r][u].x);
-          if (kind[u][1] == 0 && ps[u][1] <= a) sts8(rowS + cof[u][1] + (((chf[u][1] ^ rh) & 3) << 4), v[r][u].y);
-        }
-      }
-    }
-  }
-  // ---- A_eq: every row, every column that is stored
-#pragma unroll 1
-  for (int k0 = warp; k0 < m; k0 += kWarps * kRows) {
-    double2 v[kRows][kPairs];
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-      const int k = k0 + r * kWarps;
-#pragma unroll
-      for (int u = 0; u < kPairs; ++u) {
-        const int cp = lane + 32 * u;
-        v[r][u] = (k < m && cp < npair && (kind[u][0] < 3 || kind[u][1] < 3))
-                      ? ldg2(Ag + (size_t)k * a_rs + 2 * cp) : make_double2(0.0, 0.0);
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-      const int k = k0 + r * kWarps;
-      if (k < m) {
-        const int yr = nr8 + k, rh = (k & 7) >> 1;
-        const unsigned rowM = mS + (unsigned)tile_off(yr >> 3, 0) * 8u + ((k & 7) << 6);
-        const unsigned rowP = apS + (unsigned)((k >> 3) * dptc) * 512u + ((k & 7) << 6);
-        const unsigned colT = (unsigned)(((yr >> 3) << 9) + ((yr & 1) << 3));   // this row as a COLUMN of a D0 row
-#pragma unroll
-        for (int u = 0; u < kPairs; ++u)
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int kd = kind[u][h];
-            const unsigned base = kd == 0 ? rowM : (kd == 1 ? rowP : colT);
-            const double val = h ? v[r][u].y : v[r][u].x;
-            if (kd < 3) sts8(base + cof[u][h] + (((chf[u][h] ^ rh) & 3) << 4), val);
-          }
-      }
-    }
-  }
-}
 
 // Probe: classifies `ns` QPs spread evenly over the batch and reports the largest structure seen
 // (out[0..2] = max nr, ndp, nd0; out[3] = QPs that are structurally singular) -- the host sizes the
@@ -565,13 +371,13 @@ struct StructQP {
   int nr, nr8, ndp, dpt, nd0, NB, NB32, N8;
 };
 
-template <int kThreads, int kFront>
+template <int kThreads>
 __device__ __forceinline__ double struct_xsolve(const SolveParams& p, const StructLayout& L, double* __restrict__ smem,
                                                 const StructInts& I, const StructQP& S, const VarClass& vc,
                                                 const double* __restrict__ Qg, const double* __restrict__ Ag,
                                                 const long long q_slow, const long long q_fast, const double r,
                                                 const double hi, const double shift, const bool use_op, const bool homog,
-                                                const bool refine
+                                                const bool refine, const bool coal
 #ifdef FCCQP_DEV
                                                 , unsigned long long* s_prof, long long& t_prof
 #endif
@@ -660,7 +466,7 @@ __device__ __forceinline__ double struct_xsolve(const SolveParams& p, const Stru
     if (is_x) xs[t] = x;
     __syncthreads();
     double acc2 = 0.0;
-    if (kFront == 0) {
+    if (coal) {
       // Row-major aligned data: a warp takes whole rows (one 16-byte load per lane and column pair, kRows rows in
       // flight, L2 hits): row k of A_eq gives the constraint residual b_eq,k - a_k x (warp reduction) and, in the same
       // sweep, this warp's share of A_eq' y (per-lane column sums, combined across warps in a fixed order below);
@@ -819,6 +625,158 @@ __device__ __forceinline__ double struct_xsolve(const SolveParams& p, const Stru
   return xr;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Full-space operator of long-running QPs.  Once the explicit inverse G = inv(K_red) of the reduced rho-KKT
+// matrix sits in M (complete_inverse + form_g), an x-update through it still costs a right-hand-side reduction
+// (A_P H^-1 r_P), the product with G, and the recovery of the eliminated variables -- five barriers.  With
+//   B = A_E H_E^-1  (m x ne; E = every eliminated variable: D+, former D0 and the one-entry columns D1),
+// the x-part of the solution for a right-hand side r that is zero on the constraint rows is
+//   x_R = G_RR r_R - G_Ry B r_E,      x_E = H^-1 r_E - B' y = -B' G_yR r_R + (H^-1 + B' G_yy B) r_E,
+// i.e. x = F r with the symmetric n x n matrix, in class order [R | E],
+//   F = [[ G_RR, . ], [ X, Y ]],   X = -B' G_yR,   Y = H^-1 + B' G_yy B.
+// F replaces the constraint rows of G in M (the tile rows after R), and every later x-update is
+// x = x_base + F (rho w): one symmetric matrix-vector product in the space of the variables, permuted on the way in
+// and out.  The products are formed OUT of place through a per-CTA scratch slab in global memory (L2-resident, used
+// once per long-running QP): B, Z = G_yy B, X and Y are written there tile by tile (one output tile per warp and
+// round, all operands read-only), then copied over M.  Tiles keep the chunk swizzle, so the fragment offsets of the
+// factorization apply to the scratch tiles as well.
+struct FullOpDims {
+  int NBr, mt, dptc, dpt, ne, neT, NBF, NF;
+};
+
+template <int kThreads>
+__device__ __noinline__ void build_full_op(double* __restrict__ M, const double* __restrict__ AP, const double* __restrict__ hinv,
+                                           double* __restrict__ scr, const FullOpDims d, const int etype, const int epos,
+                                           const int krow, const int nnz, const double aval, const double hi) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kThreads / 32;
+  const int fr = lane >> 2, fq = lane & 3;
+  const int fragC = (fr << 3) + (((fq ^ (fr >> 1)) & 3) << 1);
+  const int fragT = ((2 * fq) << 3) + ((((fr >> 1) ^ fq) & 3) << 1) + (fr & 1);
+  double* const Bs = scr;                              // [mt][neT] tiles
+  double* const Zs = Bs + (size_t)d.mt * d.neT * 64;   // [mt][neT] tiles
+  double* const Xs = Zs + (size_t)d.mt * d.neT * 64;   // [neT][NBr] tiles
+  double* const Ys = Xs + (size_t)d.neT * d.NBr * 64;  // lower [neT][neT] tiles, (E, E') at E(E+1)/2 + E'
+  double* const hE = Ys + (size_t)((d.neT * (d.neT + 1)) >> 1) * 64;   // [8 neT]: 1/h of the eliminated variables
+  // ---- B = A_E H^-1 and 1/h, in class order of the eliminated variables
+  for (int e = tid; e < d.mt * d.neT * 64; e += kThreads) {
+    const int tile = e >> 6, off = e & 63;
+    const int K = tile / d.neT, E = tile - K * d.neT;
+    double v = 0.0;
+    if (E < d.dpt) {
+      const int r = off >> 3, c = ((((off >> 1) & 3) ^ (r >> 1)) & 3) * 2 + (off & 1);
+      v = AP[(size_t)(K * d.dptc + E) * 64 + off] * hinv[8 * E + c];
+    }
+    Bs[e] = v;
+  }
+  for (int e = tid; e < 8 * d.neT; e += kThreads) hE[e] = 0.0;
+  __syncthreads();
+  if (etype == VT_DP || etype == VT_D1) {
+    hE[epos] = hi;
+    if (etype == VT_D1 && nnz == 1) Bs[(size_t)((krow >> 3) * d.neT + (epos >> 3)) * 64 + el_off(krow & 7, epos & 7)] = aval * hi;
+  }
+  __syncthreads();
+  // ---- Z = G_yy B (G_yy symmetric, lower tiles of M at tile rows / columns NBr..) and X = -B' G_yR
+  const int nz = d.mt * d.neT, nx = d.neT * d.NBr;
+#pragma unroll 1
+  for (int w = warp; w < nz + nx; w += kWarps) {
+    double2 ca = make_double2(0.0, 0.0), cb = make_double2(0.0, 0.0);
+    if (w < nz) {
+      const int K = w / d.neT, E = w - K * d.neT;
+#pragma unroll 1
+      for (int K2 = 0; K2 < d.mt; ++K2) {
+        const double* bt = Bs + (size_t)(K2 * d.neT + E) * 64 + fragT;
+        double2 a;
+        if (K >= K2) a = ld2(M + tile_off(d.NBr + K, d.NBr + K2) + fragC);
+        else { const double* gt = M + tile_off(d.NBr + K2, d.NBr + K) + fragT; a = make_double2(gt[0], gt[8]); }
+        dmma(ca.x, ca.y, a.x, bt[0]);
+        dmma(cb.x, cb.y, a.y, bt[8]);
+      }
+      st2(Zs + (size_t)w * 64 + fragC, make_double2(ca.x + cb.x, ca.y + cb.y));
+    } else {
+      const int wi = w - nz, E = wi / d.NBr, J = wi - E * d.NBr;
+#pragma unroll 1
+      for (int K = 0; K < d.mt; ++K) {
+        const double* at = Bs + (size_t)(K * d.neT + E) * 64 + fragT;
+        const double* gt = M + tile_off(d.NBr + K, J) + fragT;
+        dmma(ca.x, ca.y, at[0], gt[0]);
+        dmma(cb.x, cb.y, at[8], gt[8]);
+      }
+      st2(Xs + (size_t)wi * 64 + fragC, make_double2(-(ca.x + cb.x), -(ca.y + cb.y)));
+    }
+  }
+  __syncthreads();
+  // ---- Y = H^-1 + B' Z (lower tiles)
+  const int ny = (d.neT * (d.neT + 1)) >> 1;
+#pragma unroll 1
+  for (int w = warp; w < ny; w += kWarps) {
+    int E = 0;
+    while (((E + 1) * (E + 2)) >> 1 <= w) ++E;
+    const int E2 = w - ((E * (E + 1)) >> 1);
+    double2 ca = make_double2(0.0, 0.0), cb = make_double2(0.0, 0.0);
+#pragma unroll 1
+    for (int K = 0; K < d.mt; ++K) {
+      const double* at = Bs + (size_t)(K * d.neT + E) * 64 + fragT;
+      const double* zt = Zs + (size_t)(K * d.neT + E2) * 64 + fragT;
+      dmma(ca.x, ca.y, at[0], zt[0]);
+      dmma(cb.x, cb.y, at[8], zt[8]);
+    }
+    double2 y = make_double2(ca.x + cb.x, ca.y + cb.y);
+    if (E == E2) {   // element (fr, 2 fq) and (fr, 2 fq + 1) of the tile
+      if (2 * fq == fr) y.x += hE[8 * E + fr];
+      if (2 * fq + 1 == fr) y.y += hE[8 * E + fr];
+    }
+    st2(Ys + (size_t)w * 64 + fragC, y);
+  }
+  __syncthreads();
+  // ---- F over the constraint rows of G
+#pragma unroll 1
+  for (int I = d.NBr; I < d.NBF; ++I) {
+    const int E = I - d.NBr;
+    double* dst = M + tile_off(I, 0);
+    const double* sx = Xs + (size_t)E * d.NBr * 64;
+    const double* sy = Ys + (size_t)((E * (E + 1)) >> 1) * 64;
+    for (int e = tid; e < (I + 1) * 32; e += kThreads) {
+      const int j2 = e - d.NBr * 32;
+      st2(dst + 2 * e, j2 < 0 ? ld2(sx + 2 * e) : ld2(sy + 2 * j2));
+    }
+  }
+  __syncthreads();
+}
+
+// x = x_base + F (rho w): thread `t` owns variable t with class-order index ci (-1: no variable); row t of F is
+// thread t's as well.  tbuf: operand, xb: x_base in class order, out: result in class order.
+__device__ __noinline__ double full_op_apply(const double* __restrict__ M, double* __restrict__ tbuf, const double* __restrict__ xb,
+                                             double* __restrict__ out, const int ci, const double w, const int NBF, const int NF) {
+  const int t = threadIdx.x;
+  const int tb = t >> 3, tr = t & 7, tf = tr >> 1;
+  const int colo = tr & 1, colc = tr >> 1;
+  const int flip = tb & 1;
+  if (ci >= 0) tbuf[ci] = w;
+  __syncthreads();
+  if (t < NF) {
+    const double* lrow = M + tile_off(tb, 0) + tr * 8;
+    double s0 = 0.0, s1 = 0.0;
+    int jb = 0;
+#pragma unroll 1
+    for (; jb + 1 <= tb; jb += 2) {
+      s0 += row_dot8(lrow + 64 * jb, tf, tbuf + jb * 8);
+      s1 += row_dot8(lrow + 64 * jb + 64, tf, tbuf + jb * 8 + 8);
+    }
+    if (jb <= tb) s0 += row_dot8(lrow + 64 * jb, tf, tbuf + jb * 8);
+    int ib = tb + 1;
+#pragma unroll 1
+    for (; ib + 1 < NBF; ib += 2) {
+      s0 += col_dot8(M + tile_off(ib, tb) + colo, colc, flip, tbuf + ib * 8);
+      s1 += col_dot8(M + tile_off(ib + 1, tb) + colo, colc, flip, tbuf + ib * 8 + 8);
+    }
+    if (ib < NBF) s0 += col_dot8(M + tile_off(ib, tb) + colo, colc, flip, tbuf + ib * 8);
+    out[t] = xb[t] + (s0 + s1);
+  }
+  __syncthreads();
+  return ci >= 0 ? out[ci] : 0.0;
+}
+
 #ifdef FCCQP_DEV
 #define SPROF(slot)                                                        \
   do {                                                                     \
@@ -832,9 +790,7 @@ __device__ __forceinline__ double struct_xsolve(const SolveParams& p, const Stru
 #define SPROF(slot) do { } while (0)
 #endif
 
-// kFront: 0 = register front end (row-major, 16-byte aligned Q and A_eq with an even column count; the host checks),
-// 1 = staged front end (any strides; bulk-async / cp.async staging through shared memory).
-template <int kThreads, int kMinBlocks, int kFront>
+template <int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(const SolveParams p) {
   extern __shared__ __align__(16) double smem[];
   const StructLayout& L = p.slay;
@@ -929,13 +885,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
     const bool a_vec = p.a_cs == 1 && (n & 1) == 0 && (p.a_rs & 1) == 0 && (reinterpret_cast<uintptr_t>(Ag) & 15) == 0;
     sc.q_bulk = q_vec && q_slow == n && p.struct_bulk;
     sc.a_bulk = a_vec && p.a_rs == n && p.struct_bulk;
-    bool defer;
-    if (kFront == 0)
-      defer = struct_classify_ldg<kThreads>(n, m, n8, m8, Qg, q_slow, Ag, p.a_rs, qd_s, rf, I, L.nr8c, L.ndp8c, L.nd08c, vc, S.nr,
-                                            S.ndp, S.nd0) != 0;
-    else
-      defer = struct_classify<kThreads>(n, m, n8, m8, Qg, q_slow, q_fast, q_vec, Ag, p.a_rs, p.a_cs, a_vec, M, L.stage_cap, sc,
-                                        qd_s, rf, I, L.nr8c, L.ndp8c, L.nd08c, vc, S.nr, S.ndp, S.nd0) != 0;
+    bool defer = struct_classify<kThreads>(n, m, n8, m8, Qg, q_slow, q_fast, q_vec, Ag, p.a_rs, p.a_cs, a_vec, M, L.stage_cap, sc,
+                                           qd_s, rf, I, L.nr8c, L.ndp8c, L.nd08c, vc, S.nr, S.ndp, S.nd0) != 0;
     SPROF(1);
     if (tid == 0 && w_next < p.B && p.struct_prefetch) {
       // the next QP of this CTA: start pulling its Q and A_eq into L2 (one bulk-async instruction each); by the
@@ -980,6 +931,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
       const double hi = (ve.type == VT_DP || ve.type == VT_D1) ? 1.0 / (ve.qd + shift) : 0.0;
       bool factored = false;
       bool full_inverse = false;
+      bool full_op = false;          // the full-space operator F sits in M (build_full_op)
+      int ci = -1, NBF = 0, NF = 0;  //   this thread's variable in class order [R | E]; tile rows / rows of F
       double v_xbase = 0.0;
 
 #pragma unroll 1
@@ -1003,9 +956,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
             // read of the data (L1/L2), element-wise asynchronous copies straight to their tile positions; a lane
             // keeps the same columns (lane, lane + 32, ...) for every row, so their class and position are loop
             // invariants.  Row-major A_eq walks rows per warp, column-major A_eq (Eigen callers) columns per warp.
-            if (kFront == 0) {
-              struct_scatter_ldg<kThreads>(n, m, S.nr, S.nr8, dptc, Qg, q_slow, Ag, p.a_rs, M, AP, I);
-            } else {
+            {
               constexpr int kCol = kThreads / 32;
               const unsigned mS = smem_u32(M), apS = smem_u32(AP);
               // per owned column: kind (0 R, 1 D+, 2 D0, 3 nothing to copy), the 16-byte chunk it sits in (XOR-swizzled with
@@ -1133,15 +1084,19 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
 #pragma unroll 1
           for (int rep = make_op ? 0 : 1; rep < 2; ++rep) {
             const bool base_solve = rep == 0;
+            if (!base_solve && full_op) {
+              val = full_op_apply(M, smem + L.off_tbuf, smem + L.off_ybuf, smem + L.off_sred, ci, p.rho * w, NBF, NF);
+              break;
+            }
             const bool op = !base_solve && full_inverse;
             double r = 0.0;
             if (is_x) r = (base_solve || pass == 0) ? -v_b : (op ? p.rho * w : -(v_b - p.rho * w));
 #ifdef FCCQP_DEV
-            const double res = struct_xsolve<kThreads, kFront>(p, L, smem, I, Se, ve, Qg, Ag, q_slow, q_fast, r, hi, shift, op, op,
-                                                       pass == 0 && p.struct_refine != 0, s_prof, t_prof);
+            const double res = struct_xsolve<kThreads>(p, L, smem, I, Se, ve, Qg, Ag, q_slow, q_fast, r, hi, shift, op, op,
+                                                       pass == 0 && p.struct_refine != 0, q_vec && a_vec, s_prof, t_prof);
 #else
-            const double res = struct_xsolve<kThreads, kFront>(p, L, smem, I, Se, ve, Qg, Ag, q_slow, q_fast, r, hi, shift, op, op,
-                                                       pass == 0 && p.struct_refine != 0);
+            const double res = struct_xsolve<kThreads>(p, L, smem, I, Se, ve, Qg, Ag, q_slow, q_fast, r, hi, shift, op, op,
+                                                       pass == 0 && p.struct_refine != 0, q_vec && a_vec);
 #endif
             if (base_solve) {
               v_xbase = res;
@@ -1149,6 +1104,36 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
               complete_inverse<kThreads>(M, Se.NB);
               form_g<kThreads>(M, dinv, Se.NB, Se.NB, Se.NB);
               full_inverse = true;
+              // full-space operator (build_full_op) when it fits: rows of F <= threads and vector buffers, tiles of F
+              // within the [M | AP] region (AP is not needed afterwards)
+              if (p.op_stride > 0) {
+                FullOpDims fd;
+                fd.NBr = NBr; fd.mt = mt; fd.dptc = dptc; fd.dpt = Se.dpt;
+                fd.ne = n - S.nr; fd.neT = (fd.ne + 7) >> 3; fd.NBF = NBr + fd.neT; fd.NF = fd.NBF * 8;
+                if (fd.NF <= kThreads && fd.NF <= L.NTc && tile_off(fd.NBF, 0) <= L.stage_cap) {
+                  // class order of the eliminated variables: the D+ columns (position in AP), then the one-entry columns
+                  const bool is_d1 = is_x && ve.type == VT_D1;
+                  const unsigned b1 = __ballot_sync(0xffffffffu, is_d1);
+                  if (lane == 0) I.wtot[warp] = __popc(b1);
+                  __syncthreads();
+                  int o1 = 0;
+#pragma unroll
+                  for (int w2 = 0; w2 < kWarps; ++w2) if (w2 < warp) o1 += I.wtot[w2];
+                  int epos = -1;
+                  if (is_x && ve.type == VT_DP) epos = ve.pos;
+                  else if (is_d1) epos = Se.ndp + o1 + __popc(b1 & ((1u << lane) - 1u));
+                  ci = is_x ? (ve.type == VT_R ? ve.pos : S.nr8 + epos) : -1;
+                  NBF = fd.NBF; NF = fd.NF;
+                  build_full_op<kThreads>(M, AP, hinv, p.op_scratch + (size_t)blockIdx.x * p.op_stride, fd, is_x ? ve.type : VT_NONE,
+                                          epos, ve.krow, ve.nnz, ve.aval, hi);
+                  double* const tb2 = smem + L.off_tbuf;
+                  double* const xb2 = smem + L.off_ybuf;
+                  if (t < NF) { tb2[t] = 0.0; xb2[t] = 0.0; }
+                  __syncthreads();
+                  if (ci >= 0) xb2[ci] = v_xbase;
+                  full_op = true;   // (the barrier inside full_op_apply orders the write above)
+                }
+              }
             } else {
               val = op ? v_xbase + res : res;
             }

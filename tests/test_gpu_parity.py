@@ -49,8 +49,8 @@ def check(sol, gold, qp, n_iter_exact=True):
         assert np.array_equal(np.asarray(sol.details.solve_status), gold["status"])
     for a, k in ((sol.details.eps_bounds, "res_bounds"), (sol.details.eps_friction_cone, "res_fcone"),
                  (sol.details.bounds_viol, "bounds_viol"), (sol.details.friction_cone_viol, "fcone_viol")):
-        if k in gold:
-            assert np.abs(np.asarray(a) - gold[k]).max() <= 1e-5
+        if k in gold:   # residuals / violations are differences of entries of z: same relative bar, one digit of slack
+            assert (np.abs(np.asarray(a) - gold[k]) <= 1e-5 * np.maximum(1.0, np.abs(gold["z"]).max(1))).all(), k
 
 
 def test_walking_log_one_batch_cold_host(walking_log):

@@ -39,7 +39,7 @@ def case(name, qp, gold):
         if mis:
             idx = np.nonzero(it != gold["n_iter"])[0][:8]
             print("   first mismatches", [(int(i), int(it[i]), int(gold["n_iter"][i])) for i in idx])
-    os.environ["FCCQP_STRUCT_REFINE"] = "1"
+    os.environ.pop("FCCQP_STRUCT_REFINE", None)
     z, it, st, info, dt = run(qp, "dense")
     e = rel(z, gold["z"])
     print(f"{name} dense: info={info} max_rel={e.max():.3e} mismatches={(it != gold['n_iter']).sum()}", flush=True)
