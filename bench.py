@@ -18,6 +18,7 @@ reference compiled from /root/reference; else the C restatement) on all host cor
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -107,17 +108,121 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_run(qp, sample, nthreads=None, kind=None):
-    """Cold all-core CPU solve of the first `sample` QPs; returns (qps_per_s, cores, kind, seconds)."""
+def cpu_reference_run(qp, sample, nthreads=None, kind=None, warm_mode=0):
+    """All-core CPU solve of the first `sample` QPs (cold, or warm-sequential inside each thread's chunk);
+    returns (qps_per_s, cores, kind, seconds).  kind: "reference" (oracle/_ref, the reference's own flags),
+    "reference_avx2" (same sources, -march=x86-64-v3) or "port" (the C restatement)."""
     from oracle import Oracle, colmajor_stack, have
     if kind is None:
         kind = "reference" if have("ref") else "port"
-    orc = Oracle("ref" if kind == "reference" else "port")
+    orc = Oracle({"reference": "ref", "reference_avx2": "ref_avx2", "port": "port"}[kind])
     cores = nthreads or orc.hardware_threads()
     sub = qp.take(np.arange(sample) % qp.batch)
     prepared = (colmajor_stack(sub.Q), colmajor_stack(sub.A_eq))  # layout prep outside the timed region
-    r = orc.solve_batch(sub, warm_mode=0, nthreads=cores, prepared=prepared, **OPTS)
+    r = orc.solve_batch(sub, warm_mode=warm_mode, nthreads=cores, prepared=prepared, **OPTS)
     return sample / r["elapsed"], cores, kind, r["elapsed"]
+
+
+def cpu_baseline_variants(log, sample):
+    """BASELINE.md section 3 extras, reported next to (never instead of) the cold reference-flags baseline: the
+    reference in its deployment mode (warm-started inside each thread's chunk of consecutive log QPs) and a second
+    build with the host's vector ISA enabled.  The AVX2 build runs in a child process: an illegal instruction on
+    an older host must not take the bench down."""
+    from oracle import have
+    out = {}
+    try:
+        rate, cores, kind, secs = cpu_reference_run(log, sample, warm_mode=1)
+        out["warm_within_chunk"] = {"value": rate, "unit": "QP/s", "cores": cores, "kind": kind,
+                                    "sample": f"first {sample} QPs, each thread warm-starts through its chunk, {secs:.1f} s"}
+    except Exception as e:  # pragma: no cover
+        out["warm_within_chunk"] = {"unavailable": repr(e)}
+    if have("ref_avx2"):
+        code = ("import sys, json; sys.path.insert(0, %r); import bench; from fcc_qp_b200.logdata import load_walking_log; "
+                "log = load_walking_log(); r = {}; "
+                "[r.__setitem__(k, bench.cpu_reference_run(log, %d, kind='reference_avx2', warm_mode=w)[:2]) for k, w in (('cold', 0), ('warm', 1))]; "
+                "print('RESULT ' + json.dumps(r))" % (ROOT, sample))
+        try:
+            cp = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=180)
+            res = [l for l in cp.stdout.splitlines() if l.startswith("RESULT ")]
+            if cp.returncode == 0 and res:
+                r = json.loads(res[-1][7:])
+                out["reference_avx2"] = {"cold": {"value": r["cold"][0], "unit": "QP/s", "cores": r["cold"][1]},
+                                         "warm_within_chunk": {"value": r["warm"][0], "unit": "QP/s", "cores": r["warm"][1]},
+                                         "flags": "-O3 -DNDEBUG -march=x86-64-v3", "sample": f"first {sample} QPs"}
+            else:
+                out["reference_avx2"] = {"unavailable": f"child exited {cp.returncode}: {cp.stderr.strip()[-200:]}"}
+        except Exception as e:  # pragma: no cover
+            out["reference_avx2"] = {"unavailable": repr(e)}
+    else:
+        out["reference_avx2"] = {"unavailable": "oracle/_ref/libfccqp_ref_avx2.so not built"}
+    return out
+
+
+def shape_extras(dev):
+    """BASELINE.json configs 3-5 on this GPU, device-resident (extra keys; the headline stays config 2).
+    Synthetic QPs of the named shapes (fcc_qp_b200/synthetic.py): 4096 distinct ones generated on the host and tiled
+    on the device to the batch the config states."""
+    import torch
+    from fcc_qp_b200 import synthetic as syn
+    from fcc_qp_b200 import _native as nat
+    from fcc_qp_b200.batch import FCCQPBatch, FCCQPOptionsB
+
+    def device_batch(qp, B):
+        reps = B // qp.batch
+        t = [torch.as_tensor(a, device=dev) for a in (qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)]
+        return [a.repeat((reps,) + (1,) * (a.dim() - 1)) for a in t]
+
+    def rate(s, args, B, warm):
+        best = 1e9
+        for _ in range(3):
+            if warm:      # warm solve of the same problems from the converged state of a cold solve
+                s.set_warm_start(False); s.Solve(*args); s.set_warm_start(True)
+            s.Solve(*args); torch.cuda.synchronize(dev)
+            best = min(best, s.GetSolution().details.device_time)
+        it = s.GetSolution().details.n_iter.cpu().numpy()
+        return {"ms": 1e3 * best, "qps": B / best, "iterating_fraction": float((it > 0).mean()),
+                "max_iter_fraction": float((it == OPTS["max_iter"]).mean()), "mean_iterations": float(it.mean())}
+
+    out = {}
+    for name, B, cfg in (("humanoid", 1 << 16, 3), ("quadruped", 1 << 17, 4)):
+        try:
+            qp = syn.make_batch(syn.SHAPES[name], 4096)
+            args = device_batch(qp, B)
+            s = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start, device=dev.index); s.set_options(FCCQPOptionsB(**OPTS))
+            s.set_warm_start(False); s.Solve(*args); torch.cuda.synchronize(dev)
+            out[name] = {"baseline_config": cfg, "n": qp.n, "m": qp.m, "nc": qp.nc, "batch": B,
+                         "cold": rate(s, args, B, False), "warm": rate(s, args, B, True),
+                         "launch": nat.last_launch_info(), "structure": nat.last_struct_info()}
+            if cfg == 4:
+                out[name]["note"] = "config 4 is 2^20 QPs over 8 GPUs: this is one GPU's 2^17 share"
+            del args, s
+        except Exception as e:  # pragma: no cover
+            out[name] = {"error": repr(e)}
+    # config 5: multi-contact humanoid, T = 32 sequential warm-started batches of 2^14 (b, b_eq drift 2 % per step)
+    try:
+        shp = syn.SHAPES["multicontact"]
+        B, T = 1 << 14, 32
+        qp = syn.make_batch(shp, 2048, seed=shp.seed + 1)
+        Q, b, A, beq, mu, lb, ub = device_batch(qp, B)
+        s = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start, device=dev.index); s.set_options(FCCQPOptionsB(**OPTS))
+        s.Solve(Q, b, A, beq, mu, lb, ub); torch.cuda.synchronize(dev)     # untimed warm-up launch
+        gen = torch.Generator(device=dev); gen.manual_seed(3)
+        per = []
+        for t in range(T):
+            s.set_warm_start(t > 0)
+            s.Solve(Q, b, A, beq, mu, lb, ub); torch.cuda.synchronize(dev)
+            per.append(s.GetSolution().details.device_time)
+            b = b * (1.0 + 0.02 * torch.randn(b.shape, device=dev, dtype=torch.float64, generator=gen))
+            beq = beq * (1.0 + 0.02 * torch.randn(beq.shape, device=dev, dtype=torch.float64, generator=gen))
+        it = s.GetSolution().details.n_iter.cpu().numpy()
+        out["multicontact"] = {"baseline_config": 5, "n": qp.n, "m": qp.m, "nc": qp.nc, "batch": B, "steps": T,
+                               "total_ms": 1e3 * sum(per), "qps": B * T / sum(per), "first_cold_ms": 1e3 * per[0],
+                               "cold_qps": B / per[0], "warm_ms_median": 1e3 * float(np.median(per[1:])),
+                               "iterating_fraction_last": float((it > 0).mean()),
+                               "launch": nat.last_launch_info(), "structure": nat.last_struct_info()}
+    except Exception as e:  # pragma: no cover
+        out["multicontact"] = {"error": repr(e)}
+    return out
 
 
 def run_reference_arm(args):
@@ -214,6 +319,7 @@ def run_ours(args):
     status = sol.details.solve_status.cpu().numpy()
     iters_executed = float(np.where(n_iter == OPTS["max_iter"], OPTS["max_iter"], n_iter + 1).mean())
     info = nat.last_launch_info()
+    sinfo = nat.last_struct_info()      # (of the device-resident launches just timed)
 
     # ---------------- end to end through the public API on pinned host arrays (`e2e`) ----------
     pinned = [torch.from_numpy(a).pin_memory().numpy() for a in host]
@@ -264,6 +370,37 @@ def run_ours(args):
         f32 = {"error": repr(e)}
     sharding.barrier()
 
+    # ---------------- one process, ONE call, all GPUs (fccqp_batch_solve_multi) ----------------
+    # Under torchrun every rank times its own shard (above).  The C ABI can also take the whole host batch in one
+    # call and split it over the devices itself (one host thread + stream set per device): rank 0 times that over
+    # all `world` GPUs while the other ranks wait at the barrier.  2^15 QPs per device bound the page-locked memory.
+    single_call = None
+    if world > 1 and not args.no_extras:
+        sharding.barrier()
+        if rank == 0:
+            try:
+                Bs = world * (BATCH_PER_GPU // 2)
+                qs = log.take(np.arange(Bs) % log.batch)
+                hp = [torch.from_numpy(a).pin_memory().numpy() for a in
+                      (qs.Q, qs.b, qs.A_eq, qs.b_eq, qs.friction_coeffs, qs.lb, qs.ub)]
+                del qs
+                ms = FCCQPBatch(n, m, nc, lcs, device=list(range(world)))
+                ms.set_options(FCCQPOptionsB(**OPTS))
+                ms.zero_copy_outputs = True
+                ms.Solve(*hp)
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    ms.Solve(*hp)
+                    zs = float(ms.GetSolution().z[:, 0].sum())
+                dt = (time.perf_counter() - t0) / 3
+                single_call = {"value": Bs / dt, "unit": "QP/s", "batch": Bs, "devices": world, "ms_per_call": 1e3 * dt,
+                               "h2d_bytes_per_call": int(sum(a.nbytes for a in hp)),
+                               "api": "FCCQPBatch(device=[0..N-1]).Solve(numpy pinned) -> fccqp_batch_solve_multi"}
+                del hp, ms
+            except Exception as e:  # pragma: no cover
+                single_call = {"error": repr(e)}
+        sharding.barrier()
+
     if rank != 0:
         return 0
 
@@ -280,7 +417,23 @@ def run_ours(args):
         except Exception:
             traffic = None
     flops = algorithmic_flops_per_qp(n, m, iters_executed, cold=True) * B
-    fp64_peak = 148 * 64 * 2 * 1.965e9 / 1e12  # nominal vector FP64: SMs x lanes x 2 x max clock
+    fp64_nominal = 148 * 64 * 2 * 1.965e9 / 1e12  # nominal vector FP64: SMs x lanes x 2 x max clock
+    fp64_peak, fp64_src = fp64_nominal, "nominal"
+    try:
+        tf = C.c_double(0.0)
+        nat.check(nat.lib().fccqp_measure_fp64_peak(local_rank, C.byref(tf)))
+        if tf.value > 0:
+            fp64_peak, fp64_src = tf.value, "measured in this run: ~50 ms register-only DFMA kernel (fccqp_measure_fp64_peak)"
+    except Exception:  # pragma: no cover
+        pass
+    # work the kernel actually EXECUTES (not the SURVEY 8d model of the dense algorithm): the structure-exploiting
+    # kernel factors the reduced KKT system (Nr rows instead of n + m), every cold QP once and only the QPs that
+    # iterate a second time, plus the Schur term C = A_P H^-1 A_P' and 2 Nr^2 per triangular-solve pair
+    Nr = float(sinfo["rows"] if sinfo.get("used") else n + m)
+    ndp = float(sum(sinfo["caps"][1:3])) if sinfo.get("used") else 0.0
+    f_it = float((n_iter > 0).mean())
+    per_factor = Nr ** 3 / 3.0 + m * m * ndp
+    flops_exec = B * ((1.0 + f_it) * per_factor + 2.0 * Nr * Nr * (1.0 + float(n_iter.mean())))
     line = {
         "metric": METRIC, "value": value, "unit": "QP/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
@@ -294,15 +447,21 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(out_bytes), "ms_per_step": 1e3 * e2e_s / args.steps,
                 "api": "FCCQPBatch.Solve(numpy pinned) -> fccqp_batch_solve(FCCQP_MEM_HOST)"},
         "e2e_fp32_data": f32,
+        "e2e_single_call_all_gpus": single_call,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                      "frac": achieved / peaks.get("hbm_gbs"), "traffic": traffic, "peak_source": peak_kind,
-                     "kernel": "fccqp_solve_kernel", "kernel_ms": 1e3 * kern_s,
+                     "kernel": "fccqp_struct_kernel" if sinfo.get("used") else "fccqp_solve_kernel", "kernel_ms": 1e3 * kern_s,
                      "note": "latency/FP64-bound kernel: HBM fraction is low by construction; see fp64"},
-        "roofline_fp64": {"achieved_tflops": flops / kern_s / 1e12, "peak_tflops_nominal": fp64_peak,
-                          "frac": flops / kern_s / 1e12 / fp64_peak,
-                          "flops_model": "SURVEY 8d: 2 x N^3/3 + 2 N^2 x iterations_executed per cold QP"},
+        "roofline_fp64": {"achieved_tflops": flops / kern_s / 1e12, "peak_tflops": fp64_peak, "peak_source": fp64_src,
+                          "peak_tflops_nominal": fp64_nominal, "frac": flops / kern_s / 1e12 / fp64_peak,
+                          "flops_model": "SURVEY 8d (the dense algorithm): 2 x N^3/3 + 2 N^2 x iterations_executed per cold QP",
+                          "executed_tflops": flops_exec / kern_s / 1e12, "frac_executed": flops_exec / kern_s / 1e12 / fp64_peak,
+                          "executed_model": "counted: (1 + iterating fraction) x (Nr^3/3 + m^2 ndp) + 2 Nr^2 x (1 + mean n_iter), "
+                                            "Nr = KKT rows factored per QP",
+                          "kkt_rows_factored": Nr, "kkt_rows_dense": float(n + m), "iterating_fraction": f_it},
+        "structure": sinfo,
         "latency": {"p50_ms_per_batch_launch": float(np.median(step_ms))},
     }
     # p50 latency of one warm Solve through the drop-in FCCQP object (fcc_qp_test.py loop)
@@ -337,6 +496,11 @@ def run_ours(args):
                                     "sample": f"first {sample} QPs of the same tiled log, cold, solved {reps}x, {tot:.1f} s"}
         except Exception as e:  # pragma: no cover
             line["cpu_baseline"] = {"value": None, "unit": "QP/s", "cores": 0, "kind": "port", "sample": repr(e)}
+        if not args.no_extras:
+            line["cpu_baseline_variants"] = cpu_baseline_variants(log, 4038)
+            del dev_args, pinned
+            torch.cuda.empty_cache()
+            line["shapes"] = shape_extras(dev)
     emit(line)
     return 0
 
@@ -364,6 +528,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra keys (other shapes, CPU baseline variants)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

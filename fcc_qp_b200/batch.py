@@ -59,13 +59,22 @@ def _is_torch(a) -> bool:
 
 class FCCQPBatch:
     def __init__(self, num_vars: int, num_equality_constraints: int, nc: int, lambda_c_start: int,
-                 device: int = 0, precision: str = "fp64"):
+                 device=0, precision: str = "fp64"):
         if nc % 3 != 0:
             raise ValueError("nc must be a multiple of 3 (src/fcc_qp.cpp:32)")
         if lambda_c_start < 0 or lambda_c_start + nc > num_vars:
             raise ValueError("lambda_c_start + nc must be <= num_vars (src/fcc_qp.cpp:33)")
         self.n, self.m, self.nc, self.lcs = int(num_vars), int(num_equality_constraints), int(nc), int(lambda_c_start)
-        self.device = int(device)
+        # device: one CUDA ordinal, or a sequence of them -- host (numpy) batches are then split into contiguous shards,
+        # one per device, inside ONE call (fccqp_batch_solve_multi: a host thread, streams and staging buffers per device)
+        if isinstance(device, (list, tuple)):
+            self.devices = [int(v) for v in device]
+            if not self.devices:
+                raise ValueError("device list is empty")
+            self.device = self.devices[0]
+        else:
+            self.devices = None
+            self.device = int(device)
         # "fp64": the reference's arithmetic and data.  "fp32_data": Q, b, A_eq, b_eq, friction_coeffs, lb, ub
         # travel and are stored as float32 (half the PCIe / HBM bytes), arithmetic, state and outputs stay
         # FP64 (FCCQP_PRECISION_FP32_DATA in include/fccqp.h; stated bound 2e-3 relative on z).
@@ -245,7 +254,11 @@ class FCCQPBatch:
         secs = C.c_double(0.0)
         d.device_seconds = C.pointer(secs)
         t0 = time.perf_counter()
-        nat.check(nat.lib().fccqp_batch_solve(C.byref(d)))
+        if self.devices is not None:
+            devs = (C.c_int32 * len(self.devices))(*self.devices)
+            nat.check(nat.lib().fccqp_batch_solve_multi(C.byref(d), devs, len(self.devices)))
+        else:
+            nat.check(nat.lib().fccqp_batch_solve(C.byref(d)))
         wall = time.perf_counter() - t0
         self._state = (x, mux, muc)
         # zero_copy_outputs: z and the details are views of the solver-owned page-locked buffers,

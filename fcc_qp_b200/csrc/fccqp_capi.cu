@@ -14,6 +14,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -503,6 +504,38 @@ int fccqp_device_count(void) {
   return c;
 }
 int64_t fccqp_kernel_launch_count(void) { return g_launches.load(); }
+
+int fccqp_measure_fp64_peak(int device, double* tflops) {
+  if (!tflops) return fail(FCCQP_E_INVALID, "tflops is null");
+  DeviceCtx* ctx = nullptr;
+  int rc = get_ctx(device, &ctx);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(device));
+  double* d_out = nullptr;
+  CUDA_TRY(cudaMalloc(&d_out, sizeof(double)));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  const int grid = ctx->num_sms * 4, iters = 60000;   // ~50 ms on a B200
+  double best = 0.0;
+  for (int rep = 0; rep < 3; ++rep) {   // first launch warms the clocks up
+    CUDA_TRY(cudaEventRecord(e0, 0));
+    fccqp::fp64_peak_kernel<<<grid, 256>>>(d_out, iters, 1.0);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(e1, 0));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = 2.0 * 64.0 * (double)iters * 256.0 * (double)grid;
+    const double tf = fl / (1e-3 * ms) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  g_launches.fetch_add(3);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  CUDA_TRY(cudaFree(d_out));
+  *tflops = best;
+  return FCCQP_OK;
+}
 int fccqp_last_struct_info(int* used, int* caps, int* rows, int* rows_dense, int* deferred) {
   StructInfo si;
   { std::lock_guard<std::mutex> lk(g_info_mu); si = g_last_struct; }
@@ -988,6 +1021,69 @@ int fccqp_batch_solve(const fccqp_batch_desc* desc) {
     }
   }
   for (auto& s : ctx->streams) CUDA_TRY(cudaStreamSynchronize(s));
+  if (d.device_seconds)
+    *d.device_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return FCCQP_OK;
+}
+
+// One call, several devices ("one host thread + stream set per device, host-side scatter and gather").
+// The batch shards trivially -- QPs are independent, there is no exchange step -- so device r of W takes the
+// contiguous range [B r / W, B (r+1) / W) of every stacked array (shared arrays, batch stride 0, go to every device)
+// and runs the single-device host path on its own host thread: staging buffers, streams, H2D / solve / D2H
+// pipeline and structure classification are per device.
+int fccqp_batch_solve_multi(const fccqp_batch_desc* desc, const int32_t* devices, int32_t n_devices) {
+  int rc = validate_desc(desc);
+  if (rc) return rc;
+  if (!devices || n_devices < 1) return fail(FCCQP_E_INVALID, "devices / n_devices");
+  if (desc->memory_space != FCCQP_MEM_HOST)
+    return fail(FCCQP_E_UNSUPPORTED, "fccqp_batch_solve_multi takes host memory (device pointers live on ONE device: call fccqp_batch_solve per device)");
+  for (int i = 0; i < n_devices; ++i)
+    for (int j = 0; j < i; ++j)
+      if (devices[i] == devices[j]) return fail(FCCQP_E_INVALID, "device %d listed twice", devices[i]);
+  for (int i = 0; i < n_devices; ++i) {
+    DeviceCtx* ctx = nullptr;
+    if ((rc = get_ctx(devices[i], &ctx))) return rc;
+  }
+  const fccqp_batch_desc& d = *desc;
+  const auto t0 = std::chrono::steady_clock::now();
+  const int W = n_devices;
+  std::vector<int> rcs(W, FCCQP_OK);
+  std::vector<std::string> errs(W);
+  auto shard = [&](int r) {
+    const long long lo = (long long)d.batch * r / W, hi = (long long)d.batch * (r + 1) / W;
+    if (hi <= lo) return;
+    fccqp_batch_desc s = d;
+    s.device = devices[r];
+    s.batch = (int32_t)(hi - lo);
+    s.device_seconds = nullptr;
+    const size_t es = d.precision == FCCQP_PRECISION_FP32_DATA ? sizeof(float) : sizeof(double);
+    auto adv = [&](const double* p, int64_t stride) -> const double* {   // problem data: element size es
+      return p ? reinterpret_cast<const double*>(reinterpret_cast<const char*>(p) + (size_t)lo * (size_t)stride * es) : p;
+    };
+    s.Q = adv(d.Q, d.q_batch_stride); s.b = adv(d.b, d.b_batch_stride); s.A_eq = adv(d.A_eq, d.a_batch_stride);
+    s.b_eq = adv(d.b_eq, d.beq_batch_stride); s.friction_coeffs = adv(d.friction_coeffs, d.mu_batch_stride);
+    s.lb = adv(d.lb, d.lb_batch_stride); s.ub = adv(d.ub, d.ub_batch_stride);
+    if (d.x) s.x = d.x + lo * d.n;
+    if (d.mu_x) s.mu_x = d.mu_x + lo * d.n;
+    if (d.mu_lambda_c) s.mu_lambda_c = d.mu_lambda_c + lo * d.nc;
+    if (d.n_iter) s.n_iter = d.n_iter + lo;
+    if (d.status) s.status = d.status + lo;
+    if (d.res_bounds) s.res_bounds = d.res_bounds + lo;
+    if (d.res_fcone) s.res_fcone = d.res_fcone + lo;
+    if (d.bounds_viol) s.bounds_viol = d.bounds_viol + lo;
+    if (d.fcone_viol) s.fcone_viol = d.fcone_viol + lo;
+    rcs[r] = fccqp_batch_solve(&s);
+    if (rcs[r]) errs[r] = g_err;   // (thread-local: carried back to the caller's thread below)
+  };
+  if (W == 1) shard(0);
+  else {
+    std::vector<std::thread> th;
+    th.reserve(W);
+    for (int r = 0; r < W; ++r) th.emplace_back(shard, r);
+    for (auto& t : th) t.join();
+  }
+  for (int r = 0; r < W; ++r)
+    if (rcs[r]) return fail(rcs[r], "device %d: %s", devices[r], errs[r].c_str());
   if (d.device_seconds)
     *d.device_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return FCCQP_OK;

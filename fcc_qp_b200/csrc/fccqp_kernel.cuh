@@ -1648,4 +1648,25 @@ __global__ void __launch_bounds__(256) wbc_assemble_kernel(const WbcParams p) {
   }
 }
 
+// FP64 FMA peak of this device, measured (bench.py's roofline denominator): 8 independent DFMA chains per thread,
+// 4 x 256 threads per SM, no memory traffic.  2 * fmas / time is what the vector FP64 pipe (which the DMMA
+// instruction shares, profiles/r01_fp64_ubench.log) can do at the clocks of the moment.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, const int iters, const double seed) {
+  double a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = seed + threadIdx.x * 1e-9 + k;
+  const double m1 = 1.0 - 1e-12, c1 = 1e-13;
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] = fma(a[k], m1, c1);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += a[k];
+  if (s == 12345.678) out[0] = s;   // never true: keeps the chains alive
+}
+
 }  // namespace fccqp

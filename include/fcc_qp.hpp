@@ -211,6 +211,15 @@ class FCCQPBatch {
       throw std::invalid_argument("lambda_c_start + nc must be <= num_vars (src/fcc_qp.cpp:33)");
     fccqp_default_options(&opt_);
   }
+  // Several devices of one box: every Solve() is split into contiguous shards, one per device, inside one call
+  // (fccqp_batch_solve_multi).
+  FCCQPBatch(int num_vars, int num_equality_constraints, int nc, int lambda_c_start, std::vector<int> devices)
+      : FCCQPBatch(num_vars, num_equality_constraints, nc, lambda_c_start, devices.empty() ? 0 : devices[0]) {
+    if (devices.empty()) throw std::invalid_argument("device list is empty");
+    devices_.assign(devices.begin(), devices.end());
+  }
+  // fccqp_structure (| FCCQP_STRUCTURE_REFINE) of the batched calls; default FCCQP_STRUCTURE_AUTO
+  void set_structure(int structure) { structure_ = structure; }
   void set_rho(double rho) { if (!(rho > 0)) throw std::invalid_argument("rho must be > 0"); opt_.rho = rho; }
   void set_max_iter(int n) { if (n <= 0) throw std::invalid_argument("max_iter must be > 0"); opt_.max_iter = n; }
   void set_options(FCCQPOptions o) {
@@ -245,7 +254,9 @@ class FCCQPBatch {
     d.bounds_viol = sol_.bounds_viol.data(); d.fcone_viol = sol_.friction_cone_viol.data();
     double secs = 0.0;
     d.device_seconds = &secs;
-    const int rc = fccqp_batch_solve(&d);
+    d.structure = structure_;
+    const int rc = devices_.size() > 1 ? fccqp_batch_solve_multi(&d, devices_.data(), (int32_t)devices_.size())
+                                       : fccqp_batch_solve(&d);
     if (rc == FCCQP_E_INVALID) throw std::invalid_argument(fccqp_last_error());
     if (rc != FCCQP_OK) throw std::runtime_error(fccqp_last_error());
     sol_.solve_time = secs;
@@ -256,6 +267,8 @@ class FCCQPBatch {
   const int n_, m_, nc_, lcs_, device_;
   fccqp_options opt_{};
   bool warm_ = false;
+  int structure_ = FCCQP_STRUCTURE_AUTO;
+  std::vector<int32_t> devices_;
   FCCQPBatchSolution sol_;
   std::vector<double> mu_x_, mu_c_;
 };

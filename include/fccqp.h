@@ -205,11 +205,17 @@ typedef struct fccqp_batch_desc {
   void* stream;            /* cudaStream_t for FCCQP_MEM_DEVICE (NULL = default stream).
                               Device calls are asynchronous on this stream. */
   double* device_seconds;  /* optional HOST pointer: kernel time by CUDA events (forces a sync) */
-  int32_t structure;       /* enum fccqp_structure (| FCCQP_STRUCTURE_REFINE); 0 = AUTO */
+  int32_t structure;       /* enum fccqp_structure, optionally | FCCQP_STRUCTURE_REFINE; 0 = AUTO */
   int32_t struct_caps[3];  /* FCCQP_STRUCTURE_CAPS only */
 } fccqp_batch_desc;
 
 int fccqp_batch_solve(const fccqp_batch_desc* desc);
+/* The same call spread over several devices of one box (FCCQP_MEM_HOST only; desc->device is ignored): device r
+ * of n_devices takes the contiguous range [B r / n, B (r+1) / n) of every stacked array -- QPs are independent, so
+ * there is no exchange step -- on its own host thread with its own streams and staging buffers.  Outputs land in
+ * the caller's arrays exactly as with one device; device_seconds is the wall time of the whole call.
+ * (Device-resident data lives on ONE device: shard it yourself and call fccqp_batch_solve per device.) */
+int fccqp_batch_solve_multi(const fccqp_batch_desc* desc, const int32_t* devices, int32_t n_devices);
 /* Page-locked host memory for FCCQP_MEM_HOST callers: inputs and outputs that live in
  * memory from here (or from cudaHostAlloc / torch pin_memory) move by asynchronous DMA that
  * overlaps the solve; pageable outputs go through an internal pinned bounce buffer. */
@@ -258,6 +264,9 @@ int fccqp_wbc_assemble(const fccqp_wbc_desc* desc);
 /* Introspection used by bench.py for the roofline line: kernel launches issued
  * by this library since load, and the launch geometry of the last batch call. */
 int64_t fccqp_kernel_launch_count(void);
+/* Vector-FP64 FMA peak of `device` in TFLOP/s, MEASURED with a ~50 ms register-only DFMA kernel (the FP64 tensor-core
+ * instruction the solver uses shares that pipe): the denominator of bench.py's roofline_fp64. */
+int fccqp_measure_fp64_peak(int device, double* tflops);
 int fccqp_last_launch_info(int* grid, int* block, int* smem_bytes, int* ctas_per_sm);
 /* What the last batch launch did about problem structure: used = 1 if the reduced kernel ran; caps[3] = the
  * structure bounds its layout was sized for (pass them back as FCCQP_STRUCTURE_CAPS); rows / rows_dense = padded

@@ -23,6 +23,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PORT_SO = os.path.join(_HERE, "libfccqp_oracle.so")
 _REF_SO = os.path.join(_HERE, "_ref", "libfccqp_ref.so")
+_REF_AVX2_SO = os.path.join(_HERE, "_ref", "libfccqp_ref_avx2.so")   # same sources, -march=x86-64-v3 (bench.py extra)
 REFERENCE_ROOT = "/root/reference"
 
 _dp = C.POINTER(C.c_double)
@@ -37,8 +38,12 @@ def build(ref: bool = True, quiet: bool = True) -> None:
         subprocess.check_call(["make", "-C", _HERE, "ref"], **kw)
 
 
+def _so(kind: str) -> str:
+    return {"port": _PORT_SO, "ref": _REF_SO, "ref_avx2": _REF_AVX2_SO}[kind]
+
+
 def have(kind: str) -> bool:
-    return os.path.exists(_PORT_SO if kind == "port" else _REF_SO)
+    return os.path.exists(_so(kind))
 
 
 def _ptr(a, t=_dp):
@@ -56,11 +61,11 @@ def colmajor_stack(M: np.ndarray) -> np.ndarray:
 
 class Oracle:
     def __init__(self, kind: str = "port"):
-        assert kind in ("port", "ref")
+        assert kind in ("port", "ref", "ref_avx2")
         self.kind = kind
-        path = _PORT_SO if kind == "port" else _REF_SO
+        path = _so(kind)
         if not os.path.exists(path):
-            build(ref=(kind == "ref"))
+            build(ref=(kind != "port"))
         self.lib = C.CDLL(path)
         self.p = "fccqp_oracle_" if kind == "port" else "fccqp_ref_"
         f = lambda name: getattr(self.lib, self.p + name)
