@@ -145,6 +145,16 @@ class FCCQPBatch:
         else:
             self._solve_numpy(Q, b, A_eq, b_eq, friction_coeffs, lb, ub)
 
+    @staticmethod
+    def validate_bounds(lb, ub) -> bool:
+        """``lb <= ub`` everywhere (``validate_bounds``, src/constraint_utils.cpp:67-69).  The reference only
+        ASSERTS it (src/fcc_qp.cpp:121, compiled out by its own -DNDEBUG release flags); the batched entry points
+        do not pay an O(B n) host pass per call for it either -- call this where the check is wanted.  With
+        ``lb > ub`` the projection returns ``lb`` (same min/max order as the reference)."""
+        if _is_torch(lb):
+            return bool((lb <= ub).all().item())
+        return bool(np.all(np.asarray(lb) <= np.asarray(ub)))
+
     def GetSolution(self) -> BatchSolution:
         if self._sol is None:
             raise RuntimeError("GetSolution() before Solve()")
@@ -196,7 +206,9 @@ class FCCQPBatch:
         if tuple(Q) != (B, n, n) or tuple(b) != (B, n) or tuple(A) != (B, m, n) or tuple(beq) != (B, m):
             raise ValueError(f"expected Q[{B},{n},{n}], b[{B},{n}], A_eq[{B},{m},{n}], b_eq[{B},{m}]; got "
                              f"{tuple(Q)}, {tuple(b)}, {tuple(A)}, {tuple(beq)}")
-        if tuple(mu) not in ((B, nc // 3), (nc // 3,)):
+        # (a longer friction_coeffs vector is accepted like the reference does -- it reads the first nc/3 entries,
+        # src/constraint_utils.cpp:27-35 -- the batch stride then skips the rest)
+        if not (len(mu) in (1, 2) and mu[-1] >= nc // 3 and (len(mu) == 1 or mu[0] == B)):
             if len(mu) and mu[-1] < nc // 3:
                 raise IndexError(f"friction_coeffs has {mu[-1]} entries per QP, need {nc // 3} "
                                  "(reference: std::out_of_range, src/constraint_utils.cpp:32)")
@@ -245,7 +257,7 @@ class FCCQPBatch:
         d.b, d.b_batch_stride = p(b), n
         d.A_eq, d.a_batch_stride, d.a_row_stride, d.a_col_stride = p(A_eq), (0 if shared else m * n), n, 1
         d.b_eq, d.beq_batch_stride = p(b_eq), m
-        d.friction_coeffs, d.mu_batch_stride = p(mu), (nc // 3 if mu.ndim == 2 else 0)
+        d.friction_coeffs, d.mu_batch_stride = p(mu), (mu.shape[1] if mu.ndim == 2 else 0)
         d.lb, d.lb_batch_stride = p(lb), (n if lb.ndim == 2 else 0)
         d.ub, d.ub_batch_stride = p(ub), (n if ub.ndim == 2 else 0)
         d.x, d.mu_x, d.mu_lambda_c = p(x), p(mux), p(muc)

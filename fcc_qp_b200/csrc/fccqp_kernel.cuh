@@ -244,6 +244,9 @@ __device__ __forceinline__ void block_reduce2(double& a, double& b, double* red,
   parity ^= 1;
 }
 
+// Smallest pivot, relative to the largest pivot of the same class, that the unpivoted LDL^T still trusts.
+constexpr double kPivotRatio = 1e-12;
+
 // 1/d to full double precision: MUFU seed x0 (relative error e <= 2^-23) and ONE third-order step
 // x0 (1 + e + e^2) = (1/d)(1 - e^3): three dependent FMAs behind the MUFU instead of the four of two
 // Newton steps, and far shorter than the IEEE division sequence.  d is a factorization pivot
@@ -1370,11 +1373,19 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
         // negative ones on the constraint rows.  Anything else means Q + sigma A'A (or Q + rho I) is not
         // positive definite on this QP or A_eq lost row rank -- the unpivoted factors are meaningless even
         // when x comes out finite (the reference pivots / falls back to COD there): NUMERICAL_ISSUE.
+        // A pivot of the right sign that is pure rounding noise (nearly dependent rows of A_eq; Q + sigma A'A
+        // singular to working precision) is caught by its size: below kPivotRatio times the largest pivot of its
+        // own class (variable rows / constraint rows) -- legitimate scale differences inside one class stay
+        // many orders of magnitude above that (fccqp.h, "conditioning limit").
         bool badp = false;
+        double pa = 0.0, pc = 0.0;
+        const double dn = is_row ? dneg[t] : 0.0;   // -d_t
         if (is_row) {
-          const double dn = dneg[t];   // -d_t
           badp = !isfinite(dn) || (is_c ? !(dn > 0.0) : !(dn < 0.0));
+          if (is_c) pc = fabs(dn); else if (pass == 0) pa = fabs(dn);   // (Q + rho I: any spread of scales is legitimate)
         }
+        block_reduce2<false>(pa, pc, red, parity);
+        if (is_row && fabs(dn) < kPivotRatio * (is_c ? pc : pa)) badp = true;
         factor_flag = __syncthreads_or(badp) ? 2 : 0;
       }
       if (shared_mode != 0) {

@@ -1065,12 +1065,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
             fact_cycles += (unsigned long long)(clock64() - t_f0);
             // inertia (+ on R and D0 rows and all pads, - on the constraint rows): anything else goes to the general kernel
             {
+              // (and a constraint pivot that is rounding noise next to the others -- nearly dependent rows of A_eq --
+              // goes the same way: kPivotRatio, fccqp_kernel.cuh)
               bool badp = false;
-              if (t < Se.N8) {
-                const double dn = dneg[t];
-                const bool neg = yrow >= 0 && yrow < m;
-                badp = !isfinite(dn) || (neg ? !(dn > 0.0) : !(dn < 0.0));
-              }
+              const bool neg = yrow >= 0 && yrow < m;
+              const double dn = t < Se.N8 ? dneg[t] : 0.0;
+              if (t < Se.N8) badp = !isfinite(dn) || (neg ? !(dn > 0.0) : !(dn < 0.0));
+              double pc = neg ? fabs(dn) : 0.0, pu = 0.0;
+              block_reduce2<false>(pc, pu, red, parity);
+              if (neg && fabs(dn) < kPivotRatio * pc) badp = true;
               if (__syncthreads_or(badp)) { defer = true; break; }
             }
           }  // lazy factorization

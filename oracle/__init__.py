@@ -91,6 +91,7 @@ class Oracle:
             f("set_state").argtypes = [C.c_void_p, _dp, _dp, _dp]
             self.lib.fccqp_oracle_project_cone3.argtypes = [_dp, C.c_double, _dp]
             self.lib.fccqp_oracle_set_relaxation.argtypes = [C.c_double]
+            self.lib.fccqp_oracle_set_trace.argtypes = [C.c_void_p, _dp, C.c_int]
             self.lib.fccqp_oracle_cone_violation.restype = C.c_double
             self.lib.fccqp_oracle_cone_violation.argtypes = [_dp, C.c_int, _dp]
             self.lib.fccqp_oracle_bound_violation.restype = C.c_double
@@ -179,6 +180,14 @@ class OracleSolver:
         return dict(z=z, n_iter=it.value, status=st.value, res_bounds=det[0], res_fcone=det[1],
                     bounds_viol=det[2], fcone_viol=det[3], solve_time=det[4],
                     factorization_time=det[5])
+
+    def trace_residuals(self, cap: int) -> np.ndarray:
+        """Port only: the following Solve calls record (bound residual, cone residual) per ADMM iteration
+        -- the two numbers the exit test of fcc_qp.cpp:105 compares with eps -- into the returned [cap, 2] array."""
+        assert self.o.kind == "port"
+        self._trace = np.full((cap, 2), np.nan)
+        self.o.lib.fccqp_oracle_set_trace(self.h, _ptr(self._trace), cap)
+        return self._trace
 
     def presolve_path(self) -> int:
         return int(self.o.fn("presolve_path")(self.h))

@@ -53,6 +53,10 @@ struct fccqp_oracle {
   int n_iter;
   double solve_time, factorization_time;
   int presolve_path;
+  /* test hook (not in the reference): residual history of the last DoADMM, [2 * iter] = bound residual,
+   * [2 * iter + 1] = friction-cone residual -- what the exit test of fcc_qp.cpp:105 compared with eps */
+  double* trace;
+  int trace_cap;
 };
 
 static double now_s(void) {
@@ -436,6 +440,8 @@ static double inf_norm_like_reference(const double* v, int len) {
 /* process-wide over-relaxation of the restatement (tests of the product's extension only; default 1 = reference) */
 static double g_relaxation = 1.0;
 void fccqp_oracle_set_relaxation(double alpha) { g_relaxation = alpha; }
+/* residual history of the following solves goes to buf[2 * cap] (NULL: off); caller-owned */
+void fccqp_oracle_set_trace(fccqp_oracle* o, double* buf, int cap) { o->trace = buf; o->trace_cap = cap; }
 
 static void do_admm(fccqp_oracle* o, const double* b, const double* mu, const double* lb,
                     const double* ub) {
@@ -492,6 +498,10 @@ static void do_admm(fccqp_oracle* o, const double* b, const double* mu, const do
     }
     o->x_res_norm = inf_norm_like_reference(o->x_res, n);
     o->lambda_c_res_norm = inf_norm_like_reference(o->lambda_c_res, nc);
+    if (o->trace && iter < o->trace_cap) {
+      o->trace[2 * iter] = o->x_res_norm;
+      o->trace[2 * iter + 1] = o->lambda_c_res_norm;
+    }
 
     for (int i = 0; i < n; ++i) o->mu_x[i] += o->x_res[i];
     for (int i = 0; i < nc; ++i) o->mu_lambda_c[i] += o->lambda_c_res[i];

@@ -56,6 +56,10 @@ void fccqp_oracle_project_cone3(const double f[3], double mu, double out[3]);
 double fccqp_oracle_cone_violation(const double* f, int nc, const double* mu);
 double fccqp_oracle_bound_violation(const double* x, const double* lb, const double* ub, int n);
 
+/* Test hook: per-iteration residuals (bound, friction cone) of the following solves into buf[2 * cap]; the
+ * parity tests use it to show that an iteration-count difference sits on the exit threshold. */
+void fccqp_oracle_set_trace(fccqp_oracle* o, double* buf, int cap);
+
 /* Extension used only to check the product's opt-in over-relaxation (include/fccqp.h); 1.0 = the reference. */
 void fccqp_oracle_set_relaxation(double alpha);
 

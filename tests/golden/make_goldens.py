@@ -44,13 +44,17 @@ def make_synthetic():
     the seeded generator at test time; `in_sum` guards against generator drift."""
     from fcc_qp_b200 import synthetic as syn
     ref = Oracle("ref")
-    for shp, B in ((syn.HUMANOID, 192), (syn.QUADRUPED, 192), (syn.MULTICONTACT, 96)):
+    # (the B = 4096 humanoid set is BASELINE config 3 at a size where every code path of the kernel -- lazy
+    # factorization, operator switch, deferral -- is hit hundreds of times; float32 storage of z would lose the bar,
+    # so it stays float64: 2.8 MB)
+    for shp, B, suffix in ((syn.HUMANOID, 192, ""), (syn.QUADRUPED, 192, ""), (syn.MULTICONTACT, 96, ""),
+                           (syn.HUMANOID, 4096, "_4096")):
         qp = syn.make_batch(shp, B)
         chk = np.array([qp.Q.sum(), qp.A_eq.sum(), qp.b.sum(), qp.b_eq.sum(), qp.friction_coeffs.sum()])
-        save(f"synthetic_{shp.name}_cold.npz", ref.solve_batch(qp, warm_mode=0, nthreads=8, **LOG_OPTS),
+        save(f"synthetic_{shp.name}_cold{suffix}.npz", ref.solve_batch(qp, warm_mode=0, nthreads=8, **LOG_OPTS),
              LOG_OPTS, dict(in_sum=chk))
     # config 5: multi-contact humanoid, T sequential warm-started batches with lane-wise state
-    shp, B, T = syn.MULTICONTACT, 48, 6
+    shp, B, T = syn.MULTICONTACT, 48, 32   # BASELINE config 5: T = 32 sequential warm-started batches
     qp = syn.make_batch(shp, B, seed=shp.seed + 1)
     rng = np.random.default_rng(shp.seed + 2)
     lanes = ref.lanes(B, qp.n, qp.m, qp.nc, qp.lambda_c_start)

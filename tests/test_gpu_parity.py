@@ -22,6 +22,57 @@ def rel_err(z, zref):
     return np.abs(z - zref).max(1) / np.maximum(1.0, np.abs(zref).max(1))
 
 
+# Iteration counts: identical to the reference's, except where the reference's own exit test (fcc_qp.cpp:105) is
+# decided by less than MARGIN_TOL of eps -- then a difference of the iterates far below the 1e-6 bar flips it.
+# Every differing QP is re-run through the C restatement with its residual history recorded, from the SAME warm
+# state the GPU started from, and the margin at the disputed iteration is asserted (explain_count_mismatches).
+MARGIN_TOL = 2e-2
+
+
+def exit_margin(trace, k, eps_b, eps_f):
+    """How far (relative to eps) the restatement's residuals at iteration k are from flipping its exit decision."""
+    rb, rf = trace[k]
+    if rb < eps_b and rf < eps_f:      # it exits here: the closest residual has to rise above eps
+        return min((eps_b - rb) / eps_b, (eps_f - rf) / eps_f)
+    return max((rb - eps_b) / eps_b if rb >= eps_b else 0.0, (rf - eps_f) / eps_f if rf >= eps_f else 0.0)
+
+
+def explain_count_mismatches(qp, n_gpu, n_ref, opts=LOG_OPTS, state=None, z_gpu=None, also=()):
+    """Every QP whose count differs from the reference's must sit on the exit threshold: the restatement, started from
+    the same state, either reproduces the GPU count or its residuals at the first disputed iteration are within
+    MARGIN_TOL of eps.  Counts may then differ by more than one (a slowly converging QP hovers at eps for several
+    iterations), but never without a threshold crossing.  Returns the margins (for the log)."""
+    import oracle
+    idx = np.union1d(np.nonzero(np.asarray(n_gpu) != np.asarray(n_ref))[0], np.asarray(also, dtype=np.int64)).astype(np.int64)
+    margins = []
+    if idx.size == 0:
+        return margins
+    port = oracle.Oracle("port")
+    for i in idx:
+        s = port.solver(qp.n, qp.m, qp.nc, qp.lambda_c_start)
+        s.set_options(opts["max_iter"], opts["rho"], opts["eps_fcone"], opts["eps_bound"])
+        tr = s.trace_residuals(opts["max_iter"])
+        if state is not None:
+            s.o.fn("set_state")(s.h, *[np.ascontiguousarray(a[i], dtype=np.float64).ctypes.data_as(oracle._dp) for a in state])
+            s.set_warm_start(True)
+        mu = qp.friction_coeffs[i] if np.ndim(qp.friction_coeffs) == 2 else qp.friction_coeffs
+        s.Solve(qp.Q[i], qp.b[i], qp.A_eq[i], qp.b_eq[i], mu, qp.lb[i], qp.ub[i])
+        r_or = s.GetSolution()
+        k_or = r_or["n_iter"]
+        k_gpu = int(n_gpu[i])
+        if k_or == k_gpu:
+            # same start, same count: the golden differs only through the carried state; the solution bar applies
+            if z_gpu is not None:
+                assert rel_err(np.asarray(z_gpu)[i][None], r_or["z"][None]).max() <= Z_TOL, int(i)
+            margins.append(0.0)
+            continue
+        k = min(k_or, k_gpu)
+        mg = exit_margin(tr, k, opts["eps_bound"], opts["eps_fcone"])
+        assert mg <= MARGIN_TOL, (int(i), k_gpu, k_or, int(n_ref[i]), tr[k].tolist(), mg)
+        margins.append(mg)
+    return margins
+
+
 def make_solver(qp, opts=LOG_OPTS, device=0):
     from fcc_qp_b200.batch import FCCQPBatch, FCCQPOptionsB
     s = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start, device=device)
@@ -91,7 +142,7 @@ def test_walking_log_warm_sequential_batch_of_one(walking_log):
     gold = np.load(os.path.join(G, "walking_warm.npz"))
     qp = walking_log
     s = make_solver(qp)
-    K = 700
+    K = qp.batch   # all 2019 logged QPs
     z = np.zeros((K, qp.n)); it = np.zeros(K, np.int32)
     for i in range(K):
         s.set_warm_start(i > 0)
@@ -121,23 +172,30 @@ def test_warm_batch_with_explicit_state_matches_oracle(walking_log):
         assert np.array_equal(sol.details.n_iter, ref["n_iter"]), t
 
 
-@pytest.mark.parametrize("name,B", [("humanoid", 192), ("quadruped", 192), ("multicontact", 96)])
-def test_synthetic_cold(name, B):
-    """BASELINE configs 3-5 shapes (n=90/54/120).  Here the reference's pre-solve takes its LDLT
-    branch; the GPU pre-solve is the same augmented-Lagrangian LDL^T as on the log."""
+@pytest.mark.parametrize("name,B,suffix", [("humanoid", 192, ""), ("quadruped", 192, ""), ("multicontact", 96, ""),
+                                           ("humanoid", 4096, "_4096")])
+def test_synthetic_cold(name, B, suffix):
+    """BASELINE configs 3-5 shapes (n=90/54/120); humanoid also at B = 4096.  Here the reference's pre-solve takes its
+    LDLT branch; the GPU pre-solve is the reduced (or augmented-Lagrangian) LDL^T as on the log."""
     from fcc_qp_b200 import synthetic as syn
-    gold = np.load(os.path.join(G, f"synthetic_{name}_cold.npz"))
+    gold = np.load(os.path.join(G, f"synthetic_{name}_cold{suffix}.npz"))
     qp = syn.make_batch(syn.SHAPES[name], B)
     sol, _ = solve_host(qp)
     z = np.asarray(sol.z)
-    assert rel_err(z, gold["z"]).max() <= Z_TOL
+    n_gpu = np.asarray(sol.details.n_iter)
+    same = n_gpu == gold["n_iter"]
+    # the solution bar applies where both stopped at the same iterate; a QP that stopped one iteration apart is one
+    # ADMM step (itself below eps) away and is checked through its exit margin instead
+    assert rel_err(z[same], gold["z"][same]).max() <= Z_TOL
+    assert rel_err(z, gold["z"]).max() <= 10 * Z_TOL
     o, oref = qp.objective(z), qp.objective(gold["z"])
-    assert (np.abs(o - oref) / np.maximum(1.0, np.abs(oref))).max() <= OBJ_TOL
-    # iteration counts: identical except where a residual sits within rounding of eps (stated bound 2 %)
-    mism = sol.details.n_iter != gold["n_iter"]
-    assert mism.mean() <= 0.02, (mism.sum(), sol.details.n_iter[mism], gold["n_iter"][mism])
-    assert np.abs(sol.details.n_iter.astype(int) - gold["n_iter"])[mism].max(initial=0) <= 1
-    assert np.array_equal(sol.details.solve_status[~mism], gold["status"][~mism])
+    assert (np.abs(o - oref) / np.maximum(1.0, np.abs(oref)))[same].max() <= OBJ_TOL
+    margins = explain_count_mismatches(qp, n_gpu, gold["n_iter"])
+    print(f"{name} B={B}: {len(margins)} count differences, exit margins {np.round(margins, 5).tolist()}")
+    assert (~same).mean() <= 0.005    # (measured: 0 on all four sets)
+    # status: 1 iff the count reached max_iter, on both sides
+    assert np.array_equal(sol.details.solve_status[same], gold["status"][same])
+    assert np.array_equal(np.asarray(sol.details.solve_status) == 1, n_gpu == LOG_OPTS["max_iter"])
 
 
 def test_synthetic_multicontact_warm_sequence():
@@ -148,13 +206,26 @@ def test_synthetic_multicontact_warm_sequence():
     qp = syn.make_batch(shp, B, seed=shp.seed + 1)
     rng = np.random.default_rng(shp.seed + 2)
     s = make_solver(qp)
+    state = None
+    n_diff = 0
+    diverged = np.zeros(B, bool)    # lanes that took a threshold flip earlier: they carry their own warm start from then on
     for t in range(T):
         s.set_warm_start(t > 0)
         s.Solve(qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)
         sol = s.GetSolution()
-        assert rel_err(sol.z, gold["z"][t]).max() <= Z_TOL, t
-        assert (sol.details.n_iter != gold["n_iter"][t]).mean() <= 0.05, t
+        n_gpu = np.asarray(sol.details.n_iter)
+        same = (n_gpu == gold["n_iter"][t]) & ~diverged
+        assert rel_err(np.asarray(sol.z)[same], gold["z"][t][same]).max() <= Z_TOL, t
+        # lanes whose count differs, and lanes that diverged earlier: checked against the restatement started from the
+        # state the GPU started this step from (count identical + solution within the bar, or a threshold flip)
+        margins = explain_count_mismatches(qp, n_gpu, gold["n_iter"][t], state=state, z_gpu=sol.z,
+                                           also=np.nonzero(diverged)[0])
+        n_diff += int((n_gpu != gold["n_iter"][t]).sum())
+        diverged |= n_gpu != gold["n_iter"][t]
+        state = tuple(np.array(a, copy=True) for a in s.GetState())
         qp = syn.random_walk(qp, rng)
+    print(f"warm sequence T={T}: {n_diff} lane-steps with a count difference of {T * B}, {int(diverged.sum())} lanes affected")
+    assert n_diff <= 0.005 * T * B    # (measured: 0)
 
 
 def test_full_size_properties(walking_log):
