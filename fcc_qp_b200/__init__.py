@@ -9,11 +9,11 @@ build; using a solver without the CUDA library raises ImportError.
 """
 from __future__ import annotations
 
-__all__ = ["FCCQP", "FCCQPOptions", "FCCQPSolution", "FCCQPDetails", "FCCQPBatch", "BatchSolution",
+__all__ = ["FCCQP", "FCCQPOptions", "FCCQPSolution", "FCCQPDetails", "FCCQPBatch", "FCCQPBatchCpp", "BatchSolution",
            "solve_batch", "FCCQPError"]
 
 _PYBIND = ("FCCQP", "FCCQPOptions", "FCCQPSolution", "FCCQPDetails", "FCCQPSolveStatus")
-_BATCH = ("FCCQPBatch", "BatchSolution", "BatchDetails", "FCCQPOptionsB", "solve_batch")
+_BATCH = ("FCCQPBatch", "FCCQPBatchCpp", "BatchSolution", "BatchDetails", "FCCQPOptionsB", "solve_batch")
 
 
 def __getattr__(name):

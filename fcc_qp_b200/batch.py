@@ -95,6 +95,7 @@ class FCCQPBatch:
         self.time_kernel = True
         self._state = None     # (x, mu_x, mu_c) arrays / tensors
         self._host_out = None  # page-locked output buffers of the numpy path
+        self._dev_out = None   # device output / state tensors of the torch path
         self.zero_copy_outputs = False  # numpy path: GetSolution() returns views of those buffers
         self._sol: Optional[BatchSolution] = None
         nat.lib()              # fail loudly if the CUDA library is not built
@@ -301,15 +302,28 @@ class FCCQPBatch:
         b, b_eq, mu, lb, ub = map(cont, (b, b_eq, mu, lb, ub))
         warm = self.warm_start
         st = self._state
-        if warm and st is not None and _is_torch(st[0]) and tuple(st[0].shape) == (B, n) and st[0].device == dev:
-            x, mux, muc = (a.contiguous() for a in st)
+        # Outputs and carried state live in solver-owned device tensors, allocated once per (B, device) and reused
+        # from call to call (nothing is allocated inside a steady-state Solve).  A cold solve ignores the state
+        # on input (the kernel starts from zero duals), so the buffers need no clearing.
+        ob = self._dev_out
+        if ob is None or ob["x"].shape != (B, n) or ob["x"].device != dev:
+            ob = self._dev_out = dict(x=torch.zeros((B, n), dtype=torch.float64, device=dev),
+                                      mux=torch.zeros((B, n), dtype=torch.float64, device=dev),
+                                      muc=torch.zeros((B, nc), dtype=torch.float64, device=dev),
+                                      n_iter=torch.empty(B, dtype=torch.int32, device=dev),
+                                      status=torch.empty(B, dtype=torch.int32, device=dev),
+                                      res=torch.empty((4, B), dtype=torch.float64, device=dev))
+            fresh = True
         else:
-            x = torch.zeros((B, n), dtype=torch.float64, device=dev)
-            mux = torch.zeros((B, n), dtype=torch.float64, device=dev)
-            muc = torch.zeros((B, nc), dtype=torch.float64, device=dev)
-        n_iter = torch.empty(B, dtype=torch.int32, device=dev)
-        status = torch.empty(B, dtype=torch.int32, device=dev)
-        res = torch.empty((4, B), dtype=torch.float64, device=dev)
+            fresh = False
+        x, mux, muc = ob["x"], ob["mux"], ob["muc"]
+        if warm and st is not None and _is_torch(st[0]) and tuple(st[0].shape) == (B, n) and st[0].device == dev:
+            if st[0] is not x:      # state handed in through SetState
+                x.copy_(st[0]); mux.copy_(st[1]); muc.copy_(st[2])
+        elif warm and not fresh:
+            # a never-solved reference object warm-starts from the zero state (src/fcc_qp.cpp:48-52)
+            x.zero_(); mux.zero_(); muc.zero_()
+        n_iter, status, res = ob["n_iter"], ob["status"], ob["res"]
         if self.structure == "auto" and self._caps is not None and getattr(self, "_check_deferred", False):
             # the previous launch has long been consumed by now: many QPs beyond the cached bounds -> probe again
             if nat.last_struct_info()["deferred"] > B // 16:
@@ -342,8 +356,70 @@ class FCCQPBatch:
         # keep the inputs alive until the (possibly asynchronous) launch has consumed them
         self._keepalive = (Q, b, A_eq, b_eq, mu, lb, ub)
         self._state = (x, mux, muc)
-        self._sol = BatchSolution(BatchDetails(n_iter, res[0], res[1], res[2], res[3], status, wall, secs.value),
-                                  x.clone())
+        # zero_copy_outputs: z and the details are the solver-owned tensors themselves, valid until the next Solve();
+        # default: independent copies, like FCCQP::GetSolution
+        cp = (lambda a: a) if self.zero_copy_outputs else (lambda a: a.clone())
+        self._sol = BatchSolution(BatchDetails(cp(n_iter), cp(res[0]), cp(res[1]), cp(res[2]), cp(res[3]), cp(status),
+                                               wall, secs.value), cp(x))
+
+
+class FCCQPBatchCpp:
+    """The same batched surface as a thin shim over the C++ class ``fcc_qp::FCCQPBatch`` (``include/fcc_qp.hpp``) as
+    bound in the pybind11 module (``fcc_qp_solver.FCCQPBatch``): numpy stacks go to its host path, anything with
+    ``__dlpack__`` (torch CUDA tensors, cupy arrays) to its device path -- zero-copy, asynchronous on ``stream``,
+    outputs and carried state in tensors allocated once and reused.  No option of ``FCCQPBatch`` beyond the
+    reference's own is mirrored here (precision modes, structure caps, pinned zero-copy outputs stay there)."""
+
+    def __init__(self, num_vars: int, num_equality_constraints: int, nc: int, lambda_c_start: int, device=0):
+        from . import fcc_qp_solver as mod
+        self._mod = mod
+        self.n, self.m, self.nc, self.lcs = int(num_vars), int(num_equality_constraints), int(nc), int(lambda_c_start)
+        self._s = mod.FCCQPBatch(self.n, self.m, self.nc, self.lcs, list(device)) if isinstance(device, (list, tuple)) \
+            else mod.FCCQPBatch(self.n, self.m, self.nc, self.lcs, int(device))
+        self._out = None
+        self._sol = None
+        self.time_kernel = False
+
+    def set_rho(self, rho): self._s.set_rho(float(rho))
+    def set_max_iter(self, n): self._s.set_max_iter(int(n))
+    def set_warm_start(self, warm_start): self._s.set_warm_start(bool(warm_start))
+    def contact_vars_start(self): return self.lcs
+
+    def set_options(self, opt):
+        o = self._mod.FCCQPOptions()
+        for k in ("max_iter", "rho", "eps_fcone", "eps_bound", "relaxation"):
+            if hasattr(opt, k):
+                setattr(o, k, getattr(opt, k))
+        self._s.set_options(o)
+
+    def Solve(self, Q, b, A_eq, b_eq, friction_coeffs, lb, ub):
+        if not hasattr(Q, "__dlpack__") or isinstance(Q, np.ndarray):
+            self._s.Solve(Q, b, A_eq, b_eq, friction_coeffs, lb, ub)
+            r = self._s.GetSolution()
+            self._sol = BatchSolution(BatchDetails(r.n_iter, r.eps_bounds, r.eps_friction_cone, r.bounds_viol,
+                                                   r.friction_cone_viol, r.solve_status, r.solve_time, r.solve_time), r.z)
+            return
+        import torch
+        B, dev = int(b.shape[0]), b.device
+        o = self._out
+        if o is None or o[0].shape[0] != B or o[0].device != dev:
+            f64 = dict(dtype=torch.float64, device=dev)
+            o = self._out = (torch.zeros((B, self.n), **f64), torch.zeros((B, self.n), **f64), torch.zeros((B, self.nc), **f64),
+                             torch.empty(B, dtype=torch.int32, device=dev), torch.empty(B, dtype=torch.int32, device=dev),
+                             torch.empty((4, B), **f64))
+        mu = friction_coeffs if hasattr(friction_coeffs, "__dlpack__") and not isinstance(friction_coeffs, np.ndarray) \
+            else torch.as_tensor(np.asarray(friction_coeffs, dtype=np.float64), device=dev)
+        with torch.cuda.device(dev):
+            secs = self._s.SolveDLPack(Q, b, A_eq, b_eq, mu, lb, ub, *o,
+                                       stream=torch.cuda.current_stream(dev).cuda_stream, time_kernel=self.time_kernel)
+        self._keepalive = (Q, b, A_eq, b_eq, mu, lb, ub)
+        x, _, _, n_iter, status, det = o
+        self._sol = BatchSolution(BatchDetails(n_iter, det[0], det[1], det[2], det[3], status, secs, secs), x)
+
+    def GetSolution(self) -> BatchSolution:
+        if self._sol is None:
+            raise RuntimeError("GetSolution() before Solve()")
+        return self._sol
 
 
 def solve_batch(Q, b, A_eq, b_eq, friction_coeffs, lb, ub, nc: int, lambda_c_start: int,

@@ -194,6 +194,24 @@ struct FCCQPBatchProblem {
   bool shared_friction = false;    // friction_coeffs is [nc/3]
 };
 
+// Device-resident batch (extension): every pointer is DEVICE memory of `device`, strides in elements (batch stride 0 =
+// one array shared by all QPs), outputs / carried state caller-owned ([B,n] [B,n] [B,nc], [B] ints, [B] doubles; the
+// four per-QP scalars may be null).  What DLPack-able tensors (torch CUDA, cupy) boil down to.
+struct FCCQPBatchDeviceIO {
+  const double* Q = nullptr;      std::ptrdiff_t q_batch_stride = 0, q_row_stride = 0, q_col_stride = 1;
+  const double* b = nullptr;      std::ptrdiff_t b_batch_stride = 0;
+  const double* A_eq = nullptr;   std::ptrdiff_t a_batch_stride = 0, a_row_stride = 0, a_col_stride = 1;
+  const double* b_eq = nullptr;   std::ptrdiff_t beq_batch_stride = 0;
+  const double* friction_coeffs = nullptr;  std::ptrdiff_t mu_batch_stride = 0;
+  const double* lb = nullptr;     std::ptrdiff_t lb_batch_stride = 0;
+  const double* ub = nullptr;     std::ptrdiff_t ub_batch_stride = 0;
+  double *x = nullptr, *mu_x = nullptr, *mu_lambda_c = nullptr;
+  int *n_iter = nullptr, *solve_status = nullptr;
+  double *admm_residual_bounds = nullptr, *admm_residual_friction_cone = nullptr, *bounds_viol = nullptr, *friction_cone_viol = nullptr;
+  void* stream = nullptr;         // cudaStream_t the solve is enqueued on (asynchronous unless `device_seconds` is asked for)
+  int device = 0;
+};
+
 struct FCCQPBatchSolution {
   int batch = 0;
   std::vector<double> z;                       // [B,n]
@@ -262,6 +280,37 @@ class FCCQPBatch {
     sol_.solve_time = secs;
   }
   const FCCQPBatchSolution& GetSolution() const { return sol_; }
+
+  // Device pointers; enqueued on io.stream and NOT waited for unless device_seconds is given (then the call
+  // returns after the kernels and *device_seconds holds their time).  io.x / mu_x / mu_lambda_c are the carried
+  // state when set_warm_start(true).
+  void SolveDevice(int batch, const FCCQPBatchDeviceIO& io, double* device_seconds = nullptr) {
+    fccqp_batch_desc d{};
+    d.abi_version = FCCQP_ABI_VERSION; d.batch = batch; d.n = n_; d.m = m_; d.nc = nc_; d.lambda_c_start = lcs_;
+    d.device = io.device; d.memory_space = FCCQP_MEM_DEVICE; d.precision = FCCQP_PRECISION_FP64; d.warm_start = warm_ ? 1 : 0;
+    d.options = opt_;
+    d.Q = io.Q; d.q_batch_stride = io.q_batch_stride; d.q_row_stride = io.q_row_stride; d.q_col_stride = io.q_col_stride;
+    d.b = io.b; d.b_batch_stride = io.b_batch_stride;
+    d.A_eq = io.A_eq; d.a_batch_stride = io.a_batch_stride; d.a_row_stride = io.a_row_stride; d.a_col_stride = io.a_col_stride;
+    d.b_eq = io.b_eq; d.beq_batch_stride = io.beq_batch_stride;
+    d.friction_coeffs = io.friction_coeffs; d.mu_batch_stride = io.mu_batch_stride;
+    d.lb = io.lb; d.lb_batch_stride = io.lb_batch_stride;
+    d.ub = io.ub; d.ub_batch_stride = io.ub_batch_stride;
+    d.x = io.x; d.mu_x = io.mu_x; d.mu_lambda_c = io.mu_lambda_c;
+    d.n_iter = io.n_iter; d.status = io.solve_status;
+    d.res_bounds = io.admm_residual_bounds; d.res_fcone = io.admm_residual_friction_cone;
+    d.bounds_viol = io.bounds_viol; d.fcone_viol = io.friction_cone_viol;
+    d.stream = io.stream;
+    d.device_seconds = device_seconds;
+    d.structure = structure_;
+    const int rc = fccqp_batch_solve(&d);
+    if (rc == FCCQP_E_INVALID) throw std::invalid_argument(fccqp_last_error());
+    if (rc != FCCQP_OK) throw std::runtime_error(fccqp_last_error());
+  }
+  int num_vars() const { return n_; }
+  int num_equality_constraints() const { return m_; }
+  int num_contact_vars() const { return nc_; }
+  int contact_vars_start() const { return lcs_; }
 
  private:
   const int n_, m_, nc_, lcs_, device_;

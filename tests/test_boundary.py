@@ -163,3 +163,24 @@ def test_cpp_dropin_compiles_against_eigen_surface():
         pytest.skip("no Eigen headers here")
     tgt = build.build_cpp_dropin(force=True)
     assert tgt and os.path.exists(tgt)
+
+
+def test_pybind_batch_class_is_bound_and_has_no_cpu_path():
+    """fcc_qp::FCCQPBatch through the pybind11 module: the binding parses numpy stacks and DLPack tensors on the
+    host side; without a CUDA device the host path fails loudly and a CPU tensor is refused before any launch."""
+    import numpy as np
+    import torch
+    from fcc_qp_b200 import fcc_qp_solver as mod
+    s = mod.FCCQPBatch(6, 3, 0, 0)
+    for name in ("Solve", "SolveDLPack", "GetSolution", "set_options", "set_warm_start", "set_rho", "set_max_iter",
+                 "set_structure", "contact_vars_start"):
+        assert hasattr(s, name), name
+    z = lambda *shape: torch.zeros(shape, dtype=torch.float64)
+    outs = (z(2, 6), z(2, 6), z(2, 0), torch.zeros(2, dtype=torch.int32), torch.zeros(2, dtype=torch.int32), z(4, 2))
+    with pytest.raises(TypeError, match="CUDA device memory"):
+        s.SolveDLPack(z(2, 6, 6), z(2, 6), z(2, 3, 6), z(2, 3), z(0), z(6), z(6), *outs)
+    with pytest.raises(ValueError):
+        s.Solve(np.zeros((2, 6, 6)), np.zeros((2, 5)), np.zeros((2, 3, 6)), np.zeros((2, 3)), np.zeros(0), np.zeros(6), np.zeros(6))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            s.Solve(np.zeros((2, 6, 6)), np.zeros((2, 6)), np.zeros((2, 3, 6)), np.zeros((2, 3)), np.zeros(0), np.zeros(6), np.zeros(6))
