@@ -21,6 +21,7 @@
 #include "../../include/fccqp.h"
 #include "fccqp_kernel.cuh"
 #include "fccqp_struct.cuh"
+#include "fccqp_warp.cuh"
 
 namespace {
 
@@ -186,6 +187,47 @@ bool host_classify(int n, int m, const double* Q, long long q_rs, long long q_cs
   return ok;
 }
 
+// Small problems (n + m <= 32): one QP per warp (fccqp_warp.cuh), four warps per CTA, each pulling QPs from the work
+// counter on its own; shared memory per CTA = 4 private (n + m) x ((n + m) | 1) slabs.
+int launch_warp(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream) {
+  constexpr int kW = 4;
+  const int N = p.n + p.m;
+  const size_t smem = (size_t)kW * N * (N | 1) * sizeof(double);
+  KernelFn fn = (KernelFn)fccqp::fccqp_warp_kernel<kW, 6>;
+  int ctas_per_sm = 0;
+  {
+    std::lock_guard<std::mutex> lk(ctx.mu);
+    const auto key = std::make_pair((const void*)fn, smem);
+    auto it = ctx.occupancy.find(key);
+    if (it != ctx.occupancy.end()) ctas_per_sm = it->second;
+    else {
+      CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx.max_smem_optin));
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, fn, 32 * kW, smem));
+      if (ctas_per_sm < 1) return fail(FCCQP_E_UNSUPPORTED, "warp kernel does not fit on an SM (smem %zu B)", smem);
+      ctx.occupancy[key] = ctas_per_sm;
+    }
+  }
+  static const int cta_cap = getenv("FCCQP_CTAS_PER_SM") ? atoi(getenv("FCCQP_CTAS_PER_SM")) : 0;  // developer aid
+  if (cta_cap > 0 && cta_cap < ctas_per_sm) ctas_per_sm = cta_cap;
+  int grid = ctas_per_sm * ctx.num_sms;
+  if (grid > (p.B + kW - 1) / kW) grid = (p.B + kW - 1) / kW;
+  unsigned int* scr = nullptr;   // the work counter of this call (stream-ordered: any number of calls may be in flight)
+  CUDA_TRY(cudaMallocAsync(&scr, 8 * sizeof(unsigned int), stream));
+  CUDA_TRY(cudaMemsetAsync(scr, 0, 8 * sizeof(unsigned int), stream));
+  p.work_counter = scr;
+  fn<<<grid, 32 * kW, smem, stream>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaFreeAsync(scr, stream));
+  g_launches.fetch_add(1);
+  StructInfo si;
+  si.rows = si.rows_dense = N;
+  si.device = ctx.device;
+  std::lock_guard<std::mutex> lk(g_info_mu);
+  g_last_launch = {grid, 32 * kW, (int)smem, ctas_per_sm};
+  g_last_struct = si;
+  return FCCQP_OK;
+}
+
 // Launches the fused solve on `stream` for device-resident data described by p
 // (work counters / device-side lists are allocated here, stream-ordered).
 int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool in_f32 = false,
@@ -208,6 +250,9 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool
   p.struct_refine = getenv("FCCQP_STRUCT_REFINE") ? atoi(getenv("FCCQP_STRUCT_REFINE")) : (hint_in ? hint_in->refine : 0);
   p.struct_prefetch = getenv("FCCQP_STRUCT_PREFETCH") ? atoi(getenv("FCCQP_STRUCT_PREFETCH")) : 1;
   p.struct_bulk = getenv("FCCQP_STRUCT_BULK") ? atoi(getenv("FCCQP_STRUCT_BULK")) : 1;
+  // problem-size-specialised mapping: a QP whose KKT matrix fits one row per lane goes to the warp-per-QP kernel
+  // (FCCQP_NO_WARP=1: the CTA-per-QP kernels, for A/B tests)
+  if (!f32 && p.n + p.m <= 32 && !getenv("FCCQP_NO_WARP")) return launch_warp(ctx, p, stream);
   auto occupancy_of = [&](KernelFn f, int thr, size_t sm, int* out) -> int {
     std::lock_guard<std::mutex> lk(ctx.mu);
     const auto key = std::make_pair((const void*)f, sm);
