@@ -194,6 +194,7 @@ int launch_warp(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream) {
   const int N = p.n + p.m;
   const size_t smem = (size_t)kW * N * (N | 1) * sizeof(double);
   KernelFn fn = (KernelFn)fccqp::fccqp_warp_kernel<kW, 6>;
+  // (measured, tools/bench_small.py: 6 CTAs x 4 warps at 80 registers beats 8 x 4 at 64 and 4 x 4 at 128 on every shape but n = 6)
   int ctas_per_sm = 0;
   {
     std::lock_guard<std::mutex> lk(ctx.mu);
