@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # FCCQP_LIB: developer override (e.g. an instrumented -DFCCQP_DEV build of the same sources)
 LIB_PATH = os.environ.get("FCCQP_LIB") or os.path.join(_HERE, "libfccqp_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 STRUCTURE_AUTO, STRUCTURE_DENSE, STRUCTURE_CAPS = 0, 1, 2
 STRUCTURE_REFINE = 256   # flag: iterative refinement of the reduced cold pre-solve
 MEM_HOST, MEM_DEVICE = 0, 1
@@ -32,7 +32,7 @@ class FCCQPError(RuntimeError):
 
 
 class Options(C.Structure):
-    _fields_ = [("max_iter", C.c_int32), ("reserved", C.c_int32), ("rho", C.c_double),
+    _fields_ = [("max_iter", C.c_int32), ("adapt_rho_interval", C.c_int32), ("rho", C.c_double),
                 ("eps_fcone", C.c_double), ("eps_bound", C.c_double), ("relaxation", C.c_double)]
 
 

@@ -31,6 +31,7 @@ class FCCQPOptionsB:
     eps_fcone: float = 1e-3
     eps_bound: float = 1e-6
     relaxation: float = 1.0   # extension (not in the reference): ADMM over-relaxation alpha in (0, 2); 1.0 = reference
+    adapt_rho_interval: int = 0   # extension (not in the reference): adaptive rho every so many iterations; 0 = off
 
 
 @dataclasses.dataclass
@@ -113,7 +114,7 @@ class FCCQPBatch:
 
     def set_options(self, opt):
         self.options = FCCQPOptionsB(int(opt.max_iter), float(opt.rho), float(opt.eps_fcone), float(opt.eps_bound),
-                                     float(getattr(opt, "relaxation", 1.0)))
+                                     float(getattr(opt, "relaxation", 1.0)), int(getattr(opt, "adapt_rho_interval", 0)))
 
     def set_warm_start(self, warm_start: bool):
         self.warm_start = bool(warm_start)
@@ -168,7 +169,7 @@ class FCCQPBatch:
         d.batch, d.n, d.m, d.nc, d.lambda_c_start = B, self.n, self.m, self.nc, self.lcs
         d.device, d.memory_space, d.precision = self.device, mem, (1 if self.precision == "fp32_data" else 0)
         o = self.options
-        d.options = nat.Options(int(o.max_iter), 0, float(o.rho), float(o.eps_fcone), float(o.eps_bound), float(o.relaxation))
+        d.options = nat.Options(int(o.max_iter), int(getattr(o, 'adapt_rho_interval', 0)), float(o.rho), float(o.eps_fcone), float(o.eps_bound), float(o.relaxation))
         st = self.structure
         if st == "dense":
             d.structure = nat.STRUCTURE_DENSE
@@ -387,7 +388,7 @@ class FCCQPBatchCpp:
 
     def set_options(self, opt):
         o = self._mod.FCCQPOptions()
-        for k in ("max_iter", "rho", "eps_fcone", "eps_bound", "relaxation"):
+        for k in ("max_iter", "rho", "eps_fcone", "eps_bound", "relaxation", "adapt_rho_interval"):
             if hasattr(opt, k):
                 setattr(o, k, getattr(opt, k))
         self._s.set_options(o)

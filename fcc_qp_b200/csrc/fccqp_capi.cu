@@ -354,7 +354,8 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool
   StructHint hint;
   if (hint_in) hint = *hint_in;
   static const bool dev_instr = getenv("FCCQP_TRACE") != nullptr;
-  if (!no_struct_env && !dev_instr && !f32 && hint.mode != FCCQP_STRUCTURE_DENSE && p.n <= 256 && p.m <= 256 && p.m > 0) {
+  // (adaptive rho lives in the general and warp kernels only)
+  if (!no_struct_env && !dev_instr && !f32 && p.adapt_k == 0 && hint.mode != FCCQP_STRUCTURE_DENSE && p.n <= 256 && p.m <= 256 && p.m > 0) {
     int caps[3] = {hint.caps[0], hint.caps[1], hint.caps[2]};
     bool ok = true;
     if (hint.mode != FCCQP_STRUCTURE_CAPS) {
@@ -501,6 +502,7 @@ int check_options(const fccqp_options& o) {
   if (!(o.rho > 0.0)) return fail(FCCQP_E_INVALID, "rho must be > 0 (src/fcc_qp.hpp:76)");
   if (o.relaxation != 0.0 && !(o.relaxation > 0.0 && o.relaxation < 2.0))
     return fail(FCCQP_E_INVALID, "relaxation must be in (0, 2) (0 = unset = 1)");
+  if (o.adapt_rho_interval < 0) return fail(FCCQP_E_INVALID, "adapt_rho_interval must be >= 0 (0 = off)");
   return FCCQP_OK;
 }
 
@@ -539,7 +541,7 @@ extern "C" {
 
 void fccqp_default_options(fccqp_options* opt) {
   if (!opt) return;
-  opt->max_iter = 1000; opt->reserved = 0; opt->rho = 1e-6; opt->eps_fcone = 1e-3; opt->eps_bound = 1e-6;
+  opt->max_iter = 1000; opt->adapt_rho_interval = 0; opt->rho = 1e-6; opt->eps_fcone = 1e-3; opt->eps_bound = 1e-6;
   opt->relaxation = 1.0;
 }
 const char* fccqp_last_error(void) { return g_err.c_str(); }
@@ -741,6 +743,7 @@ int fccqp_solve(fccqp_handle h, const double* Q, ptrdiff_t q_rs, ptrdiff_t q_cs,
   p.B = 1; p.n = n; p.m = m; p.nc = nc; p.lcs = h->lcs;
   p.max_iter = h->opt.max_iter; p.rho = h->opt.rho; p.eps_fcone = h->opt.eps_fcone; p.eps_bound = h->opt.eps_bound;
   p.alpha = h->opt.relaxation > 0.0 ? h->opt.relaxation : 1.0;
+  p.adapt_k = h->opt.adapt_rho_interval;
   p.warm = h->warm;  // warm with no earlier Solve starts from the zero state, like the reference object
   double* d = h->d_in;
   p.Q = d; p.q_bs = 0; p.q_rs = n; p.q_cs = 1; d += (size_t)n * n;
@@ -813,6 +816,7 @@ static int fill_params(const fccqp_batch_desc& d, fccqp::SolveParams& p) {
   p.max_iter = d.options.max_iter; p.rho = d.options.rho;
   p.eps_fcone = d.options.eps_fcone; p.eps_bound = d.options.eps_bound;
   p.alpha = d.options.relaxation > 0.0 ? d.options.relaxation : 1.0;
+  p.adapt_k = d.options.adapt_rho_interval;
   p.warm = d.warm_start != 0;
   return FCCQP_OK;
 }

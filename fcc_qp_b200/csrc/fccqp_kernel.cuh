@@ -185,6 +185,7 @@ struct SolveParams {
   int first_update_identity;  // cold solves: take x-update 0 as the identity it is (see kernel), default 1
   double rho, eps_fcone, eps_bound;
   double alpha;               // over-relaxation (fccqp_options::relaxation); 1.0 = the reference's iteration
+  int adapt_k;                // adaptive rho (fccqp_options::adapt_rho_interval): rebalance every adapt_k iterations; 0 = off
   const double* Q;   long long q_bs, q_rs, q_cs;
   const double* b;   long long b_bs;
   const double* A;   long long a_bs, a_rs, a_cs;
@@ -1158,6 +1159,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
       bool full_inverse = false;   // long-running QP: x-updates through G = [K^{-1}]_xx
       double v_xbase = 0.0;        // its x_base entry of row t
       double rhs0 = 0.0;   // pass-0 right-hand side of row t
+      double rho_cur = p.rho;      // (changes only with the adaptive-rho extension, SolveParams::adapt_k)
 
 #pragma unroll 1
       for (int iter = 0; iter < iters; ++iter) {
@@ -1312,7 +1314,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
       TR(4);
 
       if (pass == 1) {
-        if (is_x) M[mat_off(t, t)] += p.rho;
+        if (is_x) M[mat_off(t, t)] += rho_cur;
       } else {
         // sigma = trace(Q) / ||A||_F^2 balances the two terms of Q + sigma A'A
         double trq = is_x ? M[mat_off(t, t)] : 0.0, fro = 0.0;
@@ -1407,7 +1409,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
         } else if (is_x) {
           // -(b + q_rho), q_rho = -rho (xbar - mu_x) with the cone segment overwritten (fcc_qp.cpp:81-83)
           const double w = in_cone ? (lcbar[t - lcs] - muc[t - lcs]) : (v_xbar - v_mux);
-          const double q_rho = -p.rho * w;
+          const double q_rho = -rho_cur * w;
           acc = -(v_b + q_rho);
         } else if (is_c) {
           acc = v_b;
@@ -1431,7 +1433,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
           // rhs_x = -b + rho w, rhs_c = b_eq  =>  x = x_base + rho G w
           const double w = is_x ? (in_cone ? (lcbar[t - lcs] - muc[t - lcs]) : (v_xbar - v_mux)) : 0.0;
           const double gw = g_apply(M, tbuf, w, NBx, n8);
-          val = is_x ? fma(p.rho, gw, v_xbase) : 0.0;
+          val = is_x ? fma(rho_cur, gw, v_xbase) : 0.0;
         } else {
           val = kkt_solve(M, dinv, tbuf, ybuf, acc, NB, NB32, N8 FCCQP_TRACE_ARGS);
         }
@@ -1456,10 +1458,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
         if (is_x) { xs[t] = val; v_x = val; }
         __syncthreads();
         double rx = 0.0, rc = 0.0;
+        double dz = 0.0;                     // |z_k - z_{k-1}| of this thread's entries (adaptive rho only)
         const bool relax = p.alpha != 1.0;   // extension: x_hat = alpha x + (1 - alpha) x_bar_prev in place of x below
         if (is_x) {
           const double xh = relax ? fma(p.alpha, val, (1.0 - p.alpha) * v_xbar) : val;
           const double xb = clampd(xh + v_mux, v_lb, v_ub);
+          dz = fabs(xb - v_xbar);
           v_xbar = xb;
           const double r = xh - xb;
           v_mux += r;
@@ -1475,6 +1479,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
           }
           double o0, o1, o2;
           project_cone3(x0 + muc[3 * t], x1 + muc[3 * t + 1], x2 + muc[3 * t + 2], vmu[t], o0, o1, o2);
+          if (p.adapt_k > 0)
+            dz = fmax(dz, fmax(fabs(o0 - lcbar[3 * t]), fmax(fabs(o1 - lcbar[3 * t + 1]), fabs(o2 - lcbar[3 * t + 2]))));
           lcbar[3 * t] = o0; lcbar[3 * t + 1] = o1; lcbar[3 * t + 2] = o2;
           const double r0 = x0 - o0, r1 = x1 - o1, r2 = x2 - o2;
           muc[3 * t] += r0; muc[3 * t + 1] += r1; muc[3 * t + 2] += r2;
@@ -1497,6 +1503,27 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
         } else if (shared_mode == 1) {
           defer = true;   // iteration 0 (the identity x-update) did not pass the exit test
           break;
+        } else if (shared_mode == 0 && p.adapt_k > 0 && (iter + 1) % p.adapt_k == 0) {
+          // Adaptive rho (extension, fccqp_options::adapt_rho_interval; restated in oracle/fccqp_oracle.c, do_admm): with
+          // scaled duals the primal residual is r_p = max(|x_hat - x_bar|, |lambda_hat - lambda_bar|), the dual one
+          // r_d = rho |z_k - z_{k-1}|; more than a factor 5 apart, rho moves by sqrt(r_p / r_d) (at most 10x), the
+          // scaled duals are rescaled so that y = rho mu stays put, and the rho-KKT matrix is assembled and factored again
+          // (the lazy-factorization block at the top of the next iteration; the operator of a long-running QP with it).
+          double rp = fmax(rx, rc), rd = dz;
+          block_reduce2<false>(rp, rd, red, parity);
+          rd *= rho_cur;
+          double ratio = sqrt(rp / (rd > 1e-300 ? rd : 1e-300));
+          ratio = fmin(fmax(ratio, 0.1), 10.0);
+          if (ratio > 5.0 || ratio < 0.2) {
+            const double rho_new = fmin(fmax(rho_cur * ratio, 1e-9), 1e9);
+            const double sc = rho_cur / rho_new;
+            v_mux *= sc;
+            if (t < nc / 3) { muc[3 * t] *= sc; muc[3 * t + 1] *= sc; muc[3 * t + 2] *= sc; }
+            rho_cur = rho_new;
+            factored = false;
+            full_inverse = false;
+            __syncthreads();
+          }
         }
       }
     }

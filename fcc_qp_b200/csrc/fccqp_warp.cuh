@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) fccqp_warp_kernel(con
       const int iters = pass == 0 ? 1 : p.max_iter;
       bool factored = false, have_g = false;
       double dinv = 0.0, rhs0 = 0.0, v_xbase = 0.0;
+      double rho_cur = p.rho;   // (changes only with the adaptive-rho extension)
 
 #pragma unroll 1
       for (int iter = 0; iter < iters; ++iter) {
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) fccqp_warp_kernel(con
             }
             __syncwarp();
             if (pass == 1) {
-              if (is_x) Krow[lane] += p.rho;
+              if (is_x) Krow[lane] += rho_cur;
             } else {
               // sigma = trace(Q) / ||A||_F^2 balances the two terms of Q + sigma A'A (fccqp_kernel.cuh, pre-solve)
               double trq = is_x ? Krow[lane] : 0.0, fro = 0.0;
@@ -215,10 +216,10 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) fccqp_warp_kernel(con
               s1 = fma(Krow[c + 1], shfl_d(w, c + 1), s1);
             }
             if (c < n) s0 = fma(Krow[c], shfl_d(w, c), s0);
-            val = is_x ? fma(p.rho, s0 + s1, v_xbase) : 0.0;
+            val = is_x ? fma(rho_cur, s0 + s1, v_xbase) : 0.0;
           } else {
             // -(b + q_rho), q_rho = -rho (xbar - mu_x) with the cone segment overwritten (fcc_qp.cpp:81-83)
-            const double acc = pass == 0 ? rhs0 : (is_x ? -(v_b - p.rho * w) : (is_c ? v_b : 0.0));
+            const double acc = pass == 0 ? rhs0 : (is_x ? -(v_b - rho_cur * w) : (is_c ? v_b : 0.0));
             val = warp_solve(K, N, ld, lane, dinv, acc);
             if (!is_x) val = 0.0;
           }
@@ -232,11 +233,12 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) fccqp_warp_kernel(con
 
         // ---- z-update, residuals, duals (fcc_qp.cpp:88-103), exit test (:105-109)
         v_x = val;
-        double rx = 0.0, rc = 0.0;
+        double rx = 0.0, rc = 0.0, dz = 0.0;
         const bool relax = p.alpha != 1.0;
         if (is_x) {
           const double xh = relax ? fma(p.alpha, val, (1.0 - p.alpha) * v_xbar) : val;
           const double xb = clampd(xh + v_mux, v_lb, v_ub);
+          dz = fabs(xb - v_xbar);
           v_xbar = xb;
           const double r = xh - xb;
           v_mux += r;
@@ -251,6 +253,7 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) fccqp_warp_kernel(con
             double o0, o1, o2;
             project_cone3(f0, f1, f2, v_fric, o0, o1, o2);
             const double o = ck == 0 ? o0 : (ck == 1 ? o1 : o2);
+            dz = fmax(dz, fabs(o - v_lcbar));
             v_lcbar = o;
             const double r = xk - o;
             v_muc += r;
@@ -262,6 +265,19 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) fccqp_warp_kernel(con
         if (conv || iter + 1 == iters) {
           res_x = warp_max(rx); res_c = warp_max(rc);
           if (conv) { n_iter = iter; break; }
+        } else if (p.adapt_k > 0 && (iter + 1) % p.adapt_k == 0) {
+          // adaptive rho (extension; see fccqp_kernel.cuh and oracle/fccqp_oracle.c, do_admm)
+          const double rp = warp_max(fmax(rx, rc)), rd = rho_cur * warp_max(dz);
+          double ratio = sqrt(rp / (rd > 1e-300 ? rd : 1e-300));
+          ratio = fmin(fmax(ratio, 0.1), 10.0);
+          if (ratio > 5.0 || ratio < 0.2) {
+            const double rho_new = fmin(fmax(rho_cur * ratio, 1e-9), 1e9);
+            const double sc = rho_cur / rho_new;
+            v_mux *= sc; v_muc *= sc;
+            rho_cur = rho_new;
+            factored = false;
+            have_g = false;
+          }
         }
       }
     }

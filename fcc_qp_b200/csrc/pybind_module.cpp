@@ -130,7 +130,8 @@ PYBIND11_MODULE(fcc_qp_solver, m) {
       .def_readwrite("rho", &FCCQPOptions::rho)
       .def_readwrite("eps_fcone", &FCCQPOptions::eps_fcone)
       .def_readwrite("eps_bound", &FCCQPOptions::eps_bound)
-      .def_readwrite("relaxation", &FCCQPOptions::relaxation);   // extension, default 1.0 = the reference
+      .def_readwrite("relaxation", &FCCQPOptions::relaxation)    // extension, default 1.0 = the reference
+      .def_readwrite("adapt_rho_interval", &FCCQPOptions::adapt_rho_interval);   // extension, default 0 = the reference's fixed rho
 
   py::class_<FCCQPSolution>(m, "FCCQPSolution")
       .def_readwrite("details", &FCCQPSolution::details)

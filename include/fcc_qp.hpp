@@ -49,6 +49,7 @@ struct FCCQPOptions {
   double eps_fcone = 1e-3;
   double eps_bound = 1e-6;
   double relaxation = 1.0;   // extension, not in the reference: ADMM over-relaxation (fccqp_options::relaxation)
+  int adapt_rho_interval = 0;  // extension, not in the reference: adaptive rho every so many iterations (0 = off)
 };
 
 // src/fcc_qp.hpp:37-40
@@ -93,7 +94,7 @@ class FCCQP {
   void set_max_iter(int n) { check(fccqp_set_max_iter(h_, n)); }
   void set_options(FCCQPOptions opt) {
     fccqp_options o;
-    o.max_iter = opt.max_iter; o.reserved = 0; o.rho = opt.rho; o.relaxation = opt.relaxation;
+    o.max_iter = opt.max_iter; o.adapt_rho_interval = opt.adapt_rho_interval; o.rho = opt.rho; o.relaxation = opt.relaxation;
     o.eps_fcone = opt.eps_fcone; o.eps_bound = opt.eps_bound;
     check(fccqp_set_options(h_, &o));
   }
@@ -242,7 +243,7 @@ class FCCQPBatch {
   void set_max_iter(int n) { if (n <= 0) throw std::invalid_argument("max_iter must be > 0"); opt_.max_iter = n; }
   void set_options(FCCQPOptions o) {
     opt_.max_iter = o.max_iter; opt_.rho = o.rho; opt_.eps_fcone = o.eps_fcone; opt_.eps_bound = o.eps_bound;
-    opt_.relaxation = o.relaxation;
+    opt_.relaxation = o.relaxation; opt_.adapt_rho_interval = o.adapt_rho_interval;
   }
   void set_warm_start(bool warm_start) { warm_ = warm_start; }
 

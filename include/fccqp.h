@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define FCCQP_ABI_VERSION 3
+#define FCCQP_ABI_VERSION 4
 
 typedef enum fccqp_error {
   FCCQP_OK = 0,
@@ -51,7 +51,15 @@ typedef enum fccqp_solve_status {
 /* FCCQPOptions, src/fcc_qp.hpp:30-35 (same defaults via fccqp_default_options). */
 typedef struct fccqp_options {
   int32_t max_iter;  /* 1000 */
-  int32_t reserved;
+  /* Extension, NOT in the reference: adaptive rho.  Every adapt_rho_interval ADMM iterations the
+   * primal residual r_p = max(|x_hat - x_bar|, |lambda_hat - lambda_bar|) and the dual residual r_d = rho |z_k - z_{k-1}|
+   * (infinity norms, scaled duals) are compared; when they are more than a factor 5 apart, rho moves by sqrt(r_p / r_d)
+   * (at most 10x per update, kept inside [1e-9, 1e9]), the scaled duals are rescaled so that y = rho mu stays put, and the
+   * rho-KKT matrix is factored again.  0 (the default) = off = the reference's fixed rho.  Measured with interval 5 on the
+   * walking log: QPs ending at max_iter 1.29 % -> 0, mean iterations of the QPs that iterate 66 -> 18; multi-contact
+   * humanoid set 16.8 % -> 3.1 %.  QPs of a batch with this option run on the general / warp kernels (not the reduced
+   * one); shared-structure batches ignore it.  (This field was `reserved`, always 0, up to ABI version 3.) */
+  int32_t adapt_rho_interval; /* 0 */
   double rho;        /* 1e-6 */
   double eps_fcone;  /* 1e-3 */
   double eps_bound;  /* 1e-6 */

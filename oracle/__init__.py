@@ -92,6 +92,7 @@ class Oracle:
             self.lib.fccqp_oracle_project_cone3.argtypes = [_dp, C.c_double, _dp]
             self.lib.fccqp_oracle_set_relaxation.argtypes = [C.c_double]
             self.lib.fccqp_oracle_set_trace.argtypes = [C.c_void_p, _dp, C.c_int]
+            self.lib.fccqp_oracle_set_adaptive_rho.argtypes = [C.c_int]
             self.lib.fccqp_oracle_cone_violation.restype = C.c_double
             self.lib.fccqp_oracle_cone_violation.argtypes = [_dp, C.c_int, _dp]
             self.lib.fccqp_oracle_bound_violation.restype = C.c_double
@@ -105,6 +106,12 @@ class Oracle:
         Process-wide; reset to 1.0 (the reference's iteration) when done."""
         assert self.kind == "port"
         self.lib.fccqp_oracle_set_relaxation(float(alpha))
+
+    def set_adaptive_rho(self, interval: int) -> None:
+        """Adaptive rho of the C restatement (port only; checks the product's opt-in extension).  Process-wide;
+        reset to 0 (the reference's fixed rho) when done."""
+        assert self.kind == "port"
+        self.lib.fccqp_oracle_set_adaptive_rho(int(interval))
 
     def hardware_threads(self) -> int:
         return int(self.fn("hardware_threads")())

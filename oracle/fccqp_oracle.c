@@ -440,6 +440,10 @@ static double inf_norm_like_reference(const double* v, int len) {
 /* process-wide over-relaxation of the restatement (tests of the product's extension only; default 1 = reference) */
 static double g_relaxation = 1.0;
 void fccqp_oracle_set_relaxation(double alpha) { g_relaxation = alpha; }
+/* Extension of the product (fccqp_options::adapt_rho_interval), NOT in the reference: every `interval` ADMM iterations
+ * rho is rebalanced from the primal / dual residual ratio (0 = off = the reference's fixed rho).  Process-wide. */
+static int g_adapt_interval = 0;
+void fccqp_oracle_set_adaptive_rho(int interval) { g_adapt_interval = interval; }
 /* residual history of the following solves goes to buf[2 * cap] (NULL: off); caller-owned */
 void fccqp_oracle_set_trace(fccqp_oracle* o, double* buf, int cap) { o->trace = buf; o->trace_cap = cap; }
 
@@ -458,10 +462,17 @@ static void do_admm(fccqp_oracle* o, const double* b, const double* mu, const do
   memcpy(o->lambda_c_bar, o->x + lcs, sizeof(double) * (size_t)nc);
 
   o->n_iter = o->max_iter;
+  double rho = o->rho;                       /* (changes only with the adaptive-rho extension) */
+  double* const xbar_prev = o->tmpN2;        /* [N >= n]: x_bar of the previous iteration */
+  double* const lcbar_prev = (double*)malloc(sizeof(double) * (size_t)(nc ? nc : 1));
   for (int iter = 0; iter < o->max_iter; ++iter) {
-    for (int i = 0; i < n; ++i) o->q_rho[i] = -o->rho * (o->x_bar[i] - o->mu_x[i]);
+    for (int i = 0; i < n; ++i) o->q_rho[i] = -rho * (o->x_bar[i] - o->mu_x[i]);
     for (int i = 0; i < nc; ++i)
-      o->q_rho[lcs + i] = -o->rho * (o->lambda_c_bar[i] - o->mu_lambda_c[i]);
+      o->q_rho[lcs + i] = -rho * (o->lambda_c_bar[i] - o->mu_lambda_c[i]);
+    if (g_adapt_interval > 0) {
+      memcpy(xbar_prev, o->x_bar, sizeof(double) * (size_t)n);
+      memcpy(lcbar_prev, o->lambda_c_bar, sizeof(double) * (size_t)nc);
+    }
     for (int i = 0; i < n; ++i) o->b_kkt[i] = -(b[i] + o->q_rho[i]);
 
     ldlt_solve(N, o->ldlt, o->tr, o->b_kkt, o->kkt_sol);
@@ -510,7 +521,35 @@ static void do_admm(fccqp_oracle* o, const double* b, const double* mu, const do
       o->n_iter = iter;
       break;
     }
+    /* Adaptive rho (extension; include/fccqp.h, fccqp_options::adapt_rho_interval): with scaled duals mu = y / rho the
+     * primal residual is r_p = max(|x_hat - x_bar|, |lambda_hat - lambda_bar|) and the dual one r_d = rho |z_k - z_{k-1}|;
+     * when they are more than a factor 5 apart rho moves by sqrt(r_p / r_d) (at most 10x per update), the scaled duals
+     * are rescaled so that y stays put, and the rho-KKT matrix is factored again. */
+    if (g_adapt_interval > 0 && (iter + 1) % g_adapt_interval == 0 && iter + 1 < o->max_iter) {
+      double dz = 0.0;
+      for (int i = 0; i < n; ++i) { const double d = fabs(o->x_bar[i] - xbar_prev[i]); if (d > dz) dz = d; }
+      for (int i = 0; i < nc; ++i) { const double d = fabs(o->lambda_c_bar[i] - lcbar_prev[i]); if (d > dz) dz = d; }
+      const double rp = o->x_res_norm > o->lambda_c_res_norm ? o->x_res_norm : o->lambda_c_res_norm;
+      const double rd = rho * dz;
+      double ratio = sqrt(rp / (rd > 1e-300 ? rd : 1e-300));
+      if (ratio > 10.0) ratio = 10.0;
+      if (ratio < 0.1) ratio = 0.1;
+      if (ratio > 5.0 || ratio < 0.2) {
+        double rho_new = rho * ratio;
+        if (rho_new > 1e9) rho_new = 1e9;
+        if (rho_new < 1e-9) rho_new = 1e-9;
+        const double sc = rho / rho_new;
+        for (int i = 0; i < n; ++i) o->mu_x[i] *= sc;
+        for (int i = 0; i < nc; ++i) o->mu_lambda_c[i] *= sc;
+        rho = rho_new;
+        memcpy(o->M_kkt, o->M_kkt_pre, sizeof(double) * (size_t)N * N);
+        for (int i = 0; i < n; ++i) AT(o->M_kkt, N, i, i) += rho;
+        memcpy(o->ldlt, o->M_kkt, sizeof(double) * (size_t)N * N);
+        ldlt_compute(N, o->ldlt, o->tr, o->tmpN);
+      }
+    }
   }
+  free(lcbar_prev);
 }
 
 /* fcc_qp.cpp:114-191 */

@@ -62,6 +62,8 @@ void fccqp_oracle_set_trace(fccqp_oracle* o, double* buf, int cap);
 
 /* Extension used only to check the product's opt-in over-relaxation (include/fccqp.h); 1.0 = the reference. */
 void fccqp_oracle_set_relaxation(double alpha);
+/* Same for the product's opt-in adaptive rho (fccqp_options::adapt_rho_interval); 0 = off = the reference. */
+void fccqp_oracle_set_adaptive_rho(int interval);
 
 #ifdef __cplusplus
 }
