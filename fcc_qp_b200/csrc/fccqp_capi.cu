@@ -354,8 +354,7 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool
   StructHint hint;
   if (hint_in) hint = *hint_in;
   static const bool dev_instr = getenv("FCCQP_TRACE") != nullptr;
-  // (adaptive rho lives in the general and warp kernels only)
-  if (!no_struct_env && !dev_instr && !f32 && p.adapt_k == 0 && hint.mode != FCCQP_STRUCTURE_DENSE && p.n <= 256 && p.m <= 256 && p.m > 0) {
+  if (!no_struct_env && !dev_instr && !f32 && hint.mode != FCCQP_STRUCTURE_DENSE && p.n <= 256 && p.m <= 256 && p.m > 0) {
     int caps[3] = {hint.caps[0], hint.caps[1], hint.caps[2]};
     bool ok = true;
     if (hint.mode != FCCQP_STRUCTURE_CAPS) {

@@ -913,7 +913,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
         n_iter = p.max_iter;
       }
       const int iters = pass == 0 ? 1 : p.max_iter;
-      const double shift = pass == 0 ? 0.0 : p.rho;
+      double shift = pass == 0 ? 0.0 : p.rho;   // (rho of pass 1 changes only with the adaptive-rho extension)
       // In the ADMM pass the zero-cost variables have h = rho > 0 like everybody else: they are eliminated too
       // (keeping them as a trailing block with a rho-sized pivot costs three digits; tools/proto), so the
       // reduced system of pass 1 is [R, constraints] only.
@@ -928,7 +928,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
       Se.N8 = S.nr8 + m8 + ((Se.nd0 + 7) & ~7);
       Se.NB = Se.N8 >> 3;
       Se.NB32 = (Se.N8 + 31) >> 5;
-      const double hi = (ve.type == VT_DP || ve.type == VT_D1) ? 1.0 / (ve.qd + shift) : 0.0;
+      double hi = (ve.type == VT_DP || ve.type == VT_D1) ? 1.0 / (ve.qd + shift) : 0.0;
       bool factored = false;
       bool full_inverse = false;
       bool full_op = false;          // the full-space operator F sits in M (build_full_op)
@@ -1088,12 +1088,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
           for (int rep = make_op ? 0 : 1; rep < 2; ++rep) {
             const bool base_solve = rep == 0;
             if (!base_solve && full_op) {
-              val = full_op_apply(M, smem + L.off_tbuf, smem + L.off_ybuf, smem + L.off_sred, ci, p.rho * w, NBF, NF);
+              val = full_op_apply(M, smem + L.off_tbuf, smem + L.off_ybuf, smem + L.off_sred, ci, shift * w, NBF, NF);
               break;
             }
             const bool op = !base_solve && full_inverse;
             double r = 0.0;
-            if (is_x) r = (base_solve || pass == 0) ? -v_b : (op ? p.rho * w : -(v_b - p.rho * w));
+            if (is_x) r = (base_solve || pass == 0) ? -v_b : (op ? shift * w : -(v_b - shift * w));
 #ifdef FCCQP_DEV
             const double res = struct_xsolve<kThreads>(p, L, smem, I, Se, ve, Qg, Ag, q_slow, q_fast, r, hi, shift, op, op,
                                                        pass == 0 && p.struct_refine != 0, q_vec && a_vec, s_prof, t_prof);
@@ -1155,11 +1155,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
         // ---- K4 + K5 (identical to the general kernel)
         if (is_x) { xs[t] = val; v_x = val; }
         __syncthreads();
-        double rx = 0.0, rc = 0.0;
+        double rx = 0.0, rc = 0.0, dz = 0.0;
         const bool relax = p.alpha != 1.0;
         if (is_x) {
           const double xh = relax ? fma(p.alpha, val, (1.0 - p.alpha) * v_xbar) : val;
           const double xb = clampd(xh + v_mux, v_lb, v_ub);
+          dz = fabs(xb - v_xbar);
           v_xbar = xb;
           const double rr = xh - xb;
           v_mux += rr;
@@ -1175,6 +1176,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
           }
           double o0, o1, o2;
           project_cone3(x0 + muc[3 * t], x1 + muc[3 * t + 1], x2 + muc[3 * t + 2], vmu[t], o0, o1, o2);
+          if (p.adapt_k > 0)
+            dz = fmax(dz, fmax(fabs(o0 - lcbar[3 * t]), fmax(fabs(o1 - lcbar[3 * t + 1]), fabs(o2 - lcbar[3 * t + 2]))));
           lcbar[3 * t] = o0; lcbar[3 * t + 1] = o1; lcbar[3 * t + 2] = o2;
           const double r0 = x0 - o0, r1 = x1 - o1, r2 = x2 - o2;
           muc[3 * t] += r0; muc[3 * t + 1] += r1; muc[3 * t + 2] += r2;
@@ -1186,6 +1189,25 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
           block_reduce2<false>(rx, rc, red, parity);
           res_x = rx; res_c = rc;
           if (conv) { n_iter = iter; SPROF(8); break; }
+        } else if (p.adapt_k > 0 && (iter + 1) % p.adapt_k == 0) {
+          // adaptive rho (extension; fccqp_kernel.cuh, oracle/fccqp_oracle.c do_admm): rebalance, rescale the scaled duals,
+          // and have the reduced rho-KKT system (h = q + rho of every eliminated variable included) assembled and
+          // factored again at the top of the next iteration
+          double rp = fmax(rx, rc), rd = dz;
+          block_reduce2<false>(rp, rd, red, parity);
+          rd *= shift;
+          double ratio = sqrt(rp / (rd > 1e-300 ? rd : 1e-300));
+          ratio = fmin(fmax(ratio, 0.1), 10.0);
+          if (ratio > 5.0 || ratio < 0.2) {
+            const double rho_new = fmin(fmax(shift * ratio, 1e-9), 1e9);
+            const double sc = shift / rho_new;
+            v_mux *= sc;
+            if (t < nc / 3) { muc[3 * t] *= sc; muc[3 * t + 1] *= sc; muc[3 * t + 2] *= sc; }
+            shift = rho_new;
+            hi = (ve.type == VT_DP || ve.type == VT_D1) ? 1.0 / (ve.qd + shift) : 0.0;
+            factored = false; full_inverse = false; full_op = false;
+            __syncthreads();
+          }
         }
         SPROF(8);
       }

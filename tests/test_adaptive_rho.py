@@ -46,8 +46,8 @@ def test_option_default_and_validation():
 @pytest.mark.gpu
 @pytest.mark.parametrize("interval", [5, 10])
 def test_gpu_matches_adaptive_oracle(port, walking_log, interval):
-    """General kernel (the log, humanoid and multi-contact shapes: a batch with this option does not take the reduced
-    kernel) and warp kernel (a small shape) against the restatement with the same option."""
+    """Reduced kernel (the log, humanoid and multi-contact shapes), general kernel (the same with structure="dense") and
+    warp kernel (a small shape) against the restatement with the same option."""
     import sys, os
     sys.path.insert(0, os.path.dirname(__file__))
     from test_gpu_random_shapes import random_qps
@@ -60,18 +60,20 @@ def test_gpu_matches_adaptive_oracle(port, walking_log, interval):
                      (syn.make_batch(syn.MULTICONTACT, 48), LOG_OPTS),
                      (small, dict(max_iter=200, rho=1e-3, eps_fcone=1e-7, eps_bound=1e-7))):
         ref = port.solve_batch(qp, warm_mode=0, nthreads=8, **opts)
-        s = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start)
-        s.set_options(FCCQPOptionsB(adapt_rho_interval=interval, **opts))
-        s.Solve(qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)
-        sol = s.GetSolution()
-        assert not nat.last_struct_info()["used"]
-        err = np.abs(sol.z - ref["z"]).max(1) / np.maximum(1.0, np.abs(ref["z"]).max(1))
-        same = sol.details.n_iter == ref["n_iter"]
-        # (a rebalancing decision sits on a threshold too -- ratio 5 -- so a few more lanes may part ways than without it)
-        assert (~same).mean() <= 0.03, ((~same).sum(), qp.n)
-        assert err[same].max() <= 1e-6, qp.n
-        assert np.array_equal(sol.details.solve_status[same], ref["status"][same])
-        adapted += int((ref["n_iter"] >= interval).sum())
+        for structure in (("auto", "dense") if qp.n > 32 else ("auto",)):
+            s = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start)
+            s.structure = structure
+            s.set_options(FCCQPOptionsB(adapt_rho_interval=interval, **opts))
+            s.Solve(qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)
+            sol = s.GetSolution()
+            assert nat.last_struct_info()["used"] == (structure == "auto" and qp.n > 32)
+            err = np.abs(sol.z - ref["z"]).max(1) / np.maximum(1.0, np.abs(ref["z"]).max(1))
+            same = sol.details.n_iter == ref["n_iter"]
+            # (a rebalancing decision sits on a threshold too -- ratio 5 -- so a few more lanes may part ways than without it)
+            assert (~same).mean() <= 0.03, ((~same).sum(), qp.n)
+            assert err[same].max() <= 1e-6, qp.n
+            assert np.array_equal(sol.details.solve_status[same], ref["status"][same])
+            adapted += int((ref["n_iter"] >= interval).sum())
     assert adapted > 0
 
 

@@ -13,7 +13,8 @@ if shape == "odd":   # odd n, no 16-byte row alignment: the 8-byte / 4-byte stag
     qp = random_qps(np.random.default_rng(3), 24, 13, 6, 6, 5)
 else:
     qp = load_walking_log().take(np.arange(0, 2019, 48)) if shape == "walking" else syn.make_batch(syn.SHAPES[shape], 24)
-s = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start); s.set_options(FCCQPOptionsB(100, 5e-5, 1e-6, 1e-6))
+ADAPT = int(os.environ.get("SAN_ADAPT", "0"))   # adaptive rho: general / warp kernels with refactorizations
+s = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start); s.set_options(FCCQPOptionsB(100, 5e-5, 1e-6, 1e-6, 1.0, ADAPT))
 s.Solve(qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)
 it = s.GetSolution().details.n_iter
 s.set_warm_start(True)
