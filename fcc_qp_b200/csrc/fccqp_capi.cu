@@ -125,7 +125,7 @@ using KernelFn = void (*)(const fccqp::SolveParams);
 
 // Chooses the template instance (threads >= n + m; CTAs/SM hint from the packed-matrix footprint).
 int pick_kernel(const DeviceCtx& ctx, int n, int m, int nc, KernelFn* fn, int* threads, size_t* smem,
-                KernelFn* fn_shared = nullptr, KernelFn* fn_f32 = nullptr) {
+                KernelFn* fn_shared = nullptr, KernelFn* fn_f32 = nullptr, bool adapt = false) {
   const int N = n + m;
   if (N < 1) return fail(FCCQP_E_INVALID, "n + m must be >= 1");
   fccqp::Layout l(n, m, nc);
@@ -137,25 +137,26 @@ int pick_kernel(const DeviceCtx& ctx, int n, int m, int nc, KernelFn* fn, int* t
   // one thread per padded KKT row; 4 CTAs/SM for the <= 128-row shapes (Cassie, quadruped)
   if (l.N8 <= 128) {
     *threads = 128;
-    *fn = (KernelFn)fccqp::fccqp_solve_kernel<128, 4, false, false>;
+    *fn = adapt ? (KernelFn)fccqp::fccqp_solve_kernel<128, 4, false, false, true> : (KernelFn)fccqp::fccqp_solve_kernel<128, 4, false, false>;
     if (fn_shared) *fn_shared = (KernelFn)fccqp::fccqp_solve_kernel<128, 4, true, false>;
-    if (fn_f32) *fn_f32 = (KernelFn)fccqp::fccqp_solve_kernel<128, 4, false, true>;
+    if (fn_f32) *fn_f32 = adapt ? (KernelFn)fccqp::fccqp_solve_kernel<128, 4, false, true, true> : (KernelFn)fccqp::fccqp_solve_kernel<128, 4, false, true>;
   } else {
     *threads = 256;
-    *fn = (KernelFn)fccqp::fccqp_solve_kernel<256, 2, false, false>;
+    *fn = adapt ? (KernelFn)fccqp::fccqp_solve_kernel<256, 2, false, false, true> : (KernelFn)fccqp::fccqp_solve_kernel<256, 2, false, false>;
     if (fn_shared) *fn_shared = (KernelFn)fccqp::fccqp_solve_kernel<256, 2, true, false>;
-    if (fn_f32) *fn_f32 = (KernelFn)fccqp::fccqp_solve_kernel<256, 2, false, true>;
+    if (fn_f32) *fn_f32 = adapt ? (KernelFn)fccqp::fccqp_solve_kernel<256, 2, false, true, true> : (KernelFn)fccqp::fccqp_solve_kernel<256, 2, false, true>;
   }
   return FCCQP_OK;
 }
 
 // Structure-exploiting kernel instances (fccqp_struct.cuh): threads >= max(n, padded reduced KKT size).
-int pick_struct_kernel(const fccqp::StructLayout& sl, int n, KernelFn* fn, int* threads) {
+int pick_struct_kernel(const fccqp::StructLayout& sl, int n, KernelFn* fn, int* threads, bool adapt) {
   const int need = n > sl.N8c ? n : sl.N8c;
-  if (need <= 64) { *threads = 64; *fn = (KernelFn)fccqp::fccqp_struct_kernel<64, 8>; }
-  else if (need <= 96) { *threads = 96; *fn = (KernelFn)fccqp::fccqp_struct_kernel<96, 5>; }
-  else if (need <= 128) { *threads = 128; *fn = (KernelFn)fccqp::fccqp_struct_kernel<128, 4>; }
-  else if (need <= 256) { *threads = 256; *fn = (KernelFn)fccqp::fccqp_struct_kernel<256, 2>; }
+  using namespace fccqp;
+  if (need <= 64) { *threads = 64; *fn = adapt ? (KernelFn)fccqp_struct_kernel<64, 8, true> : (KernelFn)fccqp_struct_kernel<64, 8, false>; }
+  else if (need <= 96) { *threads = 96; *fn = adapt ? (KernelFn)fccqp_struct_kernel<96, 5, true> : (KernelFn)fccqp_struct_kernel<96, 5, false>; }
+  else if (need <= 128) { *threads = 128; *fn = adapt ? (KernelFn)fccqp_struct_kernel<128, 4, true> : (KernelFn)fccqp_struct_kernel<128, 4, false>; }
+  else if (need <= 256) { *threads = 256; *fn = adapt ? (KernelFn)fccqp_struct_kernel<256, 2, true> : (KernelFn)fccqp_struct_kernel<256, 2, false>; }
   else return 1;
   return 0;
 }
@@ -235,7 +236,7 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool
                  const StructHint* hint_in = nullptr) {
   if (p.B == 0) return FCCQP_OK;
   KernelFn fn, fn_shared, fn_f32; int threads; size_t smem;
-  int rc = pick_kernel(ctx, p.n, p.m, p.nc, &fn, &threads, &smem, &fn_shared, &fn_f32);
+  int rc = pick_kernel(ctx, p.n, p.m, p.nc, &fn, &threads, &smem, &fn_shared, &fn_f32, p.adapt_k > 0);
   if (rc) return rc;
   const bool f32 = in_f32;
   if (f32) fn = fn_f32;   // float32 problem data: same launch geometry, widening stage-in
@@ -379,7 +380,7 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool
       fccqp::StructLayout sl(p.n, p.m, p.nc, caps[0], caps[1] + caps[2], caps[2]);   // D+ store: pass 1 eliminates D0 too
       KernelFn sfn = nullptr; int sthreads = 0;
       // worth it when at least one tile row of the KKT matrix goes away
-      if (sl.N8c + 8 <= p.lay.N8 && sl.bytes() <= (size_t)ctx.max_smem_optin && pick_struct_kernel(sl, p.n, &sfn, &sthreads) == 0) {
+      if (sl.N8c + 8 <= p.lay.N8 && sl.bytes() <= (size_t)ctx.max_smem_optin && pick_struct_kernel(sl, p.n, &sfn, &sthreads, p.adapt_k > 0) == 0) {
         int sctas = 0;
         if ((rc = occupancy_of(sfn, sthreads, sl.bytes(), &sctas))) return rc;
         if (cta_cap > 0 && cta_cap < sctas) sctas = cta_cap;

@@ -1018,8 +1018,9 @@ __device__ __noinline__ double g_apply(const double* __restrict__ M, double* __r
 // triangular solves and all vector work).  Warp 0 is the factorization's critical-path warp,
 // warps 1.. are its helpers.
 // ---------------------------------------------------------------------------
-template <int kThreads, int kMinBlocks, bool kShared, bool kF32>
+template <int kThreads, int kMinBlocks, bool kShared, bool kF32, bool kAdapt = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const SolveParams p) {
+  // kAdapt: the adaptive-rho extension compiled in (separate instances: the default path carries none of it)
   // kF32: the problem data (Q, b, A_eq, b_eq, friction_coeffs, lb, ub) are float32 arrays (same element
   // strides); they are widened on the way into shared memory / registers, everything else is FP64.
   // kShared = false compiles the shared-structure logic out of the general kernel
@@ -1463,7 +1464,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
         if (is_x) {
           const double xh = relax ? fma(p.alpha, val, (1.0 - p.alpha) * v_xbar) : val;
           const double xb = clampd(xh + v_mux, v_lb, v_ub);
-          dz = fabs(xb - v_xbar);
+          if (kAdapt) dz = fabs(xb - v_xbar);
           v_xbar = xb;
           const double r = xh - xb;
           v_mux += r;
@@ -1479,7 +1480,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
           }
           double o0, o1, o2;
           project_cone3(x0 + muc[3 * t], x1 + muc[3 * t + 1], x2 + muc[3 * t + 2], vmu[t], o0, o1, o2);
-          if (p.adapt_k > 0)
+          if (kAdapt)
             dz = fmax(dz, fmax(fabs(o0 - lcbar[3 * t]), fmax(fabs(o1 - lcbar[3 * t + 1]), fabs(o2 - lcbar[3 * t + 2]))));
           lcbar[3 * t] = o0; lcbar[3 * t + 1] = o1; lcbar[3 * t + 2] = o2;
           const double r0 = x0 - o0, r1 = x1 - o1, r2 = x2 - o2;
@@ -1503,7 +1504,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
         } else if (shared_mode == 1) {
           defer = true;   // iteration 0 (the identity x-update) did not pass the exit test
           break;
-        } else if (shared_mode == 0 && p.adapt_k > 0 && (iter + 1) % p.adapt_k == 0) {
+        } else if (kAdapt && shared_mode == 0 && p.adapt_k > 0 && (iter + 1) % p.adapt_k == 0) {
           // Adaptive rho (extension, fccqp_options::adapt_rho_interval; restated in oracle/fccqp_oracle.c, do_admm): with
           // scaled duals the primal residual is r_p = max(|x_hat - x_bar|, |lambda_hat - lambda_bar|), the dual one
           // r_d = rho |z_k - z_{k-1}|; more than a factor 5 apart, rho moves by sqrt(r_p / r_d) (at most 10x), the

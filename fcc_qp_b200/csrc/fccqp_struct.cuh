@@ -677,6 +677,9 @@ __device__ __noinline__ void build_full_op(double* __restrict__ M, const double*
   }
   __syncthreads();
   // ---- Z = G_yy B (G_yy symmetric, lower tiles of M at tile rows / columns NBr..) and X = -B' G_yR
+  // The B / Z operands come from the global scratch slab (L2 hits, ~700 cycles each): every contraction loop below
+  // loads the operands of kU steps first and multiplies afterwards, so a tile costs ceil(mt / kU) round trips, not mt.
+  constexpr int kU = 4;
   const int nz = d.mt * d.neT, nx = d.neT * d.NBr;
 #pragma unroll 1
   for (int w = warp; w < nz + nx; w += kWarps) {
@@ -684,23 +687,45 @@ __device__ __noinline__ void build_full_op(double* __restrict__ M, const double*
     if (w < nz) {
       const int K = w / d.neT, E = w - K * d.neT;
 #pragma unroll 1
-      for (int K2 = 0; K2 < d.mt; ++K2) {
-        const double* bt = Bs + (size_t)(K2 * d.neT + E) * 64 + fragT;
-        double2 a;
-        if (K >= K2) a = ld2(M + tile_off(d.NBr + K, d.NBr + K2) + fragC);
-        else { const double* gt = M + tile_off(d.NBr + K2, d.NBr + K) + fragT; a = make_double2(gt[0], gt[8]); }
-        dmma(ca.x, ca.y, a.x, bt[0]);
-        dmma(cb.x, cb.y, a.y, bt[8]);
+      for (int K0 = 0; K0 < d.mt; K0 += kU) {
+        double b0[kU], b1[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const double* bt = Bs + (size_t)(min(K0 + u, d.mt - 1) * d.neT + E) * 64 + fragT;
+          b0[u] = bt[0]; b1[u] = bt[8];
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int K2 = K0 + u;
+          if (K2 < d.mt) {
+            double2 a;
+            if (K >= K2) a = ld2(M + tile_off(d.NBr + K, d.NBr + K2) + fragC);
+            else { const double* gt = M + tile_off(d.NBr + K2, d.NBr + K) + fragT; a = make_double2(gt[0], gt[8]); }
+            dmma(ca.x, ca.y, a.x, b0[u]);
+            dmma(cb.x, cb.y, a.y, b1[u]);
+          }
+        }
       }
       st2(Zs + (size_t)w * 64 + fragC, make_double2(ca.x + cb.x, ca.y + cb.y));
     } else {
       const int wi = w - nz, E = wi / d.NBr, J = wi - E * d.NBr;
 #pragma unroll 1
-      for (int K = 0; K < d.mt; ++K) {
-        const double* at = Bs + (size_t)(K * d.neT + E) * 64 + fragT;
-        const double* gt = M + tile_off(d.NBr + K, J) + fragT;
-        dmma(ca.x, ca.y, at[0], gt[0]);
-        dmma(cb.x, cb.y, at[8], gt[8]);
+      for (int K0 = 0; K0 < d.mt; K0 += kU) {
+        double a0[kU], a1[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const double* at = Bs + (size_t)(min(K0 + u, d.mt - 1) * d.neT + E) * 64 + fragT;
+          a0[u] = at[0]; a1[u] = at[8];
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int K = K0 + u;
+          if (K < d.mt) {
+            const double* gt = M + tile_off(d.NBr + K, J) + fragT;
+            dmma(ca.x, ca.y, a0[u], gt[0]);
+            dmma(cb.x, cb.y, a1[u], gt[8]);
+          }
+        }
       }
       st2(Xs + (size_t)wi * 64 + fragC, make_double2(-(ca.x + cb.x), -(ca.y + cb.y)));
     }
@@ -715,11 +740,21 @@ __device__ __noinline__ void build_full_op(double* __restrict__ M, const double*
     const int E2 = w - ((E * (E + 1)) >> 1);
     double2 ca = make_double2(0.0, 0.0), cb = make_double2(0.0, 0.0);
 #pragma unroll 1
-    for (int K = 0; K < d.mt; ++K) {
-      const double* at = Bs + (size_t)(K * d.neT + E) * 64 + fragT;
-      const double* zt = Zs + (size_t)(K * d.neT + E2) * 64 + fragT;
-      dmma(ca.x, ca.y, at[0], zt[0]);
-      dmma(cb.x, cb.y, at[8], zt[8]);
+    for (int K0 = 0; K0 < d.mt; K0 += kU) {
+      double a0[kU], a1[kU], z0[kU], z1[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int K = min(K0 + u, d.mt - 1);
+        const double* at = Bs + (size_t)(K * d.neT + E) * 64 + fragT;
+        const double* zt = Zs + (size_t)(K * d.neT + E2) * 64 + fragT;
+        a0[u] = at[0]; a1[u] = at[8]; z0[u] = zt[0]; z1[u] = zt[8];
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u)
+        if (K0 + u < d.mt) {
+          dmma(ca.x, ca.y, a0[u], z0[u]);
+          dmma(cb.x, cb.y, a1[u], z1[u]);
+        }
     }
     double2 y = make_double2(ca.x + cb.x, ca.y + cb.y);
     if (E == E2) {   // element (fr, 2 fq) and (fr, 2 fq + 1) of the tile
@@ -736,6 +771,7 @@ __device__ __noinline__ void build_full_op(double* __restrict__ M, const double*
     double* dst = M + tile_off(I, 0);
     const double* sx = Xs + (size_t)E * d.NBr * 64;
     const double* sy = Ys + (size_t)((E * (E + 1)) >> 1) * 64;
+#pragma unroll 4
     for (int e = tid; e < (I + 1) * 32; e += kThreads) {
       const int j2 = e - d.NBr * 32;
       st2(dst + 2 * e, j2 < 0 ? ld2(sx + 2 * e) : ld2(sy + 2 * j2));
@@ -790,7 +826,8 @@ __device__ __noinline__ double full_op_apply(const double* __restrict__ M, doubl
 #define SPROF(slot) do { } while (0)
 #endif
 
-template <int kThreads, int kMinBlocks>
+// kAdapt: the adaptive-rho extension compiled in (a separate instance: the default path carries none of it)
+template <int kThreads, int kMinBlocks, bool kAdapt>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(const SolveParams p) {
   extern __shared__ __align__(16) double smem[];
   const StructLayout& L = p.slay;
@@ -1160,7 +1197,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
         if (is_x) {
           const double xh = relax ? fma(p.alpha, val, (1.0 - p.alpha) * v_xbar) : val;
           const double xb = clampd(xh + v_mux, v_lb, v_ub);
-          dz = fabs(xb - v_xbar);
+          if (kAdapt) dz = fabs(xb - v_xbar);
           v_xbar = xb;
           const double rr = xh - xb;
           v_mux += rr;
@@ -1176,7 +1213,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
           }
           double o0, o1, o2;
           project_cone3(x0 + muc[3 * t], x1 + muc[3 * t + 1], x2 + muc[3 * t + 2], vmu[t], o0, o1, o2);
-          if (p.adapt_k > 0)
+          if (kAdapt)
             dz = fmax(dz, fmax(fabs(o0 - lcbar[3 * t]), fmax(fabs(o1 - lcbar[3 * t + 1]), fabs(o2 - lcbar[3 * t + 2]))));
           lcbar[3 * t] = o0; lcbar[3 * t + 1] = o1; lcbar[3 * t + 2] = o2;
           const double r0 = x0 - o0, r1 = x1 - o1, r2 = x2 - o2;
@@ -1189,7 +1226,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
           block_reduce2<false>(rx, rc, red, parity);
           res_x = rx; res_c = rc;
           if (conv) { n_iter = iter; SPROF(8); break; }
-        } else if (p.adapt_k > 0 && (iter + 1) % p.adapt_k == 0) {
+        } else if (kAdapt && p.adapt_k > 0 && (iter + 1) % p.adapt_k == 0) {
           // adaptive rho (extension; fccqp_kernel.cuh, oracle/fccqp_oracle.c do_admm): rebalance, rescale the scaled duals,
           // and have the reduced rho-KKT system (h = q + rho of every eliminated variable included) assembled and
           // factored again at the top of the next iteration
