@@ -198,6 +198,48 @@ def shape_extras(dev):
             del args, s
         except Exception as e:  # pragma: no cover
             out[name] = {"error": repr(e)}
+    # small QPs: the warp-per-QP kernel (n + m <= 32; fccqp_warp.cuh), random well-conditioned QPs at the settings of
+    # fccqp.pdf Table 1 (max_iter 15, eps 1e-4); the generator is the parity tests' own
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from test_gpu_random_shapes import random_qps
+        small = {}
+        for (sn, sm, snc, slcs) in ((12, 6, 6, 3), (24, 8, 6, 0)):
+            base = random_qps(np.random.default_rng(sn), 4096, sn, sm, snc, slcs)
+            B = 1 << 18
+            args = device_batch(base, B)
+            s = FCCQPBatch(sn, sm, snc, slcs, device=dev.index)
+            s.set_options(FCCQPOptionsB(max_iter=15, rho=1e-3, eps_fcone=1e-4, eps_bound=1e-4))
+            best = 1e9
+            for _ in range(3):
+                s.Solve(*args); torch.cuda.synchronize(dev)
+                best = min(best, s.GetSolution().details.device_time)
+            it = s.GetSolution().details.n_iter.cpu().numpy()
+            small[f"n{sn}_m{sm}"] = {"n": sn, "m": sm, "nc": snc, "batch": B, "ms": 1e3 * best, "qps": B / best,
+                                     "mean_iterations": float(it.mean()), "launch": nat.last_launch_info()}
+            del args, s
+        out["small_qps_warp_kernel"] = small
+    except Exception as e:  # pragma: no cover
+        out["small_qps_warp_kernel"] = {"error": repr(e)}
+    # opt-in adaptive rho (fccqp_options::adapt_rho_interval = 5; NOT the reference's iteration) on the headline workload
+    try:
+        log = load_walking_log()
+        qp = log.take(np.arange(1 << 16) % log.batch)
+        args = [torch.as_tensor(a, device=dev) for a in (qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)]
+        s = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start, device=dev.index)
+        s.set_options(FCCQPOptionsB(adapt_rho_interval=5, **OPTS))
+        best = 1e9
+        for _ in range(3):
+            s.Solve(*args); torch.cuda.synchronize(dev)
+            best = min(best, s.GetSolution().details.device_time)
+        it = s.GetSolution().details.n_iter.cpu().numpy()
+        out["walking_log_adaptive_rho_5"] = {"batch": 1 << 16, "ms": 1e3 * best, "qps": (1 << 16) / best,
+                                             "max_iter_fraction": float((it == OPTS["max_iter"]).mean()),
+                                             "mean_iterations_of_iterating": float(it[it > 0].mean()),
+                                             "note": "extension, changes the iterates: not comparable with the reference's counts"}
+        del args, s, qp
+    except Exception as e:  # pragma: no cover
+        out["walking_log_adaptive_rho_5"] = {"error": repr(e)}
     # config 5: multi-contact humanoid, T = 32 sequential warm-started batches of 2^14 (b, b_eq drift 2 % per step)
     try:
         shp = syn.SHAPES["multicontact"]

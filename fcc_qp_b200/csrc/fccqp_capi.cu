@@ -418,13 +418,14 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool
           CUDA_TRY(cudaMemcpyAsync(h, d_sprof, sizeof(h), cudaMemcpyDeviceToHost, stream));
           CUDA_TRY(cudaStreamSynchronize(stream));
           CUDA_TRY(cudaFree(d_sprof));
-          static const char* names[13] = {"fetch+vectors", "classify", "zero+scatter", "wait-copies", "C+diag", "factor", "x: rhs",
-                                          "x: solve", "project/exit", "epilogue", "x: refine", "x: recover", "x: rest"};
+          static const char* names[16] = {"fetch+vectors", "classify", "zero+scatter", "wait-copies", "C+diag", "factor", "x: rhs",
+                                          "x: solve", "project/exit", "epilogue", "x: refine | op: F", "x: recover", "x: rest",
+                                          "op: inv(L)", "(count)", "op: G"};
           double tot = 0;
-          for (int i = 0; i < 13; ++i) tot += (double)h[i];
+          for (int i = 0; i < 16; ++i) if (i != 14) tot += (double)h[i];
           fprintf(stderr, "[fccqp struct profile] B=%d grid=%d qps=%llu cycles/QP=%.0f\n", p.B, sgrid, h[14], h[14] ? tot / (double)h[14] : 0.0);
-          for (int i = 0; i < 13; ++i)
-            fprintf(stderr, "   %-14s %10.0f cyc/QP  %5.1f%%\n", names[i], h[14] ? (double)h[i] / (double)h[14] : 0.0,
+          for (int i = 0; i < 16; ++i)
+            if (i != 14) fprintf(stderr, "   %-14s %10.0f cyc/QP  %5.1f%%\n", names[i], h[14] ? (double)h[i] / (double)h[14] : 0.0,
                     tot > 0 ? 100.0 * (double)h[i] / tot : 0.0);
         }
         fccqp::SolveParams b = p;

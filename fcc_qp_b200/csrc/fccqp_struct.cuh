@@ -1141,8 +1141,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
             if (base_solve) {
               v_xbase = res;
               __syncthreads();
+              SPROF(12);
               complete_inverse<kThreads>(M, Se.NB);
+              SPROF(13);
               form_g<kThreads>(M, dinv, Se.NB, Se.NB, Se.NB);
+              SPROF(15);
               full_inverse = true;
               // full-space operator (build_full_op) when it fits: rows of F <= threads and vector buffers, tiles of F
               // within the [M | AP] region (AP is not needed afterwards)
@@ -1166,6 +1169,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
                   NBF = fd.NBF; NF = fd.NF;
                   build_full_op<kThreads>(M, AP, hinv, p.op_scratch + (size_t)blockIdx.x * p.op_stride, fd, is_x ? ve.type : VT_NONE,
                                           epos, ve.krow, ve.nnz, ve.aval, hi);
+                  SPROF(10);
                   double* const tb2 = smem + L.off_tbuf;
                   double* const xb2 = smem + L.off_ybuf;
                   if (t < NF) { tb2[t] = 0.0; xb2[t] = 0.0; }

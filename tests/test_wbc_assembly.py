@@ -1,6 +1,8 @@
 """On-device WBC assembly (include/fccqp.h: fccqp_wbc_assemble) against its CPU
 restatement synthetic.assemble_numpy, and the assembled QPs through the solver against the goldens
-of the compiled reference."""
+of the compiled reference.  The reference has no assembly step of its own (its callers hand Solve dense matrices), so
+the assembly oracle is builder-authored: a pass here says the kernel matches OUR numpy statement of fccqp.pdf section 4,
+not the reference; only the solver half (assembled QPs -> goldens) is parity with the reference."""
 import os
 
 import numpy as np
