@@ -1100,9 +1100,16 @@ int fccqp_batch_solve_multi(const fccqp_batch_desc* desc, const int32_t* devices
   const int W = n_devices;
   std::vector<int> rcs(W, FCCQP_OK);
   std::vector<std::string> errs(W);
-  auto shard = [&](int r) {
-    const long long lo = (long long)d.batch * r / W, hi = (long long)d.batch * (r + 1) / W;
-    if (hi <= lo) return;
+  // Dynamic split: the batch is cut into slabs and every device thread pulls the next slab when it is done with its
+  // own, so a device behind a slower or shared PCIe link simply takes fewer of them (measured on an 8-GPU box:
+  // 24 GB/s for GPUs 0-3 against 46-56 GB/s for GPUs 4-7 under load, profiles/r02_h2d_scaling_8gpu.log).  Results do
+  // not depend on which device solved a QP.  Slabs are multiples of the 4096-QP pipeline chunk of the host path and at
+  // least two chunks long, so that H2D, solve and D2H still overlap inside a slab.
+  long long slab = ((long long)d.batch / (4LL * W) + 4095) / 4096 * 4096;
+  if (slab < 8192) slab = 8192;
+  if (W == 1) slab = d.batch;
+  std::atomic<long long> next{0};
+  auto run_range = [&](int r, long long lo, long long hi) -> int {
     fccqp_batch_desc s = d;
     s.device = devices[r];
     s.batch = (int32_t)(hi - lo);
@@ -1123,8 +1130,16 @@ int fccqp_batch_solve_multi(const fccqp_batch_desc* desc, const int32_t* devices
     if (d.res_fcone) s.res_fcone = d.res_fcone + lo;
     if (d.bounds_viol) s.bounds_viol = d.bounds_viol + lo;
     if (d.fcone_viol) s.fcone_viol = d.fcone_viol + lo;
-    rcs[r] = fccqp_batch_solve(&s);
-    if (rcs[r]) errs[r] = g_err;   // (thread-local: carried back to the caller's thread below)
+    return fccqp_batch_solve(&s);
+  };
+  auto shard = [&](int r) {
+    for (;;) {
+      const long long lo = next.fetch_add(slab);
+      if (lo >= d.batch) return;
+      const long long hi = lo + slab < d.batch ? lo + slab : d.batch;
+      rcs[r] = run_range(r, lo, hi);
+      if (rcs[r]) { errs[r] = g_err; return; }   // (thread-local: carried back to the caller's thread below)
+    }
   };
   if (W == 1) shard(0);
   else {

@@ -218,10 +218,12 @@ typedef struct fccqp_batch_desc {
 } fccqp_batch_desc;
 
 int fccqp_batch_solve(const fccqp_batch_desc* desc);
-/* The same call spread over several devices of one box (FCCQP_MEM_HOST only; desc->device is ignored): device r
- * of n_devices takes the contiguous range [B r / n, B (r+1) / n) of every stacked array -- QPs are independent, so
- * there is no exchange step -- on its own host thread with its own streams and staging buffers.  Outputs land in
- * the caller's arrays exactly as with one device; device_seconds is the wall time of the whole call.
+/* The same call spread over several devices of one box (FCCQP_MEM_HOST only; desc->device is ignored): the batch is
+ * cut into contiguous slabs (multiples of 4096 QPs, about B / (4 n_devices) each) and every device -- on its own host
+ * thread with its own streams and staging buffers -- takes the next slab when it has finished its own, so a device
+ * behind a slower host link takes fewer.  QPs are independent: there is no exchange step, and a result does not depend
+ * on which device produced it.  Outputs land in the caller's arrays exactly as with one device; device_seconds is the
+ * wall time of the whole call.
  * (Device-resident data lives on ONE device: shard it yourself and call fccqp_batch_solve per device.) */
 int fccqp_batch_solve_multi(const fccqp_batch_desc* desc, const int32_t* devices, int32_t n_devices);
 /* Page-locked host memory for FCCQP_MEM_HOST callers: inputs and outputs that live in
