@@ -100,3 +100,29 @@ np.savez(sys.argv[2], **out)
         same = A[f"it{n}"] == Bz[f"it{n}"]
         assert same.mean() >= 0.99, (env, n, (~same).sum())
         assert rel(A[f"z{n}"][same], Bz[f"z{n}"][same]) <= 1e-8, (env, n)
+
+
+def test_dropin_object_on_small_problems_takes_the_warp_kernel():
+    """The single-problem FCCQP object (pybind, host arrays) on the reference-generated known answers: projection of a
+    point onto one friction cone (n = 3) and the closed-form equality-constrained QP (n = 12, m = 5, n_iter = 0)."""
+    from fcc_qp import FCCQP, FCCQPOptions
+    from fcc_qp_b200 import _native as nat
+    kats = np.load(os.path.join(ROOT, "tests", "golden", "kats.npz"))
+    o = FCCQPOptions(); o.max_iter, o.rho, o.eps_fcone, o.eps_bound = 2000, 1.0, 1e-10, 1e-10
+    inf3 = np.full(3, np.inf)
+    for f, z in zip(kats["cone_f"], kats["cone_z"]):
+        s = FCCQP(3, 0, 3, 0); s.set_options(o)
+        s.Solve(np.eye(3), -f, np.zeros((0, 3)), np.zeros(0), [0.5], -inf3, inf3)
+        assert nat.last_launch_info()["block"] == 128 and nat.last_launch_info()["smem_bytes"] == 4 * 3 * 3 * 8
+        assert np.abs(s.GetSolution().z - z).max() <= 1e-8
+    o2 = FCCQPOptions(); o2.max_iter, o2.rho, o2.eps_fcone, o2.eps_bound = 100, 1e-3, 1e-6, 1e-6
+    s = FCCQP(12, 5, 0, 0); s.set_options(o2)
+    inf12 = np.full(12, np.inf)
+    s.Solve(kats["eq_Q"], kats["eq_b"], kats["eq_A"], kats["eq_beq"], [], -inf12, inf12)
+    r = s.GetSolution()
+    assert r.details.n_iter == int(kats["eq_n_iter"]) == 0
+    assert np.abs(r.z - kats["eq_z"]).max() <= 1e-9 * max(1.0, np.abs(kats["eq_z"]).max())
+    # warm restart of the same object (carried state on the device)
+    s.set_warm_start(True)
+    s.Solve(kats["eq_Q"], kats["eq_b"], kats["eq_A"], kats["eq_beq"], [], -inf12, inf12)
+    assert np.abs(s.GetSolution().z - kats["eq_z"]).max() <= 1e-9 * max(1.0, np.abs(kats["eq_z"]).max())
