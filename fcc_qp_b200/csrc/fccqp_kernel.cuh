@@ -247,6 +247,9 @@ __device__ __forceinline__ void block_reduce2(double& a, double& b, double* red,
 
 // Smallest pivot, relative to the largest pivot of the same class, that the unpivoted LDL^T still trusts.
 constexpr double kPivotRatio = 1e-12;
+// Regularisation of the constraint block on the retry after a failed factorization, relative to its largest pivot.
+constexpr double kRegDelta = 1e-10;
+constexpr int kRegTries = 4;
 
 // 1/d to full double precision: MUFU seed x0 (relative error e <= 2^-23) and ONE third-order step
 // x0 (1 + e + e^2) = (1/d)(1 - e^3): three dependent FMAs behind the MUFU instead of the four of two
@@ -1131,6 +1134,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
     const long long t_start = clock64();
     unsigned long long fact_cycles = 0;
     int status_flag = 0;
+    bool reg_used = false;   // a factorization of this QP needed the regularised retry (rank-deficient A_eq)
+    bool reg_mine = false;   //   ... and this thread's constraint row is one of the regularised ones
+    double reg_delta = 0.0;  //   ... with -reg_delta on its diagonal
+    int reg_tries = 0;
     int n_iter = 0;
     double res_x = 0.0, res_c = 0.0;
     FCCQP_PROF(0);
@@ -1166,7 +1173,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
       for (int iter = 0; iter < iters; ++iter) {
       double val = v_x;    // solution component of row t (t < N8)
       if (!(pass == 1 && iter == 0 && presolve && p.first_update_identity)) {
-      if (!factored) {
+      while (!factored) {   // (a second trip only for a rank-deficient A_eq, see reg_delta below)
       factored = true;
       const long long t_f0 = clock64();
       if (shared_mode != 0 && cached_pass == pass) {
@@ -1314,6 +1321,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
       FCCQP_PROF(1);
       TR(4);
 
+      // retry after a failed factorization: -delta on the (so far zero) diagonal entry of the dependent constraint rows
+      if (reg_mine) M[mat_off(t, t)] = -reg_delta;
       if (pass == 1) {
         if (is_x) M[mat_off(t, t)] += rho_cur;
       } else {
@@ -1390,6 +1399,27 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
         block_reduce2<false>(pa, pc, red, parity);
         if (is_row && fabs(dn) < kPivotRatio * (is_c ? pc : pa)) badp = true;
         factor_flag = __syncthreads_or(badp) ? 2 : 0;
+        // Rank-deficient A_eq (dependent constraint rows): the reference's LDLT fails there too and its COD fall-back
+        // returns the minimum-norm solution of the singular KKT system (src/fcc_qp.cpp:164-177) -- whose x part, for
+        // CONSISTENT constraints, is the unique minimiser of the QP.  The same x comes out of the quasi-definite
+        // factorization when the dependent row gets -delta on its diagonal (delta = kRegDelta x the largest constraint
+        // pivot): the rows it depends on are still enforced exactly, so the constraint it states holds by itself and
+        // its multiplier comes out as (rounding) / delta.  Only the FIRST failing row of an attempt is touched (pivots
+        // behind a broken one are not to be trusted), up to kRegTries dependent rows per QP; the rows found in the
+        // pre-solve stay regularised in the rho-KKT system.  Whether the constraints were consistent is checked on
+        // the final x (epilogue): if not, the status stays NUMERICAL_ISSUE.
+        if (kShared == false && factor_flag != 0 && m > 0 && reg_tries < kRegTries && isfinite(pc) && pc > 0.0) {
+          double first = badp ? (double)(N8 - t) : 0.0, unused = 0.0;    // largest value = smallest failing row index
+          block_reduce2<false>(first, unused, red, parity);
+          const int row = N8 - (int)first;
+          if (row >= n8 && row < n8 + m) {        // a constraint row (a failing variable row is a genuine breakdown)
+            if (reg_delta == 0.0) reg_delta = kRegDelta * pc;
+            if (t == row) reg_mine = true;
+            reg_used = true;
+            ++reg_tries;
+            factored = false;
+          }
+        }
       }
       if (shared_mode != 0) {
         // shared structure: [K^{-1}]_{x,:} as an explicit operator, kept for every later QP of this CTA
@@ -1551,6 +1581,17 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_solve_kernel(const
       fv = r > 0.0 ? r : 0.0;
     }
     block_reduce2<true>(bv, fv, red, parity);
+    if (reg_used && is_c) {
+      // rank-deficient A_eq handled through the regularised retry: the answer is the reference's only if the dependent
+      // constraints were consistent, i.e. if A_eq x = b_eq still holds to rounding on the x returned
+      const size_t arow = (size_t)qp * p.a_bs + (size_t)(t - n8) * p.a_rs;   // element index (float32 or float64 data)
+      double ax = 0.0, mag = fabs(v_b);
+      for (int j = 0; j < n; ++j) {
+        const double term = ldin(p.A, arow + (size_t)j * p.a_cs) * xs[j];
+        ax += term; mag += fabs(term);
+      }
+      if (!(fabs(ax - v_b) <= 1e-7 * mag + 1e-300)) bad = 1;
+    }
     bad = __syncthreads_or(bad | (status_flag == 2));
     if (is_x) {
       p.x[(size_t)qp * n + t] = v_x;

@@ -106,6 +106,9 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) fccqp_warp_kernel(con
     const bool presolve = eqc || !p.warm;                                  // fcc_qp.cpp:159
 
     int status_flag = 0, n_iter = 0;
+    bool reg_used = false, reg_mine = false;   // regularised retry for dependent constraint rows (fccqp_kernel.cuh)
+    double reg_delta = 0.0;
+    int reg_tries = 0;
     double res_x = 0.0, res_c = 0.0;
     unsigned long long fact_cycles = 0;
 
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) fccqp_warp_kernel(con
         // x-update 0 of a cold solve is the identity (x_bar = x0, zero duals; fccqp_kernel.cuh): the rho-KKT system is
         // only factored for QPs that go on iterating
         if (!(pass == 1 && iter == 0 && presolve && p.first_update_identity)) {
-          if (!factored) {
+          while (!factored) {
             factored = true;
             const long long t_f0 = clock64();
             __syncwarp();
@@ -146,6 +149,7 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) fccqp_warp_kernel(con
               }
             }
             __syncwarp();
+            if (reg_mine) Krow[lane] = -reg_delta;
             if (pass == 1) {
               if (is_x) Krow[lane] += rho_cur;
             } else {
@@ -182,7 +186,18 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) fccqp_warp_kernel(con
               bool badp = lane < N && (!isfinite(d) || (is_c ? !(d < 0.0) : !(d > 0.0)));
               const double pa = warp_max((is_x && pass == 0) ? fabs(d) : 0.0), pc = warp_max(is_c ? fabs(d) : 0.0);
               if (lane < N && fabs(d) < kPivotRatio * (is_c ? pc : pa)) badp = true;
-              if (__any_sync(kFullMask, badp)) status_flag = 2;
+              const unsigned fmask = __ballot_sync(kFullMask, badp);
+              const int row = fmask ? __ffs(fmask) - 1 : -1;       // first failing row
+              if (fmask && row >= n && row < N && reg_tries < kRegTries && isfinite(pc) && pc > 0.0) {
+                // a dependent constraint row: -delta on its diagonal and one more attempt (fccqp_kernel.cuh)
+                if (reg_delta == 0.0) reg_delta = kRegDelta * pc;
+                if (lane == row) reg_mine = true;
+                reg_used = true;
+                ++reg_tries;
+                factored = false;
+              } else if (fmask) {
+                status_flag = 2;
+              }
             }
             fact_cycles += (unsigned long long)(clock64() - t_f0);
           }
@@ -293,7 +308,17 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) fccqp_warp_kernel(con
       }
     }
     bv = warp_sum(bv); fv = warp_sum(fv);
-    const bool bad = __any_sync(kFullMask, (is_x && !isfinite(v_x)) || status_flag == 2);
+    bool incons = false;
+    if (reg_used) {
+      // regularised retry taken: the answer is the reference's only if A_eq x = b_eq still holds (consistent dependent rows)
+      double ax = 0.0, mag = fabs(v_b);
+      for (int j = 0; j < n; ++j) {
+        const double xj = shfl_d(v_x, j);
+        if (is_c) { const double term = Ag[(long long)(lane - n) * p.a_rs + (long long)j * p.a_cs] * xj; ax += term; mag += fabs(term); }
+      }
+      incons = is_c && !(fabs(ax - v_b) <= 1e-7 * mag + 1e-300);
+    }
+    const bool bad = __any_sync(kFullMask, (is_x && !isfinite(v_x)) || status_flag == 2 || incons);
     if (is_x) {
       p.x[(size_t)qp * n + lane] = v_x;
       if (p.mu_x) p.mu_x[(size_t)qp * n + lane] = v_mux;

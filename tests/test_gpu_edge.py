@@ -122,17 +122,23 @@ def test_strided_device_inputs(walking_log):
     assert np.array_equal(s.GetSolution().details.n_iter.cpu().numpy(), gold["n_iter"][:64])
 
 
-@pytest.mark.parametrize("perturb", [0.0, 1e-14])
-def test_singular_kkt_is_flagged(perturb):
-    """(Nearly) duplicate equality rows make the KKT matrix singular.  The reference falls back to COD and returns
-    its minimum-norm answer (src/fcc_qp.cpp:164-177); the unpivoted device factorization cannot, and must say so:
-    either the answer equals the compiled reference's within the bar, or the status is
-    FCCQP_STATUS_NUMERICAL_ISSUE -- never a different answer under a success status."""
+@pytest.mark.parametrize("n,m", [(6, 3), (40, 12)])      # warp kernel / CTA kernels
+@pytest.mark.parametrize("perturb,consistent", [(0.0, True), (1e-14, True), (0.0, False)])
+def test_rank_deficient_constraints(n, m, perturb, consistent):
+    """(Nearly) duplicate equality rows make the KKT matrix singular.  The reference's LDLT fails and its COD fall-back
+    returns the minimum-norm answer (src/fcc_qp.cpp:164-177), whose x part is the unique minimiser when the dependent
+    rows are CONSISTENT.  The device factorization is unpivoted: it retries once with a regularised constraint block
+    (kRegDelta), which reproduces that x, and checks A_eq x = b_eq on the result.  Bar: either the answer equals the
+    compiled reference's within 1e-6 under the same status, or the status is FCCQP_STATUS_NUMERICAL_ISSUE -- never a
+    different answer under a success status.  Consistent cases must be solved, the inconsistent one (where COD returns a
+    least-squares compromise) must be flagged."""
     import oracle
-    rng = np.random.default_rng(11)
-    n, m = 6, 3
-    Q = np.eye(n)[None]; A = rng.standard_normal((1, m, n)); A[0, 2] = A[0, 1] * (1.0 + perturb)
-    beq = np.array([[0.3, -0.2, -0.2]]); b = rng.standard_normal((1, n))
+    rng = np.random.default_rng(11 + n)
+    G = rng.standard_normal((n, n))
+    Q = (G @ G.T / n + np.eye(n))[None]
+    A = rng.standard_normal((1, m, n)); A[0, 2] = A[0, 1] * (1.0 + perturb)
+    beq = rng.standard_normal((1, m)); beq[0, 2] = beq[0, 1] if consistent else beq[0, 1] + 0.7
+    b = rng.standard_normal((1, n))
     opts = dict(max_iter=10, rho=1e-3, eps_fcone=1e-6, eps_bound=1e-6)
     s = batch_solver(n, m, 0, 0, **opts)
     lb, ub = np.full(n, -np.inf), np.full(n, np.inf)
@@ -143,10 +149,46 @@ def test_singular_kkt_is_flagged(perturb):
     o.Solve(Q[0], b[0], A[0], beq[0], [], lb, ub)
     ref = o.GetSolution()
     same = np.isfinite(r.z).all() and np.abs(r.z[0] - ref["z"]).max() <= 1e-6 * max(1.0, np.abs(ref["z"]).max())
-    assert r.details.solve_status[0] == 2 or (same and r.details.solve_status[0] == ref["status"]), \
-        (r.details.solve_status[0], r.z[0], ref["z"])
-    # (as built, the factorization flags both cases: a pivot of rounding-noise size, or of the wrong sign)
-    assert r.details.solve_status[0] == 2
+    st = int(r.details.solve_status[0])
+    assert st == 2 or (same and st == ref["status"]), (st, r.z[0], ref["z"])
+    if consistent:
+        assert st == ref["status"] and same
+        assert np.abs(A[0] @ r.z[0] - beq[0]).max() <= 1e-8 * max(1.0, np.abs(beq).max())
+    else:
+        assert st == 2
+
+
+def test_rank_deficient_constraints_in_a_batch():
+    """The same through the reduced kernel's hand-over: a structured batch with one degenerate QP in it (two identical,
+    consistent dynamics rows).  On this input the reference's LDLT does NOT report failure (its pivot test misses the
+    dependent row, `presolve_path` 1), no COD runs, and FCCQP::Solve returns a point that violates its own equality
+    constraints by ~10 under status 0 -- there is nothing to be in parity with.  The device path returns the actual
+    minimiser: checked against the null-space solution of the equality-constrained QP (numpy), and A_eq z = b_eq."""
+    import oracle
+    from fcc_qp_b200 import synthetic as syn
+    qp = syn.make_batch(syn.QUADRUPED, 192)              # (the golden set)
+    A = qp.A_eq.copy(); beq = qp.b_eq.copy()
+    A[5, 7] = A[5, 3]; beq[5, 7] = beq[5, 3]            # QP 5: two identical, consistent rows
+    s = batch_solver(qp.n, qp.m, qp.nc, qp.lambda_c_start, **LOG_OPTS)
+    s.Solve(qp.Q, qp.b, A, beq, qp.friction_coeffs, qp.lb, qp.ub)
+    r = s.GetSolution()
+    o = oracle.Oracle("ref" if oracle.have("ref") else "port").solver(qp.n, qp.m, qp.nc, qp.lambda_c_start)
+    o.set_options(LOG_OPTS["max_iter"], LOG_OPTS["rho"], LOG_OPTS["eps_fcone"], LOG_OPTS["eps_bound"])
+    o.Solve(qp.Q[5], qp.b[5], A[5], beq[5], qp.friction_coeffs[5], qp.lb[5], qp.ub[5])
+    ref = o.GetSolution()
+    assert np.abs(A[5] @ ref["z"] - beq[5]).max() > 1.0          # the reference's answer is not a solution
+    assert int(r.details.solve_status[5]) == 0 and int(r.details.n_iter[5]) == 0
+    _, sv, Vt = np.linalg.svd(A[5])
+    rk = int((sv > 1e-10 * sv[0]).sum())
+    assert rk == qp.m - 1
+    Z = Vt[rk:].T
+    xp = np.linalg.lstsq(A[5], beq[5], rcond=None)[0]
+    xt = xp + Z @ np.linalg.solve(Z.T @ qp.Q[5] @ Z, -Z.T @ (qp.Q[5] @ xp + qp.b[5]))
+    assert np.abs(r.z[5] - xt).max() <= 1e-6 * max(1.0, np.abs(xt).max())
+    assert np.abs(A[5] @ r.z[5] - beq[5]).max() <= 1e-8 * max(1.0, np.abs(beq[5]).max())
+    others = np.arange(192) != 5
+    gold = np.load(os.path.join(G, "synthetic_quadruped_cold.npz"))
+    assert (np.abs(r.z[others] - gold["z"][others]).max(1) <= 1e-6 * np.maximum(1.0, np.abs(gold["z"][others]).max(1))).all()
 
 
 def test_well_conditioned_neighbours_are_not_flagged():
