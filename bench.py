@@ -201,8 +201,7 @@ def shape_extras(dev):
     # small QPs: the warp-per-QP kernel (n + m <= 32; fccqp_warp.cuh), random well-conditioned QPs at the settings of
     # fccqp.pdf Table 1 (max_iter 15, eps 1e-4); the generator is the parity tests' own
     try:
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        from test_gpu_random_shapes import random_qps
+        from fcc_qp_b200.synthetic import random_qps
         small = {}
         for (sn, sm, snc, slcs) in ((12, 6, 6, 3), (24, 8, 6, 0)):
             base = random_qps(np.random.default_rng(sn), 4096, sn, sm, snc, slcs)

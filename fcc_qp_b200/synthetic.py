@@ -194,3 +194,23 @@ def random_walk(qp: QPBatch, rng: np.random.Generator, sigma: float = 0.02) -> Q
     b = qp.b * (1.0 + sigma * rng.standard_normal(qp.b.shape))
     beq = qp.b_eq * (1.0 + sigma * rng.standard_normal(qp.b_eq.shape))
     return dataclasses.replace(qp, b=np.ascontiguousarray(b), b_eq=np.ascontiguousarray(beq))
+
+
+def random_qps(rng, B, n, m, nc, lcs):
+    """Well-conditioned convex QPs of arbitrary small shape with full-row-rank A_eq, a few active bounds and cones (the
+    randomised-shape parity tests and the small-QP benchmarks draw from here)."""
+    from .logdata import QPBatch
+    G = rng.standard_normal((B, n, n))
+    Q = G @ G.transpose(0, 2, 1) / n + np.eye(n) * rng.uniform(0.05, 1.0, (B, 1, 1))
+    Q = 0.5 * (Q + Q.transpose(0, 2, 1))
+    A = rng.standard_normal((B, m, n)) * (rng.random((B, m, n)) < 0.6)
+    A[:, np.arange(m), np.arange(m)] += 2.0                    # keeps the rows independent
+    b = rng.standard_normal((B, n)) * 2.0
+    beq = rng.standard_normal((B, m))
+    lb = np.full((B, n), -np.inf); ub = np.full((B, n), np.inf)
+    nb = max(1, n // 4)
+    idx = rng.choice(n, nb, replace=False)
+    lb[:, idx] = -rng.uniform(0.05, 0.5, (B, nb)); ub[:, idx] = rng.uniform(0.05, 0.5, (B, nb))
+    mu = rng.uniform(0.3, 1.0, (B, max(nc // 3, 0)))
+    c = np.ascontiguousarray
+    return QPBatch(n, m, nc, lcs, c(Q), c(b), c(A), c(beq), c(mu), c(lb), c(ub))

@@ -14,22 +14,7 @@ pytestmark = pytest.mark.gpu
 OPTS = dict(max_iter=200, rho=1e-3, eps_fcone=1e-7, eps_bound=1e-7)
 
 
-def random_qps(rng, B, n, m, nc, lcs):
-    """Well-conditioned convex QPs with full-row-rank A, a few active bounds and cones."""
-    G = rng.standard_normal((B, n, n))
-    Q = G @ G.transpose(0, 2, 1) / n + np.eye(n) * rng.uniform(0.05, 1.0, (B, 1, 1))
-    Q = 0.5 * (Q + Q.transpose(0, 2, 1))
-    A = rng.standard_normal((B, m, n)) * (rng.random((B, m, n)) < 0.6)
-    A[:, np.arange(m), np.arange(m)] += 2.0                    # keeps the rows independent
-    b = rng.standard_normal((B, n)) * 2.0
-    beq = rng.standard_normal((B, m))
-    lb = np.full((B, n), -np.inf); ub = np.full((B, n), np.inf)
-    nb = max(1, n // 4)
-    idx = rng.choice(n, nb, replace=False)
-    lb[:, idx] = -rng.uniform(0.05, 0.5, (B, nb)); ub[:, idx] = rng.uniform(0.05, 0.5, (B, nb))
-    mu = rng.uniform(0.3, 1.0, (B, max(nc // 3, 0)))
-    c = np.ascontiguousarray
-    return QPBatch(n, m, nc, lcs, c(Q), c(b), c(A), c(beq), c(mu), c(lb), c(ub))
+from fcc_qp_b200.synthetic import random_qps  # noqa: E402,F401  (the generator lives with the other synthetic sets)
 
 
 SHAPES = [(5, 2, 3, 1), (7, 0, 3, 4), (9, 4, 0, 0), (13, 6, 6, 5), (17, 9, 3, 14), (24, 8, 6, 0), (31, 15, 9, 20),

@@ -1,9 +1,9 @@
 """Throughput of small QPs: warp-per-QP kernel against the CTA-per-QP kernels (FCCQP_NO_WARP=1 in the environment).
 usage: python tools/bench_small.py [B]   -> one JSON line per shape"""
 import json, os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import numpy as np, torch
-from test_gpu_random_shapes import random_qps
+from fcc_qp_b200.synthetic import random_qps
 from fcc_qp_b200.batch import FCCQPBatch, FCCQPOptionsB
 from fcc_qp_b200 import _native as nat
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 18
