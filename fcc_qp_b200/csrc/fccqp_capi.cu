@@ -809,6 +809,31 @@ int fccqp_set_warm_state(fccqp_handle h, const double* x, const double* mu_x, co
   return FCCQP_OK;
 }
 
+// Structure bounds of a HOST batch from a sample of up to 64 of its QPs (FCCQP_STRUCTURE_AUTO); other modes pass through.
+static void host_struct_hint(const fccqp_batch_desc& d, StructHint* out) {
+  StructHint hint;
+  hint.set(d.structure);
+  hint.caps[0] = d.struct_caps[0]; hint.caps[1] = d.struct_caps[1]; hint.caps[2] = d.struct_caps[2];
+  const int B = d.batch, n = d.n, m = d.m;
+  const bool q_shared = d.q_batch_stride == 0, a_shared = d.a_batch_stride == 0;
+  if (hint.mode == FCCQP_STRUCTURE_AUTO) {
+    hint.mode = FCCQP_STRUCTURE_DENSE;
+    if (d.precision != FCCQP_PRECISION_FP32_DATA && m > 0 && !(q_shared && a_shared) && B > 0) {
+      const int ns = B < 64 ? B : 64;
+      bool ok = true;
+      for (int sidx = 0; sidx < ns && ok; ++sidx) {
+        const long long qp = ns > 1 ? (long long)sidx * (B - 1) / (ns - 1) : 0;
+        int c[3];
+        ok = host_classify(n, m, d.Q + (q_shared ? 0 : qp * (long long)n * n), d.q_row_stride, d.q_col_stride,
+                           d.A_eq + (a_shared ? 0 : qp * (long long)m * n), d.a_row_stride, d.a_col_stride, &c[0], &c[1], &c[2]);
+        for (int k = 0; k < 3; ++k) if (c[k] > hint.caps[k]) hint.caps[k] = c[k];
+      }
+      if (ok) hint.mode = FCCQP_STRUCTURE_CAPS;
+    }
+  }
+  *out = hint;
+}
+
 // ---------------------------------------------------------------------------
 // batched entry point
 // ---------------------------------------------------------------------------
@@ -978,23 +1003,7 @@ int fccqp_batch_solve(const fccqp_batch_desc* desc) {
   // structure of the batch, from the host copy of the data (a sample of up to 64 QPs; no device probe,
   // no synchronisation inside the chunk pipeline)
   StructHint hint;
-  hint.set(d.structure);
-  hint.caps[0] = d.struct_caps[0]; hint.caps[1] = d.struct_caps[1]; hint.caps[2] = d.struct_caps[2];
-  if (hint.mode == FCCQP_STRUCTURE_AUTO) {
-    hint.mode = FCCQP_STRUCTURE_DENSE;
-    if (es == sizeof(double) && m > 0 && !(q_shared && a_shared)) {
-      const int ns = B < 64 ? B : 64;
-      bool ok = true;
-      for (int sidx = 0; sidx < ns && ok; ++sidx) {
-        const long long qp = ns > 1 ? (long long)sidx * (B - 1) / (ns - 1) : 0;
-        int c[3];
-        ok = host_classify(n, m, d.Q + (q_shared ? 0 : qp * (long long)n * n), d.q_row_stride, d.q_col_stride,
-                           d.A_eq + (a_shared ? 0 : qp * (long long)m * n), d.a_row_stride, d.a_col_stride, &c[0], &c[1], &c[2]);
-        for (int k = 0; k < 3; ++k) if (c[k] > hint.caps[k]) hint.caps[k] = c[k];
-      }
-      if (ok) hint.mode = FCCQP_STRUCTURE_CAPS;
-    }
-  }
+  host_struct_hint(d, &hint);
 
   int nchunks = (B + 4095) / 4096;
   if (nchunks > 16) nchunks = 16;
@@ -1105,15 +1114,20 @@ int fccqp_batch_solve_multi(const fccqp_batch_desc* desc, const int32_t* devices
   // 24 GB/s for GPUs 0-3 against 46-56 GB/s for GPUs 4-7 under load, profiles/r02_h2d_scaling_8gpu.log).  Results do
   // not depend on which device solved a QP.  Slabs are multiples of the 4096-QP pipeline chunk of the host path and at
   // least two chunks long, so that H2D, solve and D2H still overlap inside a slab.
-  long long slab = ((long long)d.batch / (4LL * W) + 4095) / 4096 * 4096;
+  long long slab = ((long long)d.batch / (2LL * W) + 4095) / 4096 * 4096;
   if (slab < 8192) slab = 8192;
   if (W == 1) slab = d.batch;
+  // (the structure bounds are worked out once, from a sample of the whole batch, and handed to every slab)
+  StructHint mh;
+  host_struct_hint(d, &mh);
   std::atomic<long long> next{0};
   auto run_range = [&](int r, long long lo, long long hi) -> int {
     fccqp_batch_desc s = d;
     s.device = devices[r];
     s.batch = (int32_t)(hi - lo);
     s.device_seconds = nullptr;
+    s.structure = mh.mode | (mh.refine ? FCCQP_STRUCTURE_REFINE : 0);
+    s.struct_caps[0] = mh.caps[0]; s.struct_caps[1] = mh.caps[1]; s.struct_caps[2] = mh.caps[2];
     const size_t es = d.precision == FCCQP_PRECISION_FP32_DATA ? sizeof(float) : sizeof(double);
     auto adv = [&](const double* p, int64_t stride) -> const double* {   // problem data: element size es
       return p ? reinterpret_cast<const double*>(reinterpret_cast<const char*>(p) + (size_t)lo * (size_t)stride * es) : p;
