@@ -1112,11 +1112,17 @@ int fccqp_batch_solve_multi(const fccqp_batch_desc* desc, const int32_t* devices
   // Dynamic split: the batch is cut into slabs and every device thread pulls the next slab when it is done with its
   // own, so a device behind a slower or shared PCIe link simply takes fewer of them (measured on an 8-GPU box:
   // 24 GB/s for GPUs 0-3 against 46-56 GB/s for GPUs 4-7 under load, profiles/r02_h2d_scaling_8gpu.log).  Results do
-  // not depend on which device solved a QP.  Slabs are multiples of the 4096-QP pipeline chunk of the host path and at
-  // least two chunks long, so that H2D, solve and D2H still overlap inside a slab.
-  long long slab = ((long long)d.batch / (2LL * W) + 4095) / 4096 * 4096;
-  if (slab < 8192) slab = 8192;
-  if (W == 1) slab = d.batch;
+  // not depend on which device solved a QP.
+  // Guided sizes: a slab is half of an equal share of what is LEFT (multiples of the 4096-QP chunk, at least two chunks):
+  // few, large slabs while there is plenty of work -- every slab pays one pipeline fill and drain, ~1 ms -- and small
+  // ones at the end, so that the slowest device finishes at most one small slab after the others.
+  const long long Btot = d.batch;
+  auto slab_at = [&](long long lo) -> long long {
+    if (W == 1) return Btot - lo;
+    long long sz = ((Btot - lo) / (2LL * W) + 4095) / 4096 * 4096;
+    if (sz < 8192) sz = 8192;
+    return sz < Btot - lo ? sz : Btot - lo;
+  };
   // (the structure bounds are worked out once, from a sample of the whole batch, and handed to every slab)
   StructHint mh;
   host_struct_hint(d, &mh);
@@ -1148,9 +1154,13 @@ int fccqp_batch_solve_multi(const fccqp_batch_desc* desc, const int32_t* devices
   };
   auto shard = [&](int r) {
     for (;;) {
-      const long long lo = next.fetch_add(slab);
-      if (lo >= d.batch) return;
-      const long long hi = lo + slab < d.batch ? lo + slab : d.batch;
+      long long lo = next.load();
+      long long sz = 0;
+      do {
+        if (lo >= Btot) return;
+        sz = slab_at(lo);
+      } while (!next.compare_exchange_weak(lo, lo + sz));
+      const long long hi = lo + sz;
       rcs[r] = run_range(r, lo, hi);
       if (rcs[r]) { errs[r] = g_err; return; }   // (thread-local: carried back to the caller's thread below)
     }

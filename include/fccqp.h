@@ -234,7 +234,7 @@ typedef struct fccqp_batch_desc {
 
 int fccqp_batch_solve(const fccqp_batch_desc* desc);
 /* The same call spread over several devices of one box (FCCQP_MEM_HOST only; desc->device is ignored): the batch is
- * cut into contiguous slabs (multiples of 4096 QPs, about B / (2 n_devices) each) and every device -- on its own host
+ * cut into contiguous slabs (multiples of 4096 QPs; guided sizes: half an equal share of what is left, at least 8192) and every device -- on its own host
  * thread with its own streams and staging buffers -- takes the next slab when it has finished its own, so a device
  * behind a slower host link takes fewer.  QPs are independent: there is no exchange step, and a result does not depend
  * on which device produced it.  Outputs land in the caller's arrays exactly as with one device; device_seconds is the
