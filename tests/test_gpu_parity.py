@@ -338,3 +338,27 @@ def test_fp32_data_mode_synthetic(name, B):
     sol = s.GetSolution()
     assert rel_err(sol.z, gold["z"]).max() <= 2e-3
     assert (sol.details.n_iter != gold["n_iter"]).mean() <= 0.05
+
+
+def test_walking_log_reference_default_options(walking_log):
+    """The reference's DEFAULT options (src/fcc_qp.hpp:30-35: max_iter 1000, rho 1e-6, eps_fcone 1e-3, eps_bound 1e-6) -- a
+    different regime from the replay script's (rho 50x smaller, looser cone tolerance, 10x the iteration budget) -- against
+    the compiled reference run live on the same QPs (every fourth log entry)."""
+    import oracle
+    from fcc_qp_b200.batch import FCCQPBatch, FCCQPOptionsB
+    qp = walking_log.take(np.arange(0, 2019, 4))
+    opts = dict(max_iter=1000, rho=1e-6, eps_fcone=1e-3, eps_bound=1e-6)
+    ref = oracle.Oracle("ref" if oracle.have("ref") else "port").solve_batch(qp, warm_mode=0, nthreads=8, **opts)
+    s = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start)
+    s.set_options(FCCQPOptionsB())            # the defaults of the batched front end are the reference's
+    assert (s.options.max_iter, s.options.rho, s.options.eps_fcone, s.options.eps_bound) == (1000, 1e-6, 1e-3, 1e-6)
+    s.Solve(qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)
+    sol = s.GetSolution()
+    n_gpu = np.asarray(sol.details.n_iter)
+    same = n_gpu == ref["n_iter"]
+    assert rel_err(np.asarray(sol.z)[same], ref["z"][same]).max() <= Z_TOL
+    margins = explain_count_mismatches(qp, n_gpu, ref["n_iter"], opts=opts)
+    print(f"default options: {len(margins)} count differences of {qp.batch}, iterating {int((ref['n_iter'] > 0).sum())}, "
+          f"max iterations {int(ref['n_iter'].max())}")
+    assert (~same).mean() <= 0.005
+    assert np.array_equal(np.asarray(sol.details.solve_status)[same], ref["status"][same])
