@@ -362,3 +362,29 @@ def test_walking_log_reference_default_options(walking_log):
           f"max iterations {int(ref['n_iter'].max())}")
     assert (~same).mean() <= 0.005
     assert np.array_equal(np.asarray(sol.details.solve_status)[same], ref["status"][same])
+
+
+def test_jittered_log_against_the_live_reference(walking_log):
+    """SURVEY 8d config 2 with the optional jitter: the log tiled to 4096 QPs with b and b_eq perturbed by N(0, 1e-3 |.|)
+    (seed 1234), so that no two QPs of the batch are identical; compiled reference run live on the same inputs."""
+    import dataclasses
+    import oracle
+    from fcc_qp_b200.batch import FCCQPBatch, FCCQPOptionsB
+    rng = np.random.default_rng(1234)
+    base = walking_log.tile(4096)
+    qp = dataclasses.replace(base, b=np.ascontiguousarray(base.b * (1.0 + 1e-3 * rng.standard_normal(base.b.shape))),
+                             b_eq=np.ascontiguousarray(base.b_eq * (1.0 + 1e-3 * rng.standard_normal(base.b_eq.shape))))
+    ref = oracle.Oracle("ref" if oracle.have("ref") else "port").solve_batch(qp, warm_mode=0, nthreads=8, **LOG_OPTS)
+    s = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start)
+    s.set_options(FCCQPOptionsB(**LOG_OPTS))
+    s.Solve(qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)
+    sol = s.GetSolution()
+    n_gpu = np.asarray(sol.details.n_iter)
+    same = n_gpu == ref["n_iter"]
+    assert rel_err(np.asarray(sol.z)[same], ref["z"][same]).max() <= Z_TOL
+    o, oref = qp.objective(np.asarray(sol.z)), qp.objective(ref["z"])
+    assert (np.abs(o - oref) / np.maximum(1.0, np.abs(oref)))[same].max() <= OBJ_TOL
+    margins = explain_count_mismatches(qp, n_gpu, ref["n_iter"])
+    print(f"jittered log: {len(margins)} count differences of {qp.batch}, margins {np.round(margins, 5).tolist()}")
+    assert (~same).mean() <= 0.005
+    assert np.array_equal(np.asarray(sol.details.solve_status)[same], ref["status"][same])
