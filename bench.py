@@ -239,28 +239,56 @@ def shape_extras(dev):
         del args, s, qp
     except Exception as e:  # pragma: no cover
         out["walking_log_adaptive_rho_5"] = {"error": repr(e)}
+    # FCCQP_SCHEDULE_LPT (FCCQPBatch.schedule_from_previous): the same cold batch solved again into the same arrays, lanes that
+    # ran long in the previous solve pulled from the work queue first.  Same results bit for bit (tests); an extra key
+    # because the headline `value` must not depend on a previous solve of the same data.
+    try:
+        log = load_walking_log()
+        qp = log.take(np.arange(1 << 16) % log.batch)
+        args = [torch.as_tensor(a, device=dev) for a in (qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)]
+        s = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start, device=dev.index); s.set_options(FCCQPOptionsB(**OPTS))
+        s.schedule_from_previous = True
+        s.Solve(*args); torch.cuda.synchronize(dev)          # no hint yet
+        best = 1e9
+        for _ in range(3):
+            s.Solve(*args); torch.cuda.synchronize(dev)
+            best = min(best, s.GetSolution().details.device_time)
+        out["walking_log_schedule_from_previous"] = {"batch": 1 << 16, "ms": 1e3 * best, "qps": (1 << 16) / best,
+                                                     "note": "processing order from the previous solve's iteration counts"}
+        del args, s, qp
+    except Exception as e:  # pragma: no cover
+        out["walking_log_schedule_from_previous"] = {"error": repr(e)}
     # config 5: multi-contact humanoid, T = 32 sequential warm-started batches of 2^14 (b, b_eq drift 2 % per step)
     try:
         shp = syn.SHAPES["multicontact"]
         B, T = 1 << 14, 32
         qp = syn.make_batch(shp, 2048, seed=shp.seed + 1)
-        Q, b, A, beq, mu, lb, ub = device_batch(qp, B)
-        s = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start, device=dev.index); s.set_options(FCCQPOptionsB(**OPTS))
-        s.Solve(Q, b, A, beq, mu, lb, ub); torch.cuda.synchronize(dev)     # untimed warm-up launch
-        gen = torch.Generator(device=dev); gen.manual_seed(3)
-        per = []
-        for t in range(T):
-            s.set_warm_start(t > 0)
-            s.Solve(Q, b, A, beq, mu, lb, ub); torch.cuda.synchronize(dev)
-            per.append(s.GetSolution().details.device_time)
-            b = b * (1.0 + 0.02 * torch.randn(b.shape, device=dev, dtype=torch.float64, generator=gen))
-            beq = beq * (1.0 + 0.02 * torch.randn(beq.shape, device=dev, dtype=torch.float64, generator=gen))
-        it = s.GetSolution().details.n_iter.cpu().numpy()
+        Q, b0, A, beq0, mu, lb, ub = device_batch(qp, B)
+
+        def sequence(hint):
+            s = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start, device=dev.index); s.set_options(FCCQPOptionsB(**OPTS))
+            s.schedule_from_previous = hint
+            b, beq = b0, beq0
+            s.Solve(Q, b, A, beq, mu, lb, ub); torch.cuda.synchronize(dev)     # untimed warm-up launch
+            gen = torch.Generator(device=dev); gen.manual_seed(3)
+            per = []
+            for t in range(T):
+                s.set_warm_start(t > 0)
+                s.Solve(Q, b, A, beq, mu, lb, ub); torch.cuda.synchronize(dev)
+                per.append(s.GetSolution().details.device_time)
+                b = b * (1.0 + 0.02 * torch.randn(b.shape, device=dev, dtype=torch.float64, generator=gen))
+                beq = beq * (1.0 + 0.02 * torch.randn(beq.shape, device=dev, dtype=torch.float64, generator=gen))
+            return per, s.GetSolution().details.n_iter.cpu().numpy()
+
+        per, it = sequence(False)
         out["multicontact"] = {"baseline_config": 5, "n": qp.n, "m": qp.m, "nc": qp.nc, "batch": B, "steps": T,
                                "total_ms": 1e3 * sum(per), "qps": B * T / sum(per), "first_cold_ms": 1e3 * per[0],
                                "cold_qps": B / per[0], "warm_ms_median": 1e3 * float(np.median(per[1:])),
                                "iterating_fraction_last": float((it > 0).mean()),
                                "launch": nat.last_launch_info(), "structure": nat.last_struct_info()}
+        per, _ = sequence(True)    # FCCQP_SCHEDULE_LPT: each step's processing order from the step before
+        out["multicontact"]["schedule_from_previous"] = {"total_ms": 1e3 * sum(per), "qps": B * T / sum(per),
+                                                         "warm_ms_median": 1e3 * float(np.median(per[1:]))}
     except Exception as e:  # pragma: no cover
         out["multicontact"] = {"error": repr(e)}
     return out

@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get("FCCQP_LIB") or os.path.join(_HERE, "libfccqp_b200.so"
 ABI_VERSION = 4
 STRUCTURE_AUTO, STRUCTURE_DENSE, STRUCTURE_CAPS = 0, 1, 2
 STRUCTURE_REFINE = 256   # flag: iterative refinement of the reduced cold pre-solve
+SCHEDULE_LPT = 512       # flag: n_iter holds an earlier solve's counts; lanes that ran long are processed first
 MEM_HOST, MEM_DEVICE = 0, 1
 STATUS_SUCCESS, STATUS_MAX_ITERATIONS, STATUS_NUMERICAL_ISSUE = 0, 1, 2
 E_INVALID, E_CUDA, E_UNSUPPORTED = -1, -2, -3

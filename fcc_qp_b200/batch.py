@@ -91,6 +91,11 @@ class FCCQPBatch:
         # one step of iterative refinement of the reduced cold pre-solve (FCCQP_STRUCTURE_REFINE): 7e-11 instead of
         # 1.2e-7 relative on z against the reference on the walking log, ~25 % more time per cold QP
         self.refine = False
+        # device (torch) path: lanes that ran long in the PREVIOUS Solve of this object are pulled from the work queue
+        # first (FCCQP_SCHEDULE_LPT; the previous iteration counts are still in the solver-owned n_iter tensor).  For
+        # control loops re-solving a slowly changing batch: the few QPs that run to max_iter stop being the tail of
+        # the launch.  Changes the processing order only, never a result.
+        self.schedule_from_previous = False
         self._caps = None
         self.warm_start = False
         self.time_kernel = True
@@ -330,8 +335,10 @@ class FCCQPBatch:
             if nat.last_struct_info()["deferred"] > B // 16:
                 self._caps = None
         d = self._desc(B, nat.MEM_DEVICE)
-        probed = (d.structure & ~nat.STRUCTURE_REFINE) == nat.STRUCTURE_AUTO
+        probed = (d.structure & ~(nat.STRUCTURE_REFINE | nat.SCHEDULE_LPT)) == nat.STRUCTURE_AUTO
         d.warm_start = int(warm)
+        if self.schedule_from_previous and not fresh:
+            d.structure |= nat.SCHEDULE_LPT
         bs = lambda a, full_ndim: int(a.stride(0)) if a.dim() == full_ndim and B > 1 else (
             int(a.stride(0)) if a.dim() == full_ndim else 0)
         d.Q, d.q_batch_stride, d.q_row_stride, d.q_col_stride = Q.data_ptr(), bs(Q, 3), int(Q.stride(1)), int(Q.stride(2))

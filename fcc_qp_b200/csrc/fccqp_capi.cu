@@ -39,7 +39,12 @@ struct StructHint {
   int mode = FCCQP_STRUCTURE_AUTO;   // AUTO: probe on the device (one tiny kernel + a stream sync); DENSE: never; CAPS: given
   int caps[3] = {0, 0, 0};           // nr, ndp, nd0
   int refine = 0;                    // FCCQP_STRUCTURE_REFINE: one step of iterative refinement on the reduced cold pre-solve
-  void set(int structure) { mode = structure & ~FCCQP_STRUCTURE_REFINE; refine = (structure & FCCQP_STRUCTURE_REFINE) != 0; }
+  int lpt = 0;                       // FCCQP_SCHEDULE_LPT: p.n_iter holds earlier iteration counts; long lanes first
+  void set(int structure) {
+    mode = structure & ~(FCCQP_STRUCTURE_REFINE | FCCQP_SCHEDULE_LPT);
+    refine = (structure & FCCQP_STRUCTURE_REFINE) != 0;
+    lpt = (structure & FCCQP_SCHEDULE_LPT) != 0;
+  }
 };
 
 int fail(int code, const char* fmt, ...) {
@@ -280,9 +285,20 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool
   // device-side QP list, [3] spare, [4..7] structure probe, [8..8+B) the list.  One allocation per call, so
   // any number of calls may be in flight on any number of streams.
   unsigned int* scr = nullptr;
-  CUDA_TRY(cudaMallocAsync(&scr, ((size_t)p.B + 8) * sizeof(unsigned int), stream));
+  const bool lpt = hint_in && hint_in->lpt && p.n_iter != nullptr && p.B >= 2 * ctas_per_sm * ctx.num_sms;
+  CUDA_TRY(cudaMallocAsync(&scr, ((size_t)p.B * (lpt ? 2 : 1) + 8 + (lpt ? 2 : 0)) * sizeof(unsigned int), stream));
   CUDA_TRY(cudaMemsetAsync(scr, 0, 8 * sizeof(unsigned int), stream));
   p.work_counter = scr;
+  if (lpt) {
+    // FCCQP_SCHEDULE_LPT: lanes whose previous solve ran long go to the front of the processing order
+    // ([8 + B, 8 + 2B) the order, then its two counters)
+    int* const order = reinterpret_cast<int*>(scr + 8 + p.B);
+    unsigned int* const cnt = scr + 8 + 2 * (size_t)p.B;
+    CUDA_TRY(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned int), stream));
+    fccqp::lpt_order_kernel<<<(p.B + 255) / 256, 256, 0, stream>>>(p.n_iter, p.B, p.full_inverse_at, order, cnt, cnt + 1);
+    CUDA_TRY(cudaGetLastError());
+    p.index_list = order;
+  }
   unsigned int* const counter2 = scr + 1;
   unsigned int* const list_count = scr + 2;
   int* const list = reinterpret_cast<int*>(scr + 8);
@@ -696,7 +712,7 @@ int fccqp_set_warm_start(fccqp_handle h, int warm) {
 }
 int fccqp_set_structure(fccqp_handle h, int structure) {
   if (!h) return fail(FCCQP_E_INVALID, "null handle");
-  const int mode = structure & ~FCCQP_STRUCTURE_REFINE;
+  const int mode = structure & ~(FCCQP_STRUCTURE_REFINE | FCCQP_SCHEDULE_LPT);
   if (mode != FCCQP_STRUCTURE_AUTO && mode != FCCQP_STRUCTURE_DENSE)
     return fail(FCCQP_E_INVALID, "structure must be FCCQP_STRUCTURE_AUTO or FCCQP_STRUCTURE_DENSE (optionally | FCCQP_STRUCTURE_REFINE)");
   h->structure = structure;

@@ -1731,6 +1731,18 @@ __global__ void __launch_bounds__(256) wbc_assemble_kernel(const WbcParams p) {
 // FP64 FMA peak of this device, measured (bench.py's roofline denominator): 8 independent DFMA chains per thread,
 // 4 x 256 threads per SM, no memory traffic.  2 * fmas / time is what the vector FP64 pipe (which the DMMA
 // instruction shares, profiles/r01_fp64_ubench.log) can do at the clocks of the moment.
+// Processing order for FCCQP_SCHEDULE_LPT: lanes whose earlier solve took >= `long_at` iterations first (from the front of
+// `order`), everybody else from the back; counters zeroed by the caller.  The order inside the two groups is whatever the
+// atomics give -- results do not depend on it.
+__global__ void __launch_bounds__(256) lpt_order_kernel(const int* __restrict__ prev_n_iter, const int B, const int long_at,
+                                                        int* __restrict__ order, unsigned int* __restrict__ n_long,
+                                                        unsigned int* __restrict__ n_short) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  if (prev_n_iter[i] >= long_at) order[atomicAdd(n_long, 1u)] = i;
+  else order[B - 1 - (int)atomicAdd(n_short, 1u)] = i;
+}
+
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, const int iters, const double seed) {
   double a[8];
 #pragma unroll

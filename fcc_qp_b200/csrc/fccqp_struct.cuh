@@ -880,13 +880,20 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
 
   // Work indices are fetched one QP ahead (thread 0 keeps the next one in a register): the atomic's round trip
   // hides behind the QP in flight, and the index is known early enough to pull that QP's data into L2.
+  // (p.index_list: a processing order -- FCCQP_SCHEDULE_LPT -- the queue slot is mapped through it, one QP ahead as well)
   int w_next = 0;
-  if (tid == 0) w_next = (int)atomicAdd(p.work_counter, 1u);
+  if (tid == 0) {
+    w_next = (int)atomicAdd(p.work_counter, 1u);
+    if (p.index_list && w_next < p.B) w_next = p.index_list[w_next];
+  }
   for (;;) {
     __syncthreads();  // previous QP fully retired (smem reuse) before taking new work
     if (tid == 0) {
       s_work[0] = w_next;
-      if (w_next < p.B) w_next = (int)atomicAdd(p.work_counter, 1u);
+      if (w_next < p.B) {
+        w_next = (int)atomicAdd(p.work_counter, 1u);
+        if (p.index_list && w_next < p.B) w_next = p.index_list[w_next];
+      }
     }
     __syncthreads();
     const int qp = s_work[0];

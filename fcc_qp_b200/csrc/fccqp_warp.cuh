@@ -78,7 +78,10 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) fccqp_warp_kernel(con
 
   for (;;) {
     int qp = 0;
-    if (lane == 0) qp = (int)atomicAdd(p.work_counter, 1u);
+    if (lane == 0) {
+      qp = (int)atomicAdd(p.work_counter, 1u);
+      if (p.index_list && qp < p.B) qp = p.index_list[qp];    // processing order (FCCQP_SCHEDULE_LPT)
+    }
     qp = __shfl_sync(kFullMask, qp, 0);
     if (qp >= p.B) break;
     const long long t_start = clock64();

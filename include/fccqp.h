@@ -183,9 +183,16 @@ typedef enum fccqp_precision { FCCQP_PRECISION_FP64 = 0, FCCQP_PRECISION_FP32_DA
  *                          walking log (smallest cost 1e-6) the reduced pre-solve alone is within 1.2e-7 relative on z
  *                          with identical iteration counts -- inside the 1e-6 bar, the default -- and the refined one
  *                          within 7e-11, the level of the general kernel, for about 25 % more time per cold QP.
- *                          Set it when costs far below 1e-6 are eliminated. */
+ *                          Set it when costs far below 1e-6 are eliminated.
+ *   FCCQP_SCHEDULE_LPT     flag, OR-ed into any of the above (FCCQP_MEM_DEVICE only): the n_iter array of the call HOLDS THE
+ *                          ITERATION COUNTS OF AN EARLIER SOLVE of the same lanes (a control loop re-solving a slowly changing
+ *                          batch into the same arrays).  Lanes that ran long then are pulled from the work queue first
+ *                          (longest-processing-time-first with the previous count as the prediction), so the few QPs that
+ *                          run to max_iter no longer finish after everything else: 5-8 % of a 2^16 launch on the walking
+ *                          log.  Only the ORDER in which QPs are processed changes, never a result. */
 typedef enum fccqp_structure {
-  FCCQP_STRUCTURE_AUTO = 0, FCCQP_STRUCTURE_DENSE = 1, FCCQP_STRUCTURE_CAPS = 2, FCCQP_STRUCTURE_REFINE = 256
+  FCCQP_STRUCTURE_AUTO = 0, FCCQP_STRUCTURE_DENSE = 1, FCCQP_STRUCTURE_CAPS = 2, FCCQP_STRUCTURE_REFINE = 256,
+  FCCQP_SCHEDULE_LPT = 512
 } fccqp_structure;
 
 typedef struct fccqp_batch_desc {

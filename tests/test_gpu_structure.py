@@ -171,3 +171,30 @@ def test_drop_in_object_uses_host_classification(walking_log):
         assert nat.last_struct_info()["used"]
         assert np.abs(sol.z - gold["z"][i]).max() / max(1.0, np.abs(gold["z"][i]).max()) <= 1e-6
         assert sol.details.n_iter == gold["n_iter"][i]
+
+
+def test_schedule_from_previous_changes_nothing_but_the_order(walking_log):
+    """FCCQP_SCHEDULE_LPT (lanes that ran long in the previous Solve are pulled from the work queue first): bit-identical
+    results with and without it, on the reduced, the general and the warp kernels; and after a change of the batch the stale
+    hint is still only a hint."""
+    import torch
+    from fcc_qp_b200.batch import FCCQPBatch, FCCQPOptionsB
+    from fcc_qp_b200.synthetic import random_qps
+    dev = torch.device("cuda:0")
+    small = random_qps(np.random.default_rng(9), 4096, 12, 6, 6, 3)
+    for qp, structure, opts in ((walking_log.tile(8192), "auto", LOG_OPTS), (walking_log.tile(8192), "dense", LOG_OPTS),
+                                (small, "auto", dict(max_iter=50, rho=1e-3, eps_fcone=1e-6, eps_bound=1e-6))):
+        args = [torch.as_tensor(a, device=dev) for a in (qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)]
+        out = []
+        for hint in (False, True):
+            s = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start); s.set_options(FCCQPOptionsB(**opts))
+            s.structure = structure
+            s.schedule_from_previous = hint
+            s.Solve(*args)                       # (no hint yet: the n_iter tensor is fresh)
+            s.Solve(*args)                       # hinted by the first solve
+            rolled = [torch.roll(a, 17, 0) if a.dim() > 1 or a.shape[0] == qp.batch else a for a in args]
+            s.Solve(*rolled)                     # the hint now points at the wrong lanes
+            sol = s.GetSolution()
+            torch.cuda.synchronize()
+            out.append((sol.z.clone(), sol.details.n_iter.clone(), sol.details.solve_status.clone()))
+        assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])

@@ -12,6 +12,7 @@ qp = load_walking_log().tile(B)
 dev = torch.device("cuda:0")
 args = [torch.as_tensor(a, device=dev) for a in (qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)]
 s = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start); s.set_options(FCCQPOptionsB(100, 5e-5, 1e-6, 1e-6))
+s.schedule_from_previous = bool(os.environ.get("LPT"))   # FCCQP_SCHEDULE_LPT from the second Solve on
 if mode == "warm":
     s.Solve(*args); s.set_warm_start(True)
 for r in range(reps):
