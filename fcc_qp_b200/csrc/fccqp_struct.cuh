@@ -813,6 +813,116 @@ __device__ __noinline__ double full_op_apply(const double* __restrict__ M, doubl
   return ci >= 0 ? out[ci] : 0.0;
 }
 
+// ---------------------------------------------------------------------------
+// The ADMM iterations of a long-running QP once the full-space operator F is in place (build_full_op), as ONE compact loop
+// with its own registers: x = x_base + F (rho w), z-update, dual update, exit test (fcc_qp.cpp:81-109; the same
+// arithmetic in the same order as the iteration body of the kernel -- results are bit-identical to taking these
+// iterations there).  Two block barriers per iteration instead of four: the z-update stores the operand rho w of the NEXT
+// product straight into the operand buffer (the contact lanes store the cone entries through cidx, variable -> class
+// order), the exit-test barrier publishes it; x stays in the product's output buffer in class order and the contact lanes
+// read it there.  1.3 % of the walking log's QPs and 17 % of the multi-contact set spend > 90 iterations here.
+// Returns the iteration at which the loop stopped; th.conv tells whether the exit test passed there.
+// ---------------------------------------------------------------------------
+struct OpLoopArgs {   // buffers as OFFSETS into the dynamic shared memory (doubles): pointers rebuilt from the extern array
+  int M, tbuf, xb, out, xs, lcbar, muc, vmu, ints, cidx;   // in the function are known to be shared (LDS / STS, not generic LD / ST)
+  int NBF, NF, nc, lcs, iter0, iters;
+  double shift, alpha, eps_fcone, eps_bound;
+};
+struct OpLoopThread {
+  double xbar, mux, lb, ub, x, rx, rc;
+  int ci, conv, nan_seen;
+};
+
+__device__ __noinline__ int full_op_loop(const OpLoopArgs& a, OpLoopThread& th, const bool is_x, const bool in_cone) {
+  const int t = threadIdx.x;
+  const int tb = t >> 3, tr = t & 7, tf = tr >> 1;
+  const int colo = tr & 1, colc = tr >> 1;
+  const int flip = tb & 1;
+  extern __shared__ __align__(16) double smem[];
+  const double* const M = smem + a.M;
+  double* const tbuf = smem + a.tbuf;
+  double* const out = smem + a.out;
+  double* const lcbar = smem + a.lcbar;
+  double* const muc = smem + a.muc;
+  int* const cidx = reinterpret_cast<int*>(smem + a.ints) + a.cidx;   // (cidx: offset in ints inside the int region)
+  const int NBF = a.NBF;
+  const bool row = t < a.NF;
+  const bool contact = t < a.nc / 3;
+  const bool relax = a.alpha != 1.0;
+  const double shift = a.shift, alpha = a.alpha;
+  const int ci = th.ci;
+  double xbar = th.xbar, mux = th.mux;
+  const double lb = th.lb, ub = th.ub;
+  const double xbt = row ? smem[a.xb + t] : 0.0;
+  const double mu_t = contact ? smem[a.vmu + t] : 0.0;
+  // operand of the first product, and the class-order index of every variable for the contact lanes
+  if (is_x) {
+    cidx[t] = ci;
+    tbuf[ci] = shift * (in_cone ? (lcbar[t - a.lcs] - muc[t - a.lcs]) : (xbar - mux));
+  }
+  __syncthreads();
+  int c0 = 0, c1 = 0, c2 = 0;
+  if (contact) { const int o = a.lcs + 3 * t; c0 = cidx[o]; c1 = cidx[o + 1]; c2 = cidx[o + 2]; }
+  const double* const lrow = M + tile_off(tb, 0) + tr * 8;
+  double val = 0.0, rx = 0.0, rc = 0.0;
+  int iter = a.iter0, conv = 0, nan_seen = 0;
+#pragma unroll 1
+  for (;; ++iter) {
+    if (row) {   // row t of the symmetric F: tiles left of the diagonal by rows, below it by columns (full_op_apply)
+      double s0 = 0.0, s1 = 0.0;
+      int jb = 0;
+#pragma unroll 1
+      for (; jb + 1 <= tb; jb += 2) {
+        s0 += row_dot8(lrow + 64 * jb, tf, tbuf + jb * 8);
+        s1 += row_dot8(lrow + 64 * jb + 64, tf, tbuf + jb * 8 + 8);
+      }
+      if (jb <= tb) s0 += row_dot8(lrow + 64 * jb, tf, tbuf + jb * 8);
+      int ib = tb + 1;
+#pragma unroll 1
+      for (; ib + 1 < NBF; ib += 2) {
+        s0 += col_dot8(M + tile_off(ib, tb) + colo, colc, flip, tbuf + ib * 8);
+        s1 += col_dot8(M + tile_off(ib + 1, tb) + colo, colc, flip, tbuf + ib * 8 + 8);
+      }
+      if (ib < NBF) s0 += col_dot8(M + tile_off(ib, tb) + colo, colc, flip, tbuf + ib * 8);
+      out[t] = xbt + (s0 + s1);
+    }
+    __syncthreads();
+    rx = 0.0; rc = 0.0;
+    if (is_x) {
+      val = out[ci];
+      const double xh = relax ? fma(alpha, val, (1.0 - alpha) * xbar) : val;
+      const double xb = clampd(xh + mux, lb, ub);
+      xbar = xb;
+      const double rr = xh - xb;
+      mux += rr;
+      rx = fabs(rr);
+      if (!in_cone) tbuf[ci] = shift * (xbar - mux);
+    }
+    if (contact) {
+      double x0 = out[c0], x1 = out[c1], x2 = out[c2];
+      if (relax) {
+        x0 = fma(alpha, x0, (1.0 - alpha) * lcbar[3 * t]);
+        x1 = fma(alpha, x1, (1.0 - alpha) * lcbar[3 * t + 1]);
+        x2 = fma(alpha, x2, (1.0 - alpha) * lcbar[3 * t + 2]);
+      }
+      double o0, o1, o2;
+      project_cone3(x0 + muc[3 * t], x1 + muc[3 * t + 1], x2 + muc[3 * t + 2], mu_t, o0, o1, o2);
+      lcbar[3 * t] = o0; lcbar[3 * t + 1] = o1; lcbar[3 * t + 2] = o2;
+      const double r0 = x0 - o0, r1 = x1 - o1, r2 = x2 - o2;
+      const double m0 = muc[3 * t] + r0, m1 = muc[3 * t + 1] + r1, m2 = muc[3 * t + 2] + r2;
+      muc[3 * t] = m0; muc[3 * t + 1] = m1; muc[3 * t + 2] = m2;
+      rc = fmax(fabs(r0), fmax(fabs(r1), fabs(r2)));
+      tbuf[c0] = shift * (o0 - m0); tbuf[c1] = shift * (o1 - m1); tbuf[c2] = shift * (o2 - m2);
+    }
+    if (rx != rx || rc != rc) nan_seen = 1;
+    conv = __syncthreads_and((rc < a.eps_fcone) && (rx < a.eps_bound));   // fcc_qp.cpp:105-109
+    if (conv || iter + 1 == a.iters) break;
+  }
+  if (is_x) smem[a.xs + t] = val;   // the epilogue reads the cone variables from xs (behind its barrier)
+  th.xbar = xbar; th.mux = mux; th.x = val; th.rx = rx; th.rc = rc; th.conv = conv; th.nan_seen = nan_seen;
+  return iter;
+}
+
 #ifdef FCCQP_DEV
 #define SPROF(slot)                                                        \
   do {                                                                     \
@@ -1237,6 +1347,28 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) fccqp_struct_kernel(cons
           block_reduce2<false>(rx, rc, red, parity);
           res_x = rx; res_c = rc;
           if (conv) { n_iter = iter; SPROF(8); break; }
+        } else if (!kAdapt && kThreads > 64 && full_op) {
+          // every further iteration of this QP in the compact operator loop (full_op_loop).  Not in the two-warp instance:
+          // a barrier between two warps costs little, and the call cost that instance 3.5 % on the quadruped shape
+          // (profiles/r02_op_loop_ab.log).
+          OpLoopArgs oa;
+          oa.M = (int)(M - smem); oa.tbuf = L.off_tbuf; oa.xb = L.off_ybuf; oa.out = L.off_sred; oa.xs = (int)(xs - smem);
+          oa.lcbar = L.off_lcbar; oa.muc = L.off_muc; oa.vmu = L.off_mu;
+          oa.ints = L.off_int; oa.cidx = L.io_colk;          // (the front end is done with colk)
+          oa.NBF = NBF; oa.NF = NF; oa.nc = nc; oa.lcs = lcs; oa.iter0 = iter + 1; oa.iters = iters;
+          oa.shift = shift; oa.alpha = p.alpha; oa.eps_fcone = p.eps_fcone; oa.eps_bound = p.eps_bound;
+          OpLoopThread th;
+          th.xbar = v_xbar; th.mux = v_mux; th.lb = v_lb; th.ub = v_ub; th.x = v_x; th.ci = ci;
+          const int it_end = full_op_loop(oa, th, is_x, in_cone);
+          v_xbar = th.xbar; v_mux = th.mux;
+          if (is_x) v_x = th.x;
+          if (th.nan_seen) status_flag = 2;
+          rx = th.rx; rc = th.rc;
+          block_reduce2<false>(rx, rc, red, parity);
+          res_x = rx; res_c = rc;
+          if (th.conv) n_iter = it_end;
+          SPROF(8);
+          break;
         } else if (kAdapt && p.adapt_k > 0 && (iter + 1) % p.adapt_k == 0) {
           // adaptive rho (extension; fccqp_kernel.cuh, oracle/fccqp_oracle.c do_admm): rebalance, rescale the scaled duals,
           // and have the reduced rho-KKT system (h = q + rho of every eliminated variable included) assembled and
