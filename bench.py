@@ -216,7 +216,21 @@ def shape_extras(dev):
             it = s.GetSolution().details.n_iter.cpu().numpy()
             small[f"n{sn}_m{sm}"] = {"n": sn, "m": sm, "nc": snc, "batch": B, "ms": 1e3 * best, "qps": B / best,
                                      "mean_iterations": float(it.mean()), "launch": nat.last_launch_info()}
+            # FCCQP_PRECISION_FP32: float32 data + FP32 arithmetic (stated bound in include/fccqp.h), same QPs
+            z64 = s.GetSolution().z[:4096].cpu().numpy()
+            args32 = [a.to(torch.float32) for a in args]
             del args, s
+            s = FCCQPBatch(sn, sm, snc, slcs, device=dev.index, precision="fp32")
+            s.set_options(FCCQPOptionsB(max_iter=15, rho=1e-3, eps_fcone=1e-4, eps_bound=1e-4))
+            best = 1e9
+            for _ in range(3):
+                s.Solve(*args32); torch.cuda.synchronize(dev)
+                best = min(best, s.GetSolution().details.device_time)
+            z32 = s.GetSolution().z[:4096].cpu().numpy()
+            err = np.abs(z32 - z64).max(axis=1) / np.maximum(1.0, np.abs(z64).max(axis=1))
+            small[f"n{sn}_m{sm}"]["fp32_arithmetic"] = {"ms": 1e3 * best, "qps": B / best, "z_rel_err_max_vs_fp64": float(err.max()),
+                                                        "launch": nat.last_launch_info()}
+            del args32, s
         out["small_qps_warp_kernel"] = small
     except Exception as e:  # pragma: no cover
         out["small_qps_warp_kernel"] = {"error": repr(e)}

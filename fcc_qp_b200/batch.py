@@ -78,9 +78,11 @@ class FCCQPBatch:
             self.device = int(device)
         # "fp64": the reference's arithmetic and data.  "fp32_data": Q, b, A_eq, b_eq, friction_coeffs, lb, ub
         # travel and are stored as float32 (half the PCIe / HBM bytes), arithmetic, state and outputs stay
-        # FP64 (FCCQP_PRECISION_FP32_DATA in include/fccqp.h; stated bound 2e-3 relative on z).
-        if precision not in ("fp64", "fp32_data"):
-            raise ValueError("precision must be 'fp64' or 'fp32_data'")
+        # FP64 (FCCQP_PRECISION_FP32_DATA in include/fccqp.h; stated bound 2e-3 relative on z).  "fp32": float32 data AND FP32
+        # arithmetic for problems with n + m <= 32 (the warp-per-QP kernel; FCCQP_PRECISION_FP32, stated bound 1e-3 relative
+        # on z at cond <= 1e4 and eps >= 1e-4); larger problems run as "fp32_data".
+        if precision not in ("fp64", "fp32_data", "fp32"):
+            raise ValueError("precision must be 'fp64', 'fp32_data' or 'fp32'")
         self.precision = precision
         self.options = FCCQPOptionsB()
         # Problem structure (include/fccqp.h, fccqp_structure): "auto" sizes the structure-exploiting kernel from a
@@ -172,7 +174,7 @@ class FCCQPBatch:
         d = nat.BatchDesc()
         d.abi_version = nat.ABI_VERSION
         d.batch, d.n, d.m, d.nc, d.lambda_c_start = B, self.n, self.m, self.nc, self.lcs
-        d.device, d.memory_space, d.precision = self.device, mem, (1 if self.precision == "fp32_data" else 0)
+        d.device, d.memory_space, d.precision = self.device, mem, {"fp64": 0, "fp32_data": 1, "fp32": 2}[self.precision]
         o = self.options
         d.options = nat.Options(int(o.max_iter), int(getattr(o, 'adapt_rho_interval', 0)), float(o.rho), float(o.eps_fcone), float(o.eps_bound), float(o.relaxation))
         st = self.structure
@@ -226,7 +228,7 @@ class FCCQPBatch:
 
     def _solve_numpy(self, Q, b, A_eq, b_eq, mu, lb, ub):
         import time
-        in_dtype = np.float32 if self.precision == "fp32_data" else np.float64
+        in_dtype = np.float64 if self.precision == "fp64" else np.float32
         f = lambda a: np.ascontiguousarray(a, dtype=in_dtype)
         Q, b, A_eq, b_eq, mu, lb, ub = map(f, (Q, b, A_eq, b_eq, mu, lb, ub))
         if Q.ndim not in (2, 3):
@@ -293,7 +295,7 @@ class FCCQPBatch:
         if dev.type != "cuda":
             raise ValueError("torch inputs must be CUDA tensors (no CPU solve path); pass numpy arrays for host data")
         self.device = dev.index if dev.index is not None else torch.cuda.current_device()
-        in_dtype = torch.float32 if self.precision == "fp32_data" else torch.float64
+        in_dtype = torch.float64 if self.precision == "fp64" else torch.float32
         t = lambda a: a if (_is_torch(a) and a.dtype == in_dtype and a.device == dev) else \
             torch.as_tensor(a, dtype=in_dtype, device=dev)
         Q, b, A_eq, b_eq, mu, lb, ub = map(t, (Q, b, A_eq, b_eq, mu, lb, ub))

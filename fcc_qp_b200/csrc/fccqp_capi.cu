@@ -195,11 +195,12 @@ bool host_classify(int n, int m, const double* Q, long long q_rs, long long q_cs
 
 // Small problems (n + m <= 32): one QP per warp (fccqp_warp.cuh), four warps per CTA, each pulling QPs from the work
 // counter on its own; shared memory per CTA = 4 private (n + m) x ((n + m) | 1) slabs.
-int launch_warp(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream) {
+// f32: the FP32 arithmetic instance (FCCQP_PRECISION_FP32: float32 problem data, float slabs).
+int launch_warp(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool f32 = false, bool lpt_hint = false) {
   constexpr int kW = 4;
   const int N = p.n + p.m;
-  const size_t smem = (size_t)kW * N * (N | 1) * sizeof(double);
-  KernelFn fn = (KernelFn)fccqp::fccqp_warp_kernel<kW, 6>;
+  const size_t smem = (size_t)kW * N * (N | 1) * (f32 ? sizeof(float) : sizeof(double));
+  KernelFn fn = f32 ? (KernelFn)fccqp::fccqp_warp_kernel<kW, 6, float> : (KernelFn)fccqp::fccqp_warp_kernel<kW, 6, double>;
   // (measured, tools/bench_small.py: 6 CTAs x 4 warps at 80 registers beats 8 x 4 at 64 and 4 x 4 at 128 on every shape but n = 6)
   int ctas_per_sm = 0;
   {
@@ -219,9 +220,16 @@ int launch_warp(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream) {
   int grid = ctas_per_sm * ctx.num_sms;
   if (grid > (p.B + kW - 1) / kW) grid = (p.B + kW - 1) / kW;
   unsigned int* scr = nullptr;   // the work counter of this call (stream-ordered: any number of calls may be in flight)
-  CUDA_TRY(cudaMallocAsync(&scr, 8 * sizeof(unsigned int), stream));
+  const bool lpt = lpt_hint && p.n_iter != nullptr && p.B >= 2 * kW * ctas_per_sm * ctx.num_sms;
+  CUDA_TRY(cudaMallocAsync(&scr, (8 + (lpt ? (size_t)p.B : 0)) * sizeof(unsigned int), stream));
   CUDA_TRY(cudaMemsetAsync(scr, 0, 8 * sizeof(unsigned int), stream));
   p.work_counter = scr;
+  if (lpt) {   // FCCQP_SCHEDULE_LPT: [8, 8 + B) the processing order, its two counters in [4], [5]
+    int* const order = reinterpret_cast<int*>(scr + 8);
+    fccqp::lpt_order_kernel<<<(p.B + 255) / 256, 256, 0, stream>>>(p.n_iter, p.B, p.full_inverse_at, order, scr + 4, scr + 5);
+    CUDA_TRY(cudaGetLastError());
+    p.index_list = order;
+  }
   fn<<<grid, 32 * kW, smem, stream>>>(p);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaFreeAsync(scr, stream));
@@ -237,13 +245,15 @@ int launch_warp(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream) {
 
 // Launches the fused solve on `stream` for device-resident data described by p
 // (work counters / device-side lists are allocated here, stream-ordered).
-int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool in_f32 = false,
+// precision: fccqp_precision of the call (FP32_DATA and FP32: float32 problem data behind the pointers of p; FP32: FP32
+// arithmetic too where a kernel for it exists -- the warp kernel -- and FP32_DATA's FP64 arithmetic otherwise)
+int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, int precision = FCCQP_PRECISION_FP64,
                  const StructHint* hint_in = nullptr) {
   if (p.B == 0) return FCCQP_OK;
   KernelFn fn, fn_shared, fn_f32; int threads; size_t smem;
   int rc = pick_kernel(ctx, p.n, p.m, p.nc, &fn, &threads, &smem, &fn_shared, &fn_f32, p.adapt_k > 0);
   if (rc) return rc;
-  const bool f32 = in_f32;
+  const bool f32 = precision != FCCQP_PRECISION_FP64;
   if (f32) fn = fn_f32;   // float32 problem data: same launch geometry, widening stage-in
   p.lay = fccqp::Layout(p.n, p.m, p.nc);
   // developer switch: FCCQP_FIRST_UPDATE_IDENTITY=0 solves the (mathematically redundant) first x-update of cold QPs
@@ -259,7 +269,9 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool
   p.struct_bulk = getenv("FCCQP_STRUCT_BULK") ? atoi(getenv("FCCQP_STRUCT_BULK")) : 1;
   // problem-size-specialised mapping: a QP whose KKT matrix fits one row per lane goes to the warp-per-QP kernel
   // (FCCQP_NO_WARP=1: the CTA-per-QP kernels, for A/B tests)
-  if (!f32 && p.n + p.m <= 32 && !getenv("FCCQP_NO_WARP")) return launch_warp(ctx, p, stream);
+  const bool lpt_hint = hint_in && hint_in->lpt;
+  if (!f32 && p.n + p.m <= 32 && !getenv("FCCQP_NO_WARP")) return launch_warp(ctx, p, stream, false, lpt_hint);
+  if (precision == FCCQP_PRECISION_FP32 && p.n + p.m <= 32) return launch_warp(ctx, p, stream, true, lpt_hint);
   auto occupancy_of = [&](KernelFn f, int thr, size_t sm, int* out) -> int {
     std::lock_guard<std::mutex> lk(ctx.mu);
     const auto key = std::make_pair((const void*)f, sm);
@@ -782,7 +794,7 @@ int fccqp_solve(fccqp_handle h, const double* Q, ptrdiff_t q_rs, ptrdiff_t q_cs,
   if (want_struct && m > 0 &&
       host_classify(n, m, sQ, n, 1, sA, k_a_rs, k_a_cs, &hint.caps[0], &hint.caps[1], &hint.caps[2]))
     hint.mode = FCCQP_STRUCTURE_CAPS;
-  int rc = launch_solve(*h->ctx, p, h->stream, false, &hint);
+  int rc = launch_solve(*h->ctx, p, h->stream, FCCQP_PRECISION_FP64, &hint);
   if (rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(h->h_out, h->d_x, sizeof(double) * (n + 8), cudaMemcpyDeviceToHost, h->stream));   // packed outputs
   CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -834,7 +846,7 @@ static void host_struct_hint(const fccqp_batch_desc& d, StructHint* out) {
   const bool q_shared = d.q_batch_stride == 0, a_shared = d.a_batch_stride == 0;
   if (hint.mode == FCCQP_STRUCTURE_AUTO) {
     hint.mode = FCCQP_STRUCTURE_DENSE;
-    if (d.precision != FCCQP_PRECISION_FP32_DATA && m > 0 && !(q_shared && a_shared) && B > 0) {
+    if (d.precision == FCCQP_PRECISION_FP64 && m > 0 && !(q_shared && a_shared) && B > 0) {
       const int ns = B < 64 ? B : 64;
       bool ok = true;
       for (int sidx = 0; sidx < ns && ok; ++sidx) {
@@ -872,8 +884,8 @@ static int validate_desc(const fccqp_batch_desc* d) {
   if (rc) return rc;
   rc = check_options(d->options);
   if (rc) return rc;
-  if (d->precision != FCCQP_PRECISION_FP64 && d->precision != FCCQP_PRECISION_FP32_DATA)
-    return fail(FCCQP_E_UNSUPPORTED, "precision must be FCCQP_PRECISION_FP64 or FCCQP_PRECISION_FP32_DATA");
+  if (d->precision != FCCQP_PRECISION_FP64 && d->precision != FCCQP_PRECISION_FP32_DATA && d->precision != FCCQP_PRECISION_FP32)
+    return fail(FCCQP_E_UNSUPPORTED, "precision must be FCCQP_PRECISION_FP64, FCCQP_PRECISION_FP32_DATA or FCCQP_PRECISION_FP32");
   if (d->memory_space != FCCQP_MEM_HOST && d->memory_space != FCCQP_MEM_DEVICE)
     return fail(FCCQP_E_INVALID, "bad memory_space");
   if (d->batch == 0) return FCCQP_OK;
@@ -920,7 +932,7 @@ int fccqp_batch_solve(const fccqp_batch_desc* desc) {
       CUDA_TRY(cudaEventCreate(&ev1));
       CUDA_TRY(cudaEventRecord(ev0, st));
     }
-    rc = launch_solve(*ctx, p, st, d.precision == FCCQP_PRECISION_FP32_DATA, &hint);
+    rc = launch_solve(*ctx, p, st, d.precision, &hint);
     if (rc) { if (ev0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); } return rc; }
     if (d.device_seconds) {
       float ms = 0.f;
@@ -979,7 +991,7 @@ int fccqp_batch_solve(const fccqp_batch_desc* desc) {
   cudaStream_t s0 = ctx->streams[0];
   // problem data are float32 in FCCQP_PRECISION_FP32_DATA (es = 4): half the bytes over PCIe; the staging
   // segments keep their FP64 size, state and outputs are always FP64
-  const size_t es = d.precision == FCCQP_PRECISION_FP32_DATA ? sizeof(float) : sizeof(double);
+  const size_t es = d.precision != FCCQP_PRECISION_FP64 ? sizeof(float) : sizeof(double);
   auto h2d_shared = [&](const Seg& s, const double* src) -> int {
     if (s.shared && s.per_qp && src)
       CUDA_TRY(cudaMemcpyAsync(dp(s), src, s.per_qp * es, cudaMemcpyHostToDevice, s0));
@@ -1060,7 +1072,7 @@ int fccqp_batch_solve(const fccqp_batch_desc* desc) {
     p.n_iter = d_niter + lo; p.status = d_status + lo;
     double* res = dp(sres);
     p.res_b = res + lo; p.res_f = res + (size_t)B + lo; p.bviol = res + 2 * (size_t)B + lo; p.fviol = res + 3 * (size_t)B + lo;
-    rc = launch_solve(*ctx, p, st, es == sizeof(float), &hint);
+    rc = launch_solve(*ctx, p, st, d.precision, &hint);
     if (rc) return rc;
     // D2H: straight into the caller's buffer when it is page-locked (a true asynchronous DMA);
     // otherwise into the pinned bounce buffer, copied out below once the chunk's event has fired
@@ -1150,7 +1162,7 @@ int fccqp_batch_solve_multi(const fccqp_batch_desc* desc, const int32_t* devices
     s.device_seconds = nullptr;
     s.structure = mh.mode | (mh.refine ? FCCQP_STRUCTURE_REFINE : 0);
     s.struct_caps[0] = mh.caps[0]; s.struct_caps[1] = mh.caps[1]; s.struct_caps[2] = mh.caps[2];
-    const size_t es = d.precision == FCCQP_PRECISION_FP32_DATA ? sizeof(float) : sizeof(double);
+    const size_t es = d.precision != FCCQP_PRECISION_FP64 ? sizeof(float) : sizeof(double);
     auto adv = [&](const double* p, int64_t stride) -> const double* {   // problem data: element size es
       return p ? reinterpret_cast<const double*>(reinterpret_cast<const char*>(p) + (size_t)lo * (size_t)stride * es) : p;
     };

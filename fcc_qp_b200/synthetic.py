@@ -214,3 +214,12 @@ def random_qps(rng, B, n, m, nc, lcs):
     mu = rng.uniform(0.3, 1.0, (B, max(nc // 3, 0)))
     c = np.ascontiguousarray
     return QPBatch(n, m, nc, lcs, c(Q), c(b), c(A), c(beq), c(mu), c(lb), c(ub))
+
+
+def scale_constraint_rows(qp, rng, spread):
+    """The same QPs with every row of A_eq (and b_eq) scaled by 10^u, u uniform in [-spread, spread]: the solutions do not
+    change, the conditioning of the KKT matrix does (FP32-mode accuracy against conditioning, tools/fp32_run.py)."""
+    from .logdata import QPBatch
+    sc = 10.0 ** rng.uniform(-spread, spread, (qp.batch, qp.m))
+    return QPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start, qp.Q, qp.b, np.ascontiguousarray(qp.A_eq * sc[:, :, None]),
+                   np.ascontiguousarray(qp.b_eq * sc), qp.friction_coeffs, qp.lb, qp.ub)

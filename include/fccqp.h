@@ -160,8 +160,22 @@ typedef enum fccqp_memory_space { FCCQP_MEM_HOST = 0, FCCQP_MEM_DEVICE = 1 } fcc
  * state and every output stay FP64.  Halves the bytes moved per QP (PCIe and HBM).  Stated bound: 2e-3
  * relative on z, 1e-5 relative on the objective (measured on the walking log: p50 1e-7, max 7.7e-4 on z --
  * the ill-conditioned, nearly cost-free force directions -- and 1e-8 on the objective; iteration counts
- * unchanged). */
-typedef enum fccqp_precision { FCCQP_PRECISION_FP64 = 0, FCCQP_PRECISION_FP32_DATA = 1 } fccqp_precision;
+ * unchanged).
+ * FCCQP_PRECISION_FP32: float32 problem data as above AND FP32 ARITHMETIC -- KKT matrix, factorization, solves,
+ * projections, duals, residuals and the exit test all in float -- where a kernel for it exists: problems with
+ * n + m <= 32 (the warp-per-QP kernel).  Larger problems run as FCCQP_PRECISION_FP32_DATA (FP64 arithmetic): plain
+ * FP32 factors lose the answers of whole-body QPs at cond ~ 1e8.  Warm state and outputs stay
+ * FP64 arrays.  Stated bound: 1e-4 relative on z (max |dz| / max(1, max |z|)) and on the objective against the
+ * FP64 reference for problems whose rho-KKT matrix [[Q + rho I, A'], [A, 0]] has cond <= 1e3, with tolerances eps_fcone,
+ * eps_bound >= 1e-4 (the exit test cannot resolve residuals below ~1e-6 |x| in float).  Measured on random QPs
+ * (profiles/r02_fp32_mode.jsonl): max 2.7e-5 on z, 9.3e-5 on the objective at cond <= 80, max 6.9e-6 on z at
+ * 1e2 < cond <= 1e3 (rows of A_eq scaled apart), same status and iteration count for every QP; 1.5-1.9 x the FP64 rate.
+ * Beyond cond ~ 1e3 the float factorization of the pre-solve system breaks down on some QPs (it squares the conditioning
+ * of A_eq): most of those are reported as FCCQP_STATUS_NUMERICAL_ISSUE by the pivot test, NOT all -- use FP32_DATA or
+ * FP64 there. */
+typedef enum fccqp_precision {
+  FCCQP_PRECISION_FP64 = 0, FCCQP_PRECISION_FP32_DATA = 1, FCCQP_PRECISION_FP32 = 2
+} fccqp_precision;
 
 /* Problem structure.  Whole-body-control QPs are mostly made of variables that enter the
  * cost only through their own square (torques, constraint forces, slacks: diagonal-only rows of Q).  The

@@ -111,6 +111,10 @@ def test_batch_argument_checks():
         s.set_rho(0.0)
     with pytest.raises(ValueError):
         s.set_max_iter(0)
+    with pytest.raises(ValueError):
+        FCCQPBatch(6, 0, 6, 0, precision="fp16")
+    for prec, code in (("fp64", 0), ("fp32_data", 1), ("fp32", 2)):     # fccqp_precision of include/fccqp.h
+        assert FCCQPBatch(6, 0, 6, 0, precision=prec)._desc(1, 0).precision == code
 
 
 def test_compact_log_roundtrip(tmp_path, walking_log):

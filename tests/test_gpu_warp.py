@@ -126,3 +126,51 @@ def test_dropin_object_on_small_problems_takes_the_warp_kernel():
     s.set_warm_start(True)
     s.Solve(kats["eq_Q"], kats["eq_b"], kats["eq_A"], kats["eq_beq"], [], -inf12, inf12)
     assert np.abs(s.GetSolution().z - kats["eq_z"]).max() <= 1e-9 * max(1.0, np.abs(kats["eq_z"]).max())
+
+
+@pytest.mark.parametrize("n,m,nc,lcs", [(6, 3, 3, 3), (12, 6, 6, 3), (24, 8, 6, 0), (32, 0, 12, 20)])
+def test_fp32_arithmetic_mode_within_its_stated_bound(n, m, nc, lcs):
+    """FCCQP_PRECISION_FP32 (include/fccqp.h): float32 problem data and FP32 arithmetic on the warp kernel.  Stated bound:
+    1e-4 relative on z and on the objective against the FP64 reference (here: its pinned C restatement on the ORIGINAL
+    double data) for QPs whose rho-KKT matrix has cond <= 1e3, eps >= 1e-4; same status.  Checked on the random set
+    (cond <= 80) and on the same QPs with the rows of A_eq scaled apart (cond up to ~1e3: QPs beyond are left out)."""
+    from fcc_qp_b200 import _native as nat
+    from fcc_qp_b200.batch import FCCQPBatch, FCCQPOptionsB
+    from fcc_qp_b200.synthetic import scale_constraint_rows
+    opts = dict(max_iter=200, rho=1e-3, eps_fcone=1e-4, eps_bound=1e-4)
+    base = random_qps(np.random.default_rng(31 * n + m), 512, n, m, nc, lcs)
+    sets = [base] + ([scale_constraint_rows(base, np.random.default_rng(3), 1.0)] if m else [])
+    for qp in sets:
+        cond = np.empty(qp.batch)
+        for i in range(qp.batch):
+            K = np.zeros((n + m, n + m))
+            K[:n, :n] = qp.Q[i] + opts["rho"] * np.eye(n); K[n:, :n] = qp.A_eq[i]; K[:n, n:] = qp.A_eq[i].T
+            cond[i] = np.linalg.cond(K)
+        ok = cond <= 1e3
+        assert ok.mean() > 0.5
+        ref = oracle.Oracle("port").solve_batch(qp, warm_mode=0, nthreads=8, **opts)
+        s = FCCQPBatch(n, m, nc, lcs, precision="fp32"); s.set_options(FCCQPOptionsB(**opts))
+        s.Solve(qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)
+        sol = s.GetSolution()
+        assert nat.last_launch_info()["smem_bytes"] == 4 * (n + m) * ((n + m) | 1) * 4      # float slabs: the FP32 instance ran
+        err = np.abs(sol.z - ref["z"]).max(axis=1) / np.maximum(1.0, np.abs(ref["z"]).max(axis=1))
+        assert err[ok].max() <= 1e-4, err[ok].max()
+        obj = lambda z: 0.5 * np.einsum("bi,bij,bj->b", z, qp.Q, z) + np.einsum("bi,bi->b", qp.b, z)
+        oerr = np.abs(obj(sol.z) - obj(ref["z"])) / np.maximum(1.0, np.abs(obj(ref["z"])))
+        assert oerr[ok].max() <= 1e-4, oerr[ok].max()
+        assert np.array_equal(sol.details.solve_status[ok], ref["status"][ok])
+        assert (sol.details.n_iter[ok] == ref["n_iter"][ok]).mean() >= 0.98
+
+
+def test_fp32_mode_on_a_large_problem_runs_as_fp32_data(walking_log):
+    """n + m > 32: no FP32-arithmetic kernel; FCCQP_PRECISION_FP32 then means float32 data with FP64 arithmetic, bit for bit
+    the result of FCCQP_PRECISION_FP32_DATA."""
+    from fcc_qp_b200.batch import FCCQPBatch, FCCQPOptionsB
+    qp = walking_log.take(np.arange(64))
+    out = []
+    for prec in ("fp32", "fp32_data"):
+        s = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start, precision=prec)
+        s.set_options(FCCQPOptionsB(100, 5e-5, 1e-6, 1e-6))
+        s.Solve(qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)
+        out.append(s.GetSolution())
+    assert np.array_equal(out[0].z, out[1].z) and np.array_equal(out[0].details.n_iter, out[1].details.n_iter)
