@@ -34,3 +34,10 @@ if shape not in ("walking", "odd"):
 s3 = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start, precision="fp32_data"); s3.set_options(FCCQPOptionsB(100, 5e-5, 1e-6, 1e-6))
 s3.Solve(qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)
 print("fp32_data", shape, "QPs", qp.batch, np.unique(s3.GetSolution().details.n_iter, return_counts=True)[1][:3])
+# FP32 arithmetic (warp kernel, float instance) where it exists
+if qp.n + qp.m <= 32:
+    s4 = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start, precision="fp32"); s4.set_options(FCCQPOptionsB(100, 5e-5, 1e-4, 1e-4))
+    s4.Solve(qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)
+    s4.set_warm_start(True)
+    s4.Solve(qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)
+    print("fp32", shape, "QPs", qp.batch, np.unique(s4.GetSolution().details.n_iter, return_counts=True)[1][:3])
