@@ -201,7 +201,8 @@ int launch_warp(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, bool 
   const int N = p.n + p.m;
   const size_t smem = (size_t)kW * N * (N | 1) * (f32 ? sizeof(float) : sizeof(double));
   KernelFn fn = f32 ? (KernelFn)fccqp::fccqp_warp_kernel<kW, 6, float> : (KernelFn)fccqp::fccqp_warp_kernel<kW, 6, double>;
-  // (measured, tools/bench_small.py: 6 CTAs x 4 warps at 80 registers beats 8 x 4 at 64 and 4 x 4 at 128 on every shape but n = 6)
+  // (measured, tools/bench_small.py: 6 CTAs x 4 warps at 80 registers beats 8 x 4 at 64 and 4 x 4 at 128 on every shape but n = 6;
+  //  float instance, tools/fp32_occ.py: 6 / 8 / 10 / 12 CTAs -> 82.7 / 78.5 / 71.4 / 70.5 M QP/s at n = 6, 22.4 / 23.1 / 21.1 / 21.7 at n = 24)
   int ctas_per_sm = 0;
   {
     std::lock_guard<std::mutex> lk(ctx.mu);

@@ -22,3 +22,7 @@ ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum 
 python tools/bench_small.py > gpurun_out/r2_small.jsonl 2>/dev/null
 FCCQP_NO_WARP=1 python tools/bench_small.py >> gpurun_out/r2_small.jsonl 2>/dev/null
 cat gpurun_out/r2_pytest.log gpurun_out/r2_bench.json gpurun_out/r2_bench_ref.json; tail -3 gpurun_out/r2_dram65536.csv
+# processing order from the previous solve (FCCQP_SCHEDULE_LPT) against the default order, same process conditions
+python tools/prof_run.py 65536 5 cold 2>&1 | tail -3 > gpurun_out/r2_lpt.log
+LPT=1 python tools/prof_run.py 65536 5 cold 2>&1 | tail -3 >> gpurun_out/r2_lpt.log
+cat gpurun_out/r2_lpt.log
