@@ -272,6 +272,33 @@ def shape_extras(dev):
         del args, s, qp
     except Exception as e:  # pragma: no cover
         out["walking_log_schedule_from_previous"] = {"error": repr(e)}
+    # opt-in solution polish (FCCQPBatch.Polish: active-set guess + one more batched KKT solve + acceptance tests) on the headline
+    # workload: time of the polish step next to the solve, accepted fraction, friction-cone violation of the QPs that ended at
+    # max_iter before / after
+    try:
+        log = load_walking_log()
+        qp = log.take(np.arange(1 << 16) % log.batch)
+        args = [torch.as_tensor(a, device=dev) for a in (qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)]
+        s = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start, device=dev.index); s.set_options(FCCQPOptionsB(**OPTS))
+        s.Solve(*args); s.Polish(); torch.cuda.synchronize(dev)            # warm-up (allocations, structure probe of the inner solver)
+        best = 1e9
+        for _ in range(3):
+            s.Solve(*args); torch.cuda.synchronize(dev)
+            a = s.GetSolution()
+            fv0, st0 = a.details.friction_cone_viol.clone(), a.details.solve_status.clone()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); pz = s.Polish(); e1.record(); torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1) * 1e-3)
+        flag = pz.details.polished.bool()
+        late = flag & (st0 == 1)
+        out["walking_log_polish"] = {"batch": 1 << 16, "polish_ms": 1e3 * best, "accepted_fraction": float(flag.double().mean()),
+                                     "at_max_iter": int((st0 == 1).sum()), "at_max_iter_accepted": int(late.sum()),
+                                     "fcone_viol_max_before": float(fv0[late].max()) if bool(late.any()) else None,
+                                     "fcone_viol_max_after": float(pz.details.friction_cone_viol[late].max()) if bool(late.any()) else None,
+                                     "note": "extension (the reference has no polish step): not part of value / e2e"}
+        del args, s, qp
+    except Exception as e:  # pragma: no cover
+        out["walking_log_polish"] = {"error": repr(e)}
     # config 5: multi-contact humanoid, T = 32 sequential warm-started batches of 2^14 (b, b_eq drift 2 % per step)
     try:
         shp = syn.SHAPES["multicontact"]

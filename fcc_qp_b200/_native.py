@@ -88,6 +88,28 @@ class WbcDesc(C.Structure):
     ]
 
 
+class PolishDesc(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("batch", C.c_int32), ("n", C.c_int32), ("m", C.c_int32), ("nc", C.c_int32),
+        ("lambda_c_start", C.c_int32), ("device", C.c_int32), ("reserved", C.c_int32),
+        ("eps_fcone", C.c_double), ("eps_bound", C.c_double), ("eps_objective", C.c_double),
+        ("Q", C.c_void_p), ("q_batch_stride", C.c_int64),
+        ("b", C.c_void_p), ("b_batch_stride", C.c_int64),
+        ("A_eq", C.c_void_p), ("a_batch_stride", C.c_int64),
+        ("b_eq", C.c_void_p), ("beq_batch_stride", C.c_int64),
+        ("friction_coeffs", C.c_void_p), ("mu_batch_stride", C.c_int64),
+        ("lb", C.c_void_p), ("lb_batch_stride", C.c_int64),
+        ("ub", C.c_void_p), ("ub_batch_stride", C.c_int64),
+        ("x", C.c_void_p), ("mu_x", C.c_void_p), ("mu_lambda_c", C.c_void_p),
+        ("Qp", C.c_void_p), ("bp", C.c_void_p), ("Ap", C.c_void_p), ("beqp", C.c_void_p),
+        ("rot", C.c_void_p),
+        ("y", C.c_void_p), ("y_status", C.c_void_p),
+        ("z", C.c_void_p), ("bounds_viol", C.c_void_p), ("fcone_viol", C.c_void_p),
+        ("polished", C.c_void_p),
+        ("stream", C.c_void_p),
+    ]
+
+
 # every symbol include/fccqp.h declares (tests check that the library exports them all)
 EXPORTS = [
     "fccqp_default_options", "fccqp_last_error", "fccqp_abi_version", "fccqp_device_count",
@@ -97,6 +119,7 @@ EXPORTS = [
     "fccqp_release_workspaces", "fccqp_kernel_launch_count", "fccqp_last_launch_info",
     "fccqp_alloc_pinned", "fccqp_free_pinned", "fccqp_wbc_assemble",
     "fccqp_last_struct_info", "fccqp_set_structure", "fccqp_batch_solve_multi", "fccqp_measure_fp64_peak",
+    "fccqp_polish_prepare", "fccqp_polish_finish",
 ]
 
 _lib = None
@@ -137,6 +160,8 @@ def lib() -> C.CDLL:
     L.fccqp_alloc_pinned.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     L.fccqp_free_pinned.argtypes = [C.c_void_p]
     L.fccqp_wbc_assemble.argtypes = [C.POINTER(WbcDesc)]
+    L.fccqp_polish_prepare.argtypes = [C.POINTER(PolishDesc)]
+    L.fccqp_polish_finish.argtypes = [C.POINTER(PolishDesc)]
     _lib = L
     return L
 

@@ -45,6 +45,7 @@ class BatchDetails:
     solve_status: Any
     solve_time: float = 0.0          # host wall seconds of the whole batched call
     device_time: float = 0.0         # CUDA-event seconds of the solve kernel (device inputs) or staged call
+    polished: Any = None             # after Polish(): 1 where the polished point replaced the ADMM one, 0 where it was rejected
 
 
 @dataclasses.dataclass
@@ -371,6 +372,78 @@ class FCCQPBatch:
         cp = (lambda a: a) if self.zero_copy_outputs else (lambda a: a.clone())
         self._sol = BatchSolution(BatchDetails(cp(n_iter), cp(res[0]), cp(res[1]), cp(res[2]), cp(res[3]), cp(status),
                                                wall, secs.value), cp(x))
+
+
+    # ------------------------------------------------------------------
+    def Polish(self):
+        """Opt-in solution polish of the batch just solved (extension: NOT in the reference; include/fccqp.h,
+        fccqp_polish_prepare / _finish).  Device path only: call after ``Solve`` on torch CUDA tensors in FP64.  The active
+        set is guessed from the solver's state, the resulting equality-constrained QPs (same n, m) are solved by a second
+        batched launch (nc = 0, no bounds: the KKT solve), and a QP takes the polished point only if that solve succeeded
+        and the point satisfies every bound and friction cone to the solver's tolerances and is not worse in objective
+        than the ADMM iterate by more than ``polish_objective_slack`` (1e-3, relative).  Updates ``GetSolution()``:
+        ``z``, ``bounds_viol``, ``friction_cone_viol`` of the accepted QPs, ``details.polished`` [B] = 1 / 0; iteration
+        counts, residuals, status and the carried duals are left as the ADMM solve wrote them."""
+        import torch
+        if self._dev_out is None or getattr(self, "_keepalive", None) is None or self._sol is None or not _is_torch(self._sol.z):
+            raise RuntimeError("Polish() needs a preceding Solve() on torch CUDA tensors (device path)")
+        if self.precision != "fp64":
+            raise ValueError("Polish() is an FP64 path")
+        Q, b, A_eq, b_eq, mu, lb, ub = self._keepalive
+        ob = self._dev_out
+        n, m, nc = self.n, self.m, self.nc
+        B = ob["x"].shape[0]
+        dev = ob["x"].device
+        # dense row-major per QP (batch stride 0 = shared is fine)
+        dense = lambda a: a if (a.stride(-1) == 1 and a.stride(-2) == a.shape[-1]) or a.numel() == 0 else a.contiguous()
+        Q, A_eq = dense(Q), dense(A_eq)
+        pb = getattr(self, "_polish_buf", None)
+        if pb is None or pb["Qp"].shape[0] != B or pb["Qp"].device != dev:
+            f = lambda *s_: torch.empty(s_, dtype=torch.float64, device=dev)
+            pb = self._polish_buf = dict(Qp=f(B, n, n), bp=f(B, n), Ap=f(B, m, n), beqp=f(B, m), rot=f(B, max(nc // 3, 1), 4),
+                                         flag=torch.empty(B, dtype=torch.int32, device=dev),
+                                         inf_lo=torch.full((n,), -float("inf"), dtype=torch.float64, device=dev),
+                                         inf_hi=torch.full((n,), float("inf"), dtype=torch.float64, device=dev),
+                                         no_mu=torch.empty((0,), dtype=torch.float64, device=dev))
+            inner = FCCQPBatch(n, m, 0, 0, device=self.device)
+            inner.zero_copy_outputs = True
+            inner.time_kernel = False
+            inner.refine = True       # the polish is about accuracy: one refinement step of the reduced pre-solve (7e-11 instead of 1.2e-7)
+            pb["inner"] = inner
+        inner = pb["inner"]
+        inner.set_options(self.options)
+        inner.structure = self.structure if isinstance(self.structure, str) else "auto"
+        d = nat.PolishDesc()
+        d.abi_version = nat.ABI_VERSION
+        d.batch, d.n, d.m, d.nc, d.lambda_c_start, d.device = B, n, m, nc, self.lcs, self.device
+        d.eps_fcone, d.eps_bound = float(self.options.eps_fcone), float(self.options.eps_bound)
+        d.eps_objective = float(getattr(self, "polish_objective_slack", 1e-3))
+        bs = lambda a, full_ndim: int(a.stride(0)) if a.dim() == full_ndim else 0
+        d.Q, d.q_batch_stride = Q.data_ptr(), bs(Q, 3)
+        d.b, d.b_batch_stride = b.data_ptr(), bs(b, 2)
+        d.A_eq, d.a_batch_stride = A_eq.data_ptr(), bs(A_eq, 3)
+        d.b_eq, d.beq_batch_stride = b_eq.data_ptr(), bs(b_eq, 2)
+        d.friction_coeffs, d.mu_batch_stride = mu.data_ptr(), bs(mu, 2)
+        d.lb, d.lb_batch_stride = lb.data_ptr(), bs(lb, 2)
+        d.ub, d.ub_batch_stride = ub.data_ptr(), bs(ub, 2)
+        d.x, d.mu_x, d.mu_lambda_c = ob["x"].data_ptr(), ob["mux"].data_ptr(), ob["muc"].data_ptr()
+        d.Qp, d.bp, d.Ap, d.beqp, d.rot = (pb[k].data_ptr() for k in ("Qp", "bp", "Ap", "beqp", "rot"))
+        d.stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            nat.check(nat.lib().fccqp_polish_prepare(C.byref(d)))
+            inner.set_warm_start(False)
+            inner.Solve(pb["Qp"], pb["bp"], pb["Ap"], pb["beqp"], pb["no_mu"], pb["inf_lo"], pb["inf_hi"])
+            y = inner.GetSolution()
+            d.y, d.y_status = y.z.data_ptr(), y.details.solve_status.data_ptr()
+            res = ob["res"]
+            d.z, d.bounds_viol, d.fcone_viol = ob["x"].data_ptr(), res[2].data_ptr(), res[3].data_ptr()
+            d.polished = pb["flag"].data_ptr()
+            nat.check(nat.lib().fccqp_polish_finish(C.byref(d)))
+        cp = (lambda a: a) if self.zero_copy_outputs else (lambda a: a.clone())
+        det = self._sol.details
+        self._sol = BatchSolution(dataclasses.replace(det, bounds_viol=cp(res[2]), friction_cone_viol=cp(res[3]),
+                                                      polished=cp(pb["flag"])), cp(ob["x"]))
+        return self._sol
 
 
 class FCCQPBatchCpp:

@@ -22,6 +22,7 @@
 #include "fccqp_kernel.cuh"
 #include "fccqp_struct.cuh"
 #include "fccqp_warp.cuh"
+#include "fccqp_polish.cuh"
 
 namespace {
 
@@ -1241,6 +1242,66 @@ int fccqp_wbc_assemble(const fccqp_wbc_desc* d) {
   int grid = ctx->num_sms * 8;
   if (grid > d->batch) grid = d->batch;
   fccqp::wbc_assemble_kernel<<<grid, 256, smem, (cudaStream_t)d->stream>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return FCCQP_OK;
+}
+
+namespace {
+int polish_params(const fccqp_polish_desc* d, fccqp::PolishParams* out, DeviceCtx** ctx, bool finish) {
+  if (!d) return fail(FCCQP_E_INVALID, "desc is null");
+  if (d->abi_version != FCCQP_ABI_VERSION) return fail(FCCQP_E_INVALID, "abi_version %d != %d", d->abi_version, FCCQP_ABI_VERSION);
+  int rc = check_dims(d->n, d->m, d->nc, d->lambda_c_start);
+  if (rc) return rc;
+  if (d->batch < 0) return fail(FCCQP_E_INVALID, "batch < 0");
+  if ((rc = get_ctx(d->device, ctx))) return rc;
+  if (d->batch == 0) return FCCQP_OK;
+  if (!d->lb || !d->ub || !d->rot || (d->nc > 0 && !d->friction_coeffs))
+    return fail(FCCQP_E_INVALID, "null polish pointer (lb, ub, rot, friction_coeffs)");
+  if (!finish && (!d->Q || !d->b || (d->m > 0 && (!d->A_eq || !d->b_eq)) || !d->x || !d->mu_x || (d->nc > 0 && !d->mu_lambda_c) ||
+                  !d->Qp || !d->bp || (d->m > 0 && (!d->Ap || !d->beqp))))
+    return fail(FCCQP_E_INVALID, "null polish pointer (prepare needs the QP, x, mu_x, mu_lambda_c, Qp, bp, Ap, beqp)");
+  if (finish && (!d->Q || !d->b || (d->m > 0 && (!d->A_eq || !d->b_eq)) || !d->y || !d->y_status || !d->z || !d->bounds_viol || !d->fcone_viol || !d->polished))
+    return fail(FCCQP_E_INVALID, "null polish pointer (finish needs Q, b, A_eq, b_eq, y, y_status, z, bounds_viol, fcone_viol, polished)");
+  fccqp::PolishParams p{};
+  p.B = d->batch; p.n = d->n; p.m = d->m; p.nc = d->nc; p.lcs = d->lambda_c_start;
+  p.eps_fcone = d->eps_fcone; p.eps_bound = d->eps_bound; p.eps_objective = d->eps_objective;
+  p.Q = d->Q; p.q_bs = d->q_batch_stride; p.b = d->b; p.b_bs = d->b_batch_stride;
+  p.A = d->A_eq; p.a_bs = d->a_batch_stride; p.beq = d->b_eq; p.beq_bs = d->beq_batch_stride;
+  p.mu = d->friction_coeffs; p.mu_bs = d->mu_batch_stride;
+  p.lb = d->lb; p.lb_bs = d->lb_batch_stride; p.ub = d->ub; p.ub_bs = d->ub_batch_stride;
+  p.x = d->x; p.mu_x = d->mu_x; p.mu_c = d->mu_lambda_c;
+  p.Qp = d->Qp; p.bp = d->bp; p.Ap = d->Ap; p.beqp = d->beqp; p.rot = d->rot;
+  p.y = d->y; p.y_status = d->y_status; p.z = d->z; p.bviol = d->bounds_viol; p.fviol = d->fcone_viol; p.polished = d->polished;
+  *out = p;
+  return FCCQP_OK;
+}
+}  // namespace
+
+int fccqp_polish_prepare(const fccqp_polish_desc* d) {
+  fccqp::PolishParams p{};
+  DeviceCtx* ctx = nullptr;
+  int rc = polish_params(d, &p, &ctx, false);
+  if (rc || d->batch == 0) return rc;
+  CUDA_TRY(cudaSetDevice(d->device));
+  const size_t smem = (size_t)d->n * (5 * sizeof(double) + 3 * sizeof(int));
+  int grid = ctx->num_sms * 8;
+  if (grid > d->batch) grid = d->batch;
+  fccqp::polish_prepare_kernel<<<grid, 128, smem, (cudaStream_t)d->stream>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return FCCQP_OK;
+}
+
+int fccqp_polish_finish(const fccqp_polish_desc* d) {
+  fccqp::PolishParams p{};
+  DeviceCtx* ctx = nullptr;
+  int rc = polish_params(d, &p, &ctx, true);
+  if (rc || d->batch == 0) return rc;
+  CUDA_TRY(cudaSetDevice(d->device));
+  int grid = (d->batch + 3) / 4;
+  if (grid > ctx->num_sms * 16) grid = ctx->num_sms * 16;
+  fccqp::polish_finish_kernel<<<grid, 128, (size_t)4 * 2 * d->n * sizeof(double), (cudaStream_t)d->stream>>>(p);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
   return FCCQP_OK;

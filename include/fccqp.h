@@ -307,6 +307,55 @@ typedef struct fccqp_wbc_desc {
 
 int fccqp_wbc_assemble(const fccqp_wbc_desc* desc);
 
+/* ------------------------------------------------------------------------- *
+ * Opt-in solution polish.  NOT part of the reference: src/fcc_qp.cpp returns the ADMM iterate as it
+ * is (fccqp.pdf Table 2 lists polish among the OSQP features FCCQP lacks), so nothing here is covered by the parity bar.
+ * The active set is guessed from the solver's own state: a bounded variable outside the contact block with
+ * x + mu_x at or beyond a bound sits on it; a contact is classified by the branch of project_to_friction_cone
+ * (src/constraint_utils.cpp:5-25) its argument x_c + mu_c takes: inside (free), polar cone (lambda_c = 0), otherwise on the
+ * boundary, free in the tangent plane of the cone at the projection o (lambda_c = alpha o/|o| + beta t1, t1 the horizontal
+ * tangent; the plane leaves the cone only to second order in beta).  fccqp_polish_prepare writes the resulting
+ * equality-constrained QP -- SAME n and m: boundary contacts rotated into (alpha, beta, normal = 0), fixed variables decoupled
+ * with their coupling moved to the right-hand sides -- which the caller solves with fccqp_batch_solve as a QP with nc = 0 and
+ * infinite bounds (the pre-solve is the KKT solve, src/fcc_qp.cpp:159-178).  fccqp_polish_finish rotates that answer back
+ * and ACCEPTS it per QP only if the solve returned FCCQP_STATUS_SUCCESS, the point satisfies A_eq z = b_eq (1e-7 relative to
+ * the magnitude of the terms plus a rounding-level floor: a guess that fixes too much leaves an inconsistent system), every bound to eps_bound and
+ * every friction cone to eps_fcone, and its objective is not above the ADMM iterate's by more than eps_objective relative
+ * (f_p <= f_admm + eps_objective max(1, |f_admm|): a feasible point of a wrong guess is optimal for the wrong problem; the
+ * ADMM iterate's objective is a lower estimate of the optimum).  z, bounds_viol, fcone_viol of accepted QPs are overwritten,
+ * polished[i] = 1 / 0.
+ * Device memory only; Q / A_eq dense row-major per QP (batch strides in elements, 0 = shared).  Bounds on contact
+ * variables are not part of the guess (they still gate acceptance).  Python: FCCQPBatch.Polish().
+ * ------------------------------------------------------------------------- */
+typedef struct fccqp_polish_desc {
+  int32_t abi_version;
+  int32_t batch, n, m, nc, lambda_c_start;
+  int32_t device;
+  int32_t reserved;
+  double eps_fcone, eps_bound, eps_objective;
+  const double* Q;               int64_t q_batch_stride;     /* [B,n,n] */
+  const double* b;               int64_t b_batch_stride;
+  const double* A_eq;            int64_t a_batch_stride;     /* [B,m,n] */
+  const double* b_eq;            int64_t beq_batch_stride;
+  const double* friction_coeffs; int64_t mu_batch_stride;
+  const double* lb;              int64_t lb_batch_stride;
+  const double* ub;              int64_t ub_batch_stride;
+  const double* x;               /* [B,n]  ADMM result (prepare) */
+  const double* mu_x;            /* [B,n]  */
+  const double* mu_lambda_c;     /* [B,nc] */
+  double* Qp; double* bp; double* Ap; double* beqp;          /* polished QP, contiguous [B,n,n] [B,n] [B,m,n] [B,m] */
+  double* rot;                   /* [B, nc/3, 4] scratch written by prepare, read by finish */
+  const double* y;               /* [B,n]  solution of the polished QP (finish) */
+  const int32_t* y_status;       /* [B]    its status */
+  double* z;                     /* [B,n]  overwritten where accepted (may be the x array) */
+  double* bounds_viol; double* fcone_viol;                   /* [B] overwritten where accepted */
+  int32_t* polished;             /* [B] out */
+  void* stream;
+} fccqp_polish_desc;
+
+int fccqp_polish_prepare(const fccqp_polish_desc* desc);
+int fccqp_polish_finish(const fccqp_polish_desc* desc);
+
 /* Introspection used by bench.py for the roofline line: kernel launches issued
  * by this library since load, and the launch geometry of the last batch call. */
 int64_t fccqp_kernel_launch_count(void);
