@@ -39,7 +39,7 @@ def pybind_target() -> str:
 
 
 def build_cuda(force=False, verbose=False, extra=()):
-    srcs = [os.path.join(CSRC, f) for f in ("fccqp_capi.cu", "fccqp_kernel.cuh", "fccqp_struct.cuh", "fccqp_warp.cuh")] + \
+    srcs = [os.path.join(CSRC, f) for f in ("fccqp_capi.cu", "fccqp_kernel.cuh", "fccqp_struct.cuh", "fccqp_warp.cuh", "fccqp_polish.cuh")] + \
            [os.path.join(ROOT, "include", "fccqp.h")]
     if force or _stale(LIB, srcs):
         nvcc = os.environ.get("NVCC", "nvcc")
