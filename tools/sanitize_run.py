@@ -41,3 +41,12 @@ if qp.n + qp.m <= 32:
     s4.set_warm_start(True)
     s4.Solve(qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)
     print("fp32", shape, "QPs", qp.batch, np.unique(s4.GetSolution().details.n_iter, return_counts=True)[1][:3])
+# opt-in solution polish (device path: prepare kernel, inner eq-only solve, finish kernel)
+if os.environ.get("SAN_POLISH"):
+    import torch
+    dev = torch.device("cuda:0")
+    targs = [torch.as_tensor(a, device=dev) for a in (qp.Q, qp.b, qp.A_eq, qp.b_eq, qp.friction_coeffs, qp.lb, qp.ub)]
+    s5 = FCCQPBatch(qp.n, qp.m, qp.nc, qp.lambda_c_start); s5.set_options(FCCQPOptionsB(100, 5e-5, 1e-6, 1e-6))
+    s5.Solve(*targs)
+    pz = s5.Polish(); torch.cuda.synchronize()
+    print("polish", shape, "QPs", qp.batch, "accepted", int(pz.details.polished.sum()))
