@@ -262,7 +262,7 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, int 
   static const int fui = getenv("FCCQP_FIRST_UPDATE_IDENTITY") ? atoi(getenv("FCCQP_FIRST_UPDATE_IDENTITY")) : 1;
   p.first_update_identity = fui != 0;
   // developer switch: ADMM iteration at which long-running QPs complete inv(L) (huge value = never)
-  static const int fia = getenv("FCCQP_FULL_INVERSE_AT") ? atoi(getenv("FCCQP_FULL_INVERSE_AT")) : 8;
+  static const int fia = getenv("FCCQP_FULL_INVERSE_AT") ? atoi(getenv("FCCQP_FULL_INVERSE_AT")) : 6;   // (8 until the compact operator loop; sweep: profiles/r02_full_inverse_at_sweep.log)
   p.full_inverse_at = fia < 1 ? 1 : fia;
   // iterative refinement of the reduced cold pre-solve: FCCQP_STRUCTURE_REFINE of the caller (developer override
   // FCCQP_STRUCT_REFINE=0/1, read per call)
@@ -272,6 +272,7 @@ int launch_solve(DeviceCtx& ctx, fccqp::SolveParams p, cudaStream_t stream, int 
   // problem-size-specialised mapping: a QP whose KKT matrix fits one row per lane goes to the warp-per-QP kernel
   // (FCCQP_NO_WARP=1: the CTA-per-QP kernels, for A/B tests)
   const bool lpt_hint = hint_in && hint_in->lpt;
+  if (p.n + p.m <= 32 && !getenv("FCCQP_FULL_INVERSE_AT")) p.full_inverse_at = 8;   // the warp kernel keeps its own (tuned) switch point
   if (!f32 && p.n + p.m <= 32 && !getenv("FCCQP_NO_WARP")) return launch_warp(ctx, p, stream, false, lpt_hint);
   if (precision == FCCQP_PRECISION_FP32 && p.n + p.m <= 32) return launch_warp(ctx, p, stream, true, lpt_hint);
   auto occupancy_of = [&](KernelFn f, int thr, size_t sm, int* out) -> int {

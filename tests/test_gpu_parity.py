@@ -254,7 +254,7 @@ def test_full_size_properties(walking_log):
 
 @pytest.mark.parametrize("switch_at", ["1", "1000000"])
 def test_long_running_path_switch_point(switch_at, tmp_path):
-    """Long-running QPs switch to the G = [K^-1]_xx operator after FCCQP_FULL_INVERSE_AT iterations (default 8).  Both
+    """Long-running QPs switch to the G = [K^-1]_xx operator after FCCQP_FULL_INVERSE_AT iterations (default 6; 8 on the warp kernel).  Both
     extremes -- every iterating QP on the operator path from its first real x-update, and the
     path never taken -- must meet the same parity bar on every shape (128- and 256-thread kernels,
     NB = 11 ... 24 tile rows).  The switch is read once per process, hence the subprocess."""
