@@ -188,3 +188,32 @@ def test_pybind_batch_class_is_bound_and_has_no_cpu_path():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             s.Solve(np.zeros((2, 6, 6)), np.zeros((2, 6)), np.zeros((2, 3, 6)), np.zeros((2, 3)), np.zeros(0), np.zeros(6), np.zeros(6))
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The ctypes mirrors of the C-ABI descriptors (fcc_qp_b200/_native.py) against what a C compiler makes of include/fccqp.h:
+    sizes and the offsets of the last members."""
+    import subprocess
+    import ctypes as C
+    from fcc_qp_b200 import _native as nat
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "fccqp.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(fccqp_options), sizeof(fccqp_details), sizeof(fccqp_batch_desc),
+         offsetof(fccqp_batch_desc, struct_caps), sizeof(fccqp_wbc_desc), sizeof(fccqp_polish_desc),
+         offsetof(fccqp_polish_desc, polished), offsetof(fccqp_polish_desc, eps_objective));
+  printf("%d %d %d %d %d\n", FCCQP_ABI_VERSION, FCCQP_PRECISION_FP32, FCCQP_STRUCTURE_REFINE, FCCQP_SCHEDULE_LPT, FCCQP_STATUS_NUMERICAL_ISSUE);
+  return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    l1, l2 = subprocess.check_output([str(exe)], text=True).splitlines()
+    got = [int(v) for v in l1.split()]
+    want = [C.sizeof(nat.Options), C.sizeof(nat.Details), C.sizeof(nat.BatchDesc), nat.BatchDesc.struct_caps.offset,
+            C.sizeof(nat.WbcDesc), C.sizeof(nat.PolishDesc), nat.PolishDesc.polished.offset, nat.PolishDesc.eps_objective.offset]
+    assert got == want, (got, want)
+    assert [int(v) for v in l2.split()] == [nat.ABI_VERSION, 2, nat.STRUCTURE_REFINE, nat.SCHEDULE_LPT, nat.STATUS_NUMERICAL_ISSUE]
